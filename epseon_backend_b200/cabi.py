@@ -1,0 +1,210 @@
+"""ctypes binding of the C ABI declared in ``include/epseon_cuda.h``.
+
+This is the call path tests and ``bench.py`` use to reach the CUDA hot path
+"through the C ABI".  It loads ``lib/libepseon_cuda.so`` and nothing else: no
+oracle, no CPU fallback -- a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libepseon_cuda.so"
+
+EPS_OK = 0
+ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EPS_ERR_STATE",
+             5: "EPS_ERR_NOMEM"}
+
+# every symbol include/epseon_cuda.h declares
+SYMBOLS = [
+    "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
+    "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
+    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_timer_start", "eps_timer_stop",
+    "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
+]
+
+
+class EpsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class DeviceProps(C.Structure):
+    _fields_ = [("name", C.c_char * 256), ("ordinal", C.c_int32), ("cc_major", C.c_int32),
+                ("cc_minor", C.c_int32), ("sm_count", C.c_int32), ("clock_khz", C.c_int32),
+                ("driver_version", C.c_int32), ("runtime_version", C.c_int32),
+                ("pci_domain", C.c_int32), ("pci_bus", C.c_int32), ("pci_device", C.c_int32),
+                ("integrated", C.c_int32), ("max_threads_per_block", C.c_int32),
+                ("max_grid", C.c_int32 * 3), ("max_block", C.c_int32 * 3), ("l2_bytes", C.c_int32),
+                ("total_global_mem", C.c_uint64), ("shared_mem_per_block_optin", C.c_uint64),
+                ("shared_mem_per_sm", C.c_uint64), ("uuid", C.c_uint8 * 16)]
+
+
+class CurveInfo(C.Structure):
+    _fields_ = [("i0", C.c_uint32), ("n_steps", C.c_uint32), ("scale", C.c_double),
+                ("v_min", C.c_double), ("v_last", C.c_double)]
+
+
+class SolveParams(C.Structure):
+    _fields_ = [("v_min", C.c_uint32), ("v_max", C.c_uint32), ("n_coarse", C.c_uint32),
+                ("refine_points", C.c_uint32), ("max_rounds", C.c_uint32), ("reserved", C.c_uint32),
+                ("rel_tol", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("sweep_launches", C.c_uint64), ("other_launches", C.c_uint64),
+                ("grid_steps", C.c_uint64), ("sweep_ms", C.c_double), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libepseon_cuda.so (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() -- there is no "
+                               "CPU fallback for the hot path")
+        lib = C.CDLL(str(LIB_PATH))
+        lib.eps_last_error.restype = C.c_char_p
+        lib.eps_last_error.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _ptr(a, dtype):
+    if a is None:
+        return None
+    assert a.dtype == dtype and a.flags.c_contiguous, (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = load().eps_device_count(C.byref(n))
+    if rc != EPS_OK:
+        raise EpsError(rc, (load().eps_last_error(None) or b"").decode())
+    return n.value
+
+
+def device_props(dev: int) -> DeviceProps:
+    p = DeviceProps()
+    rc = load().eps_device_get_props(dev, C.byref(p))
+    if rc != EPS_OK:
+        raise EpsError(rc, (load().eps_last_error(None) or b"").decode())
+    return p
+
+
+def _vec(x, n):
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
+
+
+class Context:
+    """One ``eps_ctx`` (one CUDA device, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.eps_ctx_create(device, C.byref(self.h))
+        if rc != EPS_OK:
+            raise EpsError(rc, (self.lib.eps_last_error(None) or b"").decode())
+        self.n_curves = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eps_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != EPS_OK:
+            raise EpsError(rc, (self.lib.eps_last_error(self.h) or b"").decode())
+
+    def sync(self):
+        self._ck(self.lib.eps_sync(self.h))
+
+    def set_potentials(self, V: np.ndarray, scale) -> None:
+        V = np.ascontiguousarray(np.atleast_2d(V), dtype=np.float64)
+        scale = _vec(scale, V.shape[0])
+        self._ck(self.lib.eps_set_potentials(self.h, _ptr(V, np.float64), C.c_uint32(V.shape[0]),
+                                             C.c_uint32(V.shape[1]), _ptr(scale, np.float64)))
+        self.n_curves = V.shape[0]
+
+    def curve_info(self, curve: int = 0) -> CurveInfo:
+        ci = CurveInfo()
+        self._ck(self.lib.eps_get_curve_info(self.h, C.c_uint32(curve), C.byref(ci)))
+        return ci
+
+    def _outs(self, nE, nodes, tails):
+        shape = (self.n_curves, nE)
+        n = np.empty(shape, dtype=np.uint32) if nodes else None
+        m = np.empty(shape, dtype=np.float64) if tails else None
+        x = np.empty(shape, dtype=np.int32) if tails else None
+        return n, m, x
+
+    def sweep(self, E: np.ndarray, nodes: bool = True, tails: bool = True):
+        E = np.ascontiguousarray(np.atleast_2d(E), dtype=np.float64)
+        assert E.shape[0] == self.n_curves
+        n, m, x = self._outs(E.shape[1], nodes, tails)
+        self._ck(self.lib.eps_sweep(self.h, _ptr(E, np.float64), C.c_uint64(E.shape[1]),
+                                    _ptr(n, np.uint32), _ptr(m, np.float64), _ptr(x, np.int32)))
+        return n, m, x
+
+    def sweep_uniform(self, E_lo, E_hi, nE: int, nodes: bool = True, tails: bool = True):
+        lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
+        n, m, x = self._outs(nE, nodes, tails)
+        self._ck(self.lib.eps_sweep_uniform(self.h, _ptr(lo, np.float64), _ptr(hi, np.float64),
+                                            C.c_uint64(nE), _ptr(n, np.uint32), _ptr(m, np.float64),
+                                            _ptr(x, np.int32)))
+        return n, m, x
+
+    def solve_levels(self, E_lo, E_hi, n_coarse: int, v_min: int, v_max: int, refine_points: int,
+                     rel_tol: float = 1e-12, max_rounds: int = 8):
+        """-> (levels[nC, nlev], widths[nC, nlev], n_below[nC])"""
+        lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
+        nlev = v_max - v_min + 1
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        levels = np.empty((self.n_curves, nlev), dtype=np.float64)
+        widths = np.empty((self.n_curves, nlev), dtype=np.float64)
+        nb = np.empty(self.n_curves, dtype=np.uint32)
+        self._ck(self.lib.eps_solve_levels(self.h, C.byref(p), _ptr(lo, np.float64),
+                                           _ptr(hi, np.float64), _ptr(levels, np.float64),
+                                           _ptr(widths, np.float64), _ptr(nb, np.uint32)))
+        return levels, widths, nb
+
+    def timer_start(self):
+        self._ck(self.lib.eps_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.eps_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._ck(self.lib.eps_stats_get(self.h, C.byref(s)))
+        return s
+
+    def stats_reset(self):
+        self._ck(self.lib.eps_stats_reset(self.h))
+
+    def l2_flush(self):
+        self._ck(self.lib.eps_l2_flush(self.h))
+
+    def fp64_probe(self):
+        t, ms = C.c_double(), C.c_float()
+        self._ck(self.lib.eps_fp64_probe(self.h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value

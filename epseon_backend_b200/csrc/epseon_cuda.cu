@@ -1,0 +1,588 @@
+// epseon_cuda.cu -- C ABI (include/epseon_cuda.h) over the sm_100a kernels.
+//
+// Host side of the hot path that replaces the Vulkan body of
+// VibwaAlgorithm<FP>::run (cpp/gpu/include/epseon/gpu/algorithms/vibwa.hpp:605-637):
+// logical device -> eps_ctx (stream + device buffers), VMA staging/device/output
+// buffer triplets (vibwa.hpp:57-234) -> one resident coefficient table per curve
+// plus node/tail/level output buffers, descriptor sets -> kernel arguments.
+// No CPU fallback: every compute entry point fails with EPS_ERR_CUDA when the
+// CUDA runtime cannot provide the device.
+#include "../../include/epseon_cuda.h"
+#include "numerov_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace eps;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+constexpr double kTMax       = 0.5;  // window rule / validity bound on |q - e|
+constexpr size_t kFlushBytes = 256u << 20;
+constexpr int    kEventPairs = 64;
+
+template <typename T>
+struct DevBuf {
+    T*     p   = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p   = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct eps_ctx {
+    int          dev      = -1;
+    int          sm_count = 0;
+    cudaStream_t stream   = nullptr;
+    std::string  err;
+
+    // resident potentials
+    uint32_t                    nC = 0, N = 0;
+    uint64_t                    slot = 0;  // double2 per curve
+    DevBuf<double2>             d_AB;
+    DevBuf<CurveDev>            d_curves;
+    std::vector<eps_curve_info> curves;
+
+    // sweep buffers
+    DevBuf<Job>      d_jobs, d_jobs_ref;
+    DevBuf<double>   d_E, d_mant, d_Elo, d_Ehi;
+    DevBuf<uint32_t> d_nodes;
+    DevBuf<int32_t>  d_exp;
+    unsigned long long* d_steps = nullptr;
+
+    // level-search state
+    DevBuf<double>   d_lo, d_hi, d_levels, d_widths;
+    DevBuf<uint32_t> d_state, d_jstar, d_nbelow, d_nactive;
+    uint32_t*        h_pinned = nullptr;  // small pinned scratch (readbacks)
+
+    // measurement
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev[kEventPairs][2];
+    int         ev_used = 0;
+    eps_stats   stats{};
+    void*       d_flush = nullptr;
+};
+
+namespace {
+
+int fail(eps_ctx* ctx, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define EPS_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail(ctx, EPS_ERR_CUDA,                                               \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+#define EPS_REQUIRE(ctx, cond, code, msg) \
+    do {                                  \
+        if (!(cond)) return fail(ctx, code, msg); \
+    } while (0)
+
+int bind(eps_ctx* ctx) {
+    if (!ctx) return fail(nullptr, EPS_ERR_INVALID, "null context");
+    EPS_CUDA(ctx, cudaSetDevice(ctx->dev));
+    return EPS_OK;
+}
+
+// Fold finished sweep event pairs into stats.sweep_ms (synchronises the stream).
+int fold_events(eps_ctx* ctx) {
+    if (ctx->ev_used == 0) return EPS_OK;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->ev_used; i++) {
+        float ms = 0.f;
+        EPS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]));
+        ctx->stats.sweep_ms += ms;
+    }
+    ctx->ev_used = 0;
+    return EPS_OK;
+}
+
+size_t sweep_smem_bytes() { return sizeof(double2) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
+
+// Launch the sweep over n_jobs rows of nE energies each (jobs already on device).
+int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
+                 bool tails) {
+    const uint64_t chunks = (static_cast<uint64_t>(nE) + kEnergiesPerCta - 1) / kEnergiesPerCta;
+    const uint64_t grid   = chunks * n_jobs;
+    EPS_REQUIRE(ctx, grid > 0 && grid < (1ull << 31), EPS_ERR_INVALID, "sweep grid out of range");
+    const size_t n_out = static_cast<size_t>(n_jobs) * nE;
+    EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
+    if (tails) {
+        EPS_CUDA(ctx, ctx->d_mant.reserve(n_out));
+        EPS_CUDA(ctx, ctx->d_exp.reserve(n_out));
+    }
+    if (ctx->ev_used == kEventPairs) {
+        int rc = fold_events(ctx);
+        if (rc) return rc;
+    }
+    cudaEvent_t* pair = ctx->ev[ctx->ev_used++];
+    EPS_CUDA(ctx, cudaEventRecord(pair[0], ctx->stream));
+    const size_t smem = sweep_smem_bytes();
+    if (tails)
+        numerov_sweep_kernel<true><<<static_cast<unsigned>(grid), kSweepThreads, smem, ctx->stream>>>(
+            ctx->d_AB.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE,
+            ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p, ctx->d_steps);
+    else
+        numerov_sweep_kernel<false><<<static_cast<unsigned>(grid), kSweepThreads, smem, ctx->stream>>>(
+            ctx->d_AB.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE,
+            ctx->d_nodes.p, nullptr, nullptr, ctx->d_steps);
+    EPS_CUDA(ctx, cudaGetLastError());
+    EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
+    ctx->stats.sweep_launches++;
+    return EPS_OK;
+}
+
+// Validity of a trial-energy range on a curve: |s (E - V_min)| <= T_MAX keeps every
+// f_i = 1 - (q_i - e) positive inside the window (Sturm property, bounded growth).
+bool range_ok(const eps_curve_info& ci, double E_a, double E_b) {
+    const double a = ci.scale * (E_a - ci.v_min), b = ci.scale * (E_b - ci.v_min);
+    return std::isfinite(a) && std::isfinite(b) && std::fabs(a) <= kTMax && std::fabs(b) <= kTMax;
+}
+
+int fetch_sweep(eps_ctx* ctx, size_t n, uint32_t* nodes, double* mant, int32_t* expo) {
+    if (nodes) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(nodes, ctx->d_nodes.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += n * sizeof(uint32_t);
+    }
+    if (mant) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(mant, ctx->d_mant.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += n * sizeof(double);
+    }
+    if (expo) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(expo, ctx->d_exp.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += n * sizeof(int32_t);
+    }
+    if (nodes || mant || expo) EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eps_abi_version(void) { return EPS_ABI_VERSION; }
+
+const char* eps_last_error(const eps_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int eps_device_count(int* count) {
+    if (!count) return fail(nullptr, EPS_ERR_INVALID, "count is null");
+    *count = 0;
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, EPS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return EPS_OK;
+}
+
+int eps_device_get_props(int device, eps_device_props* out) {
+    if (!out) return fail(nullptr, EPS_ERR_INVALID, "out is null");
+    cudaDeviceProp p;
+    EPS_CUDA(nullptr, cudaGetDeviceProperties(&p, device));
+    std::memset(out, 0, sizeof(*out));
+    std::snprintf(out->name, sizeof(out->name), "%s", p.name);
+    out->ordinal  = device;
+    out->cc_major = p.major;
+    out->cc_minor = p.minor;
+    out->sm_count = p.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    out->clock_khz = khz;
+    cudaDriverGetVersion(&out->driver_version);
+    cudaRuntimeGetVersion(&out->runtime_version);
+    out->pci_domain            = p.pciDomainID;
+    out->pci_bus               = p.pciBusID;
+    out->pci_device            = p.pciDeviceID;
+    out->integrated            = p.integrated;
+    out->max_threads_per_block = p.maxThreadsPerBlock;
+    for (int i = 0; i < 3; i++) {
+        out->max_grid[i]  = p.maxGridSize[i];
+        out->max_block[i] = p.maxThreadsDim[i];
+    }
+    out->l2_bytes                   = p.l2CacheSize;
+    out->total_global_mem           = p.totalGlobalMem;
+    out->shared_mem_per_block_optin = p.sharedMemPerBlockOptin;
+    out->shared_mem_per_sm          = p.sharedMemPerMultiprocessor;
+    std::memcpy(out->uuid, p.uuid.bytes, 16);
+    return EPS_OK;
+}
+
+int eps_ctx_create(int device, eps_ctx** out) {
+    if (!out) return fail(nullptr, EPS_ERR_INVALID, "out is null");
+    *out  = nullptr;
+    int n = 0, rc = eps_device_count(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) return fail(nullptr, EPS_ERR_INVALID, "no such CUDA device");
+    eps_ctx* ctx = new (std::nothrow) eps_ctx();
+    if (!ctx) return fail(nullptr, EPS_ERR_NOMEM, "out of host memory");
+    ctx->dev = device;
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+        eps_ctx_destroy(ctx);
+        return fail(nullptr, EPS_ERR_CUDA, m);
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    int cc_major = 0;
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cc_major < 10) {
+        eps_ctx_destroy(ctx);
+        return fail(nullptr, EPS_ERR_CUDA, "device is not sm_100-class (kernels are built for sm_100a only)");
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (auto& pr : ctx->ev)
+        for (auto& evt : pr)
+            if ((e = cudaEventCreate(&evt)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_steps), sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), 4096)) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaFuncSetAttribute(numerov_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()))) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    if ((e = cudaFuncSetAttribute(numerov_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()))) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    *out = ctx;
+    return EPS_OK;
+}
+
+int eps_ctx_destroy(eps_ctx* ctx) {
+    if (!ctx) return EPS_OK;
+    if (ctx->dev >= 0 && cudaSetDevice(ctx->dev) == cudaSuccess) {
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        ctx->d_AB.release();
+        ctx->d_curves.release();
+        ctx->d_jobs.release();
+        ctx->d_jobs_ref.release();
+        ctx->d_E.release();
+        ctx->d_mant.release();
+        ctx->d_Elo.release();
+        ctx->d_Ehi.release();
+        ctx->d_nodes.release();
+        ctx->d_exp.release();
+        ctx->d_lo.release();
+        ctx->d_hi.release();
+        ctx->d_levels.release();
+        ctx->d_widths.release();
+        ctx->d_state.release();
+        ctx->d_jstar.release();
+        ctx->d_nbelow.release();
+        ctx->d_nactive.release();
+        if (ctx->d_steps) cudaFree(ctx->d_steps);
+        if (ctx->d_flush) cudaFree(ctx->d_flush);
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        if (ctx->t0) cudaEventDestroy(ctx->t0);
+        if (ctx->t1) cudaEventDestroy(ctx->t1);
+        for (auto& pr : ctx->ev)
+            for (auto& evt : pr)
+                if (evt) cudaEventDestroy(evt);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return EPS_OK;
+}
+
+int eps_sync(eps_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPS_OK;
+}
+
+// Preparation (spec DESIGN.md section 3.2, oracle orc_prep): q = s V, window
+// [i0, iend] around the minimum with q - q_min <= T_MAX, A = 2 + 10 q, B = 1 - q.
+int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
+                       const double* scale) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, V && scale, EPS_ERR_INVALID, "V/scale is null");
+    EPS_REQUIRE(ctx, n_curves >= 1 && n_points >= 3, EPS_ERR_INVALID, "need >=1 curve of >=3 points");
+    const uint32_t N    = n_points;
+    const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
+    std::vector<double2>        ab(static_cast<size_t>(slot) * n_curves, make_double2(2.0, 1.0));
+    std::vector<CurveDev>       cds(n_curves);
+    std::vector<eps_curve_info> infos(n_curves);
+    for (uint32_t c = 0; c < n_curves; c++) {
+        const double* v = V + static_cast<size_t>(c) * N;
+        const double  s = scale[c];
+        EPS_REQUIRE(ctx, std::isfinite(s) && s > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < N; i++) {
+            EPS_REQUIRE(ctx, std::isfinite(v[i]), EPS_ERR_RANGE, "potential table holds a non-finite value");
+            if (s * v[i] < s * v[m]) m = i;
+        }
+        const double qmin = s * v[m];
+        const double thr  = qmin + kTMax;
+        uint32_t     ilo  = 0;
+        for (uint32_t j = 0; j < m; j++)
+            if (s * v[j] > thr) ilo = j + 1;
+        uint32_t ihi = N - 1;
+        for (uint32_t j = N - 1; j > m; j--)
+            if (s * v[j] > thr) ihi = j - 1;
+        const uint32_t i0   = ilo < 1 ? 1 : ilo;
+        const uint32_t iend = (ihi + 1 < N - 1) ? ihi + 1 : N - 1;
+        EPS_REQUIRE(ctx, iend >= i0 + 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
+        const uint32_t n   = iend - i0;
+        double2*       dst = ab.data() + static_cast<size_t>(c) * slot;
+        for (uint32_t k = 0; k < n; k++) {
+            const double q = s * v[i0 + k];
+            dst[k].x       = 2.0 + 10.0 * q;
+            dst[k].y       = 1.0 - q;
+        }
+        cds[c]   = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, v[m]};
+        infos[c] = eps_curve_info{i0, n, s, v[m], v[N - 1]};
+    }
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EPS_CUDA(ctx, ctx->d_AB.reserve(ab.size()));
+    EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_AB.p, ab.data(), ab.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_curves.p, cds.data(), cds.size() * sizeof(CurveDev), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += ab.size() * sizeof(double2) + cds.size() * sizeof(CurveDev);
+    ctx->nC     = n_curves;
+    ctx->N      = N;
+    ctx->slot   = slot;
+    ctx->curves = std::move(infos);
+    return EPS_OK;
+}
+
+int eps_get_curve_info(eps_ctx* ctx, uint32_t curve, eps_curve_info* out) {
+    if (!ctx) return fail(nullptr, EPS_ERR_INVALID, "null context");
+    EPS_REQUIRE(ctx, out, EPS_ERR_INVALID, "out is null");
+    EPS_REQUIRE(ctx, curve < ctx->nC, EPS_ERR_INVALID, "no such curve");
+    *out = ctx->curves[curve];
+    return EPS_OK;
+}
+
+int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* nodes, double* tail_mant,
+              int32_t* tail_exp) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
+    EPS_REQUIRE(ctx, E && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
+    const uint32_t nE = static_cast<uint32_t>(n_energies);
+    std::vector<Job> jobs(ctx->nC);
+    for (uint32_t c = 0; c < ctx->nC; c++) {
+        const double* row = E + static_cast<size_t>(c) * nE;
+        double        mn = row[0], mx = row[0];
+        for (uint32_t j = 1; j < nE; j++) {
+            mn = std::min(mn, row[j]);
+            mx = std::max(mx, row[j]);
+        }
+        bool finite = true;
+        for (uint32_t j = 0; j < nE && finite; j++) finite = std::isfinite(row[j]);
+        EPS_REQUIRE(ctx, finite && range_ok(ctx->curves[c], mn, mx), EPS_ERR_RANGE,
+                    "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+        jobs[c] = Job{0.0, 0.0, static_cast<uint64_t>(c) * nE, c, 0, nE, 0, c, 0};
+    }
+    const size_t n = static_cast<size_t>(ctx->nC) * nE;
+    EPS_CUDA(ctx, ctx->d_E.reserve(n));
+    EPS_CUDA(ctx, ctx->d_jobs.reserve(ctx->nC));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_E.p, E, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(double) + jobs.size() * sizeof(Job);
+    // jobs lives on the host stack of this call: make sure the copy is done before returning
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, ctx->d_E.p, tail_mant || tail_exp)) return rc;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return fetch_sweep(ctx, n, nodes, tail_mant, tail_exp);
+}
+
+int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint64_t n_energies,
+                      uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
+    EPS_REQUIRE(ctx, E_lo && E_hi && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
+    const uint32_t nE = static_cast<uint32_t>(n_energies);
+    for (uint32_t c = 0; c < ctx->nC; c++)
+        EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
+                    "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+    EPS_CUDA(ctx, ctx->d_Elo.reserve(ctx->nC));
+    EPS_CUDA(ctx, ctx->d_Ehi.reserve(ctx->nC));
+    EPS_CUDA(ctx, ctx->d_jobs.reserve(ctx->nC));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Elo.p, E_lo, ctx->nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Ehi.p, E_hi, ctx->nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += 2ull * ctx->nC * sizeof(double);
+    make_coarse_jobs_kernel<<<(ctx->nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, ctx->nC, nE, ctx->d_jobs.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    // E_lo/E_hi are pageable host memory: the async copies above are staged before return
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, nullptr, tail_mant || tail_exp)) return rc;
+    return fetch_sweep(ctx, static_cast<size_t>(ctx->nC) * nE, nodes, tail_mant, tail_exp);
+}
+
+int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo, const double* E_hi,
+                     double* levels, double* widths, uint32_t* n_below) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
+    EPS_REQUIRE(ctx, p && E_lo && E_hi && levels, EPS_ERR_INVALID, "null argument");
+    EPS_REQUIRE(ctx, p->v_max >= p->v_min, EPS_ERR_INVALID, "v_max < v_min");
+    EPS_REQUIRE(ctx, p->n_coarse >= 2 && p->refine_points >= 1, EPS_ERR_INVALID, "n_coarse >= 2 and refine_points >= 1 required");
+    const uint32_t nC = ctx->nC, nlev = p->v_max - p->v_min + 1, M = p->refine_points;
+    const uint64_t total64 = static_cast<uint64_t>(nC) * nlev;
+    EPS_REQUIRE(ctx, total64 < (1ull << 31), EPS_ERR_INVALID, "too many (curve, level) pairs");
+    const uint32_t total = static_cast<uint32_t>(total64);
+    for (uint32_t c = 0; c < nC; c++) {
+        EPS_REQUIRE(ctx, E_hi[c] >= E_lo[c], EPS_ERR_INVALID, "E_hi < E_lo");
+        EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
+                    "search range outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+    }
+    EPS_CUDA(ctx, ctx->d_Elo.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_Ehi.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_jobs.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(total));
+    EPS_CUDA(ctx, ctx->d_lo.reserve(total));
+    EPS_CUDA(ctx, ctx->d_hi.reserve(total));
+    EPS_CUDA(ctx, ctx->d_levels.reserve(total));
+    EPS_CUDA(ctx, ctx->d_widths.reserve(total));
+    EPS_CUDA(ctx, ctx->d_state.reserve(total));
+    EPS_CUDA(ctx, ctx->d_jstar.reserve(total));
+    EPS_CUDA(ctx, ctx->d_nbelow.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_nactive.reserve(1));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Elo.p, E_lo, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Ehi.p, E_hi, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += 2ull * nC * sizeof(double);
+
+    // ---- coarse sweep + bracketing ----
+    const uint32_t nE = p->n_coarse;
+    make_coarse_jobs_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, nC, nE, ctx->d_jobs.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false)) return rc;
+    EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, total * sizeof(uint32_t), ctx->stream));
+    {
+        const uint32_t bpr = (nE + 255) / 256;
+        crossing_kernel<<<bpr * nC, 256, 0, ctx->stream>>>(ctx->d_nodes.p, nE, nE, bpr, ctx->d_jobs.p, 1, p->v_min, nlev, ctx->d_jstar.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        bracket_init_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_nodes.p, nE, ctx->d_jobs.p, ctx->d_jstar.p, nC, p->v_min, nlev,
+                                                                         ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, ctx->d_nbelow.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches += 3;
+    }
+    // ---- k-section refinement rounds ----
+    for (uint32_t round = 0; round < p->max_rounds; round++) {
+        check_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
+                                                          ctx->d_jobs_ref.p, ctx->d_nactive.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches++;
+        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += sizeof(uint32_t);
+        const uint32_t n_active = ctx->h_pinned[0];
+        if (n_active == 0) break;
+        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false)) return rc;
+        EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_active * sizeof(uint32_t), ctx->stream));
+        const uint32_t bpr = (M + 255) / 256;
+        crossing_kernel<<<bpr * n_active, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        bracket_update_kernel<<<(n_active + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_jobs_ref.p, ctx->d_jstar.p, n_active, M, ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches += 2;
+    }
+    finalize_levels_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, total, ctx->d_levels.p, ctx->d_widths.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    EPS_CUDA(ctx, cudaMemcpyAsync(levels, ctx->d_levels.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += total * sizeof(double);
+    if (widths) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(widths, ctx->d_widths.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += total * sizeof(double);
+    }
+    if (n_below) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(n_below, ctx->d_nbelow.p, nC * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += nC * sizeof(uint32_t);
+    }
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPS_OK;
+}
+
+int eps_timer_start(eps_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+    return EPS_OK;
+}
+
+int eps_timer_stop(eps_ctx* ctx, float* ms) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ms, EPS_ERR_INVALID, "ms is null");
+    EPS_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+    EPS_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    EPS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return EPS_OK;
+}
+
+int eps_stats_get(eps_ctx* ctx, eps_stats* out) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, out, EPS_ERR_INVALID, "out is null");
+    if (int rc = fold_events(ctx)) return rc;
+    unsigned long long steps = 0;
+    EPS_CUDA(ctx, cudaMemcpyAsync(&steps, ctx->d_steps, sizeof(steps), cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.grid_steps = steps;
+    *out                  = ctx->stats;
+    return EPS_OK;
+}
+
+int eps_stats_reset(eps_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    if (int rc = fold_events(ctx)) return rc;
+    EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats = eps_stats{};
+    return EPS_OK;
+}
+
+int eps_l2_flush(eps_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    if (!ctx->d_flush) EPS_CUDA(ctx, cudaMalloc(&ctx->d_flush, kFlushBytes));
+    EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_flush, 0x5a, kFlushBytes, ctx->stream));
+    return EPS_OK;
+}
+
+int eps_fp64_probe(eps_ctx* ctx, double* tflops, float* ms_out) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, tflops, EPS_ERR_INVALID, "tflops is null");
+    const int    blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 13;
+    DevBuf<double> out;
+    EPS_CUDA(ctx, out.reserve(static_cast<size_t>(blocks) * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        EPS_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+        fp64_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, iters, 1.0000001, 1e-9);
+        EPS_CUDA(ctx, cudaGetLastError());
+        EPS_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+        EPS_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+        float ms = 0.f;
+        EPS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    out.release();
+    const double flops = 2.0 * 64.0 * iters * static_cast<double>(blocks) * threads;
+    *tflops            = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return EPS_OK;
+}
+
+}  // extern "C"

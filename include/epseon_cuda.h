@@ -1,0 +1,156 @@
+/*
+ * epseon_cuda.h -- C ABI of the B200-native Numerov hot path (libepseon_cuda.so).
+ *
+ * This is the drop-in boundary under the reference's algorithm slot
+ *     virtual void Algorithm<FP>::run(const std::stop_token&, TaskHandle<FP>*)
+ *         (cpp/gpu/include/epseon/gpu/algorithms/algorithm.hpp:34)
+ * as implemented by VibwaAlgorithm<FP>::run
+ *         (cpp/gpu/include/epseon/gpu/algorithms/vibwa.hpp:605-637),
+ * whose Vulkan logical-device / VMA / descriptor-set body it replaces.  The
+ * reference has no FFI of its own for this path (the slot does no arithmetic);
+ * the entry points below are what that slot binds instead.  Each one cites the
+ * reference interface it stands in for.  Plain C: pointers and sizes only, no
+ * C++/torch/Python types, no exceptions across the boundary.
+ *
+ * Conventions
+ *   - every call returns an int status (EPS_OK == 0); the text of the last
+ *     failure is eps_last_error(ctx) (ctx may be NULL for creation failures);
+ *   - one eps_ctx per CUDA device and per host thread (thread-compatible, like
+ *     the reference's one-jthread-per-TaskHandle model, task_handle.hpp:100);
+ *   - the caller owns every host buffer; the ctx owns every device buffer;
+ *   - work is stream-ordered on the ctx's stream; calls that return data to a
+ *     host buffer synchronise before returning, the others do not
+ *     (eps_sync() waits explicitly);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with EPS_ERR_CUDA.
+ *
+ * Units follow the build's spec: energies in cm^-1,
+ * lengths in Angstrom, masses in amu; `scale` = h^2 * (2 mu / hbar^2) / 12.
+ */
+#ifndef EPSEON_CUDA_H
+#define EPSEON_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPS_ABI_VERSION 1
+
+enum {
+    EPS_OK          = 0,
+    EPS_ERR_INVALID = 1, /* bad argument                                   */
+    EPS_ERR_CUDA    = 2, /* CUDA runtime failure / no device               */
+    EPS_ERR_RANGE   = 3, /* energy or table outside the validity window    */
+    EPS_ERR_STATE   = 4, /* call order (e.g. sweep before set_potentials)  */
+    EPS_ERR_NOMEM   = 5
+};
+
+typedef struct eps_ctx eps_ctx;
+
+/* Device description.  Replaces what the reference reads from
+ * vk::PhysicalDeviceProperties / vk::PhysicalDeviceMemoryProperties
+ * (compute_context.hpp:45-48, compute_context.cpp:94-104). */
+typedef struct eps_device_props {
+    char     name[256];
+    int32_t  ordinal;               /* CUDA ordinal: the unique device_id */
+    int32_t  cc_major, cc_minor;
+    int32_t  sm_count;
+    int32_t  clock_khz;
+    int32_t  driver_version;        /* cudaDriverGetVersion  */
+    int32_t  runtime_version;       /* cudaRuntimeGetVersion */
+    int32_t  pci_domain, pci_bus, pci_device;
+    int32_t  integrated;
+    int32_t  max_threads_per_block;
+    int32_t  max_grid[3];
+    int32_t  max_block[3];
+    int32_t  l2_bytes;
+    uint64_t total_global_mem;
+    uint64_t shared_mem_per_block_optin;
+    uint64_t shared_mem_per_sm;
+    uint8_t  uuid[16];
+} eps_device_props;
+
+/* Per-curve facts computed by eps_set_potentials. */
+typedef struct eps_curve_info {
+    uint32_t i0;       /* first integrated grid index (energy independent)  */
+    uint32_t n_steps;  /* recurrence steps per trial energy                 */
+    double   scale;    /* s: E[cm^-1] -> dimensionless Numerov energy       */
+    double   v_min;    /* minimum of the table                              */
+    double   v_last;   /* last table value (taken as the asymptote)         */
+} eps_curve_info;
+
+/* Level-search parameters.  v_min/v_max are VibwaAlgorithmConfig::min_level /
+ * max_level (algorithm_config.hpp:82-83); level_count = v_max-v_min+1 is the
+ * reference's planned output-buffer length (algorithm_config.hpp:177). */
+typedef struct eps_solve_params {
+    uint32_t v_min, v_max;
+    uint32_t n_coarse;       /* trial energies of the bracketing sweep (per curve)  */
+    uint32_t refine_points;  /* interior trial energies per level per round (M)     */
+    uint32_t max_rounds;
+    uint32_t reserved;
+    double   rel_tol;        /* stop when hi-lo <= rel_tol*max(|lo|,|hi|)           */
+} eps_solve_params;
+
+/* Counters since the last eps_stats_reset(). */
+typedef struct eps_stats {
+    uint64_t sweep_launches;   /* Numerov sweep kernel launches                    */
+    uint64_t other_launches;   /* prep / bracketing / bookkeeping kernel launches  */
+    uint64_t grid_steps;       /* grid-steps x trial-energies executed by sweeps   */
+    double   sweep_ms;         /* summed CUDA-event time of the sweep launches     */
+    uint64_t h2d_bytes, d2h_bytes;
+} eps_stats;
+
+/* ---- devices and contexts (replaces ComputeContext::getPhysicalDevicesInfo /
+ * getDeviceInterface, compute_context.cpp:94-117, and createLogicalDevice,
+ * vibwa.hpp:654-674) ------------------------------------------------------- */
+int         eps_abi_version(void);
+int         eps_device_count(int* count);
+int         eps_device_get_props(int device, eps_device_props* out);
+int         eps_ctx_create(int device, eps_ctx** out);
+int         eps_ctx_destroy(eps_ctx* ctx);
+const char* eps_last_error(const eps_ctx* ctx);
+int         eps_sync(eps_ctx* ctx);
+
+/* ---- potentials (replaces the staging->device upload the reference plans in
+ * ShaderResources, vibwa.hpp:57-234; input is the table that
+ * PotentialSource<FP>::get_potential_data() returns, potential_source.hpp:38)
+ * V: host, n_curves rows of n_points doubles; scale: host, one per curve. */
+int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
+                       const double* scale);
+int eps_get_curve_info(eps_ctx* ctx, uint32_t curve, eps_curve_info* out);
+
+/* ---- Numerov sweep + node count (the missing compute dispatch of
+ * vibwa.hpp:605-637).  Per curve, n_energies trial energies; outputs are host
+ * buffers [n_curves][n_energies] and any of them may be NULL (results then
+ * stay resident on the device).
+ *   eps_sweep:          explicit energies E[n_curves][n_energies] (host).
+ *   eps_sweep_uniform:  E_j = E_lo[c] + j*dE, dE=(E_hi[c]-E_lo[c])/(n-1),
+ *                       generated on the device. */
+int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* nodes,
+              double* tail_mant, int32_t* tail_exp);
+int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint64_t n_energies,
+                      uint32_t* nodes, double* tail_mant, int32_t* tail_exp);
+
+/* ---- bracketing + k-section refinement of levels v_min..v_max of every
+ * resident curve inside [E_lo[c], E_hi[c]].  Outputs (host):
+ *   levels[n_curves][level_count]  (NaN where the level is not in range) --
+ *     the reference's planned output buffer (algorithm_config.hpp:183-190);
+ *   widths[n_curves][level_count]  final bracket widths (may be NULL);
+ *   n_below[n_curves]              levels below E_hi[c]   (may be NULL). */
+int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo,
+                     const double* E_hi, double* levels, double* widths, uint32_t* n_below);
+
+/* ---- measurement helpers (bench.py / tests) ------------------------------- */
+int eps_timer_start(eps_ctx* ctx);
+int eps_timer_stop(eps_ctx* ctx, float* ms);
+int eps_stats_get(eps_ctx* ctx, eps_stats* out);
+int eps_stats_reset(eps_ctx* ctx);
+int eps_l2_flush(eps_ctx* ctx);
+int eps_fp64_probe(eps_ctx* ctx, double* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPSEON_CUDA_H */

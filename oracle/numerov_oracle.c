@@ -1,0 +1,302 @@
+/*
+ * numerov_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may build, load or call this file.  Nothing under
+ * epseon_backend_b200/ links it; the product path fails loudly without its
+ * CUDA library.
+ *
+ * PARITY UNPINNED against the reference: the reference repository
+ * (UniversityOfGdanskTeamPython/epseon_backend @ f2996b0) contains NO
+ * implementation of this path -- VibwaAlgorithm<FP>::run only allocates
+ * buffers (cpp/gpu/include/epseon/gpu/algorithms/vibwa.hpp:605-637),
+ * MorsePotentialGenerator::get_potential_data returns {}
+ * (cpp/gpu/include/epseon/gpu/task_configurator/potential_source.hpp:223-225)
+ * and _libepseon_cpu is a greet() stub (cpp/cpu/source/libcpu.cpp:3-36).
+ * There is no reference arithmetic, golden vector or known-answer test to
+ * follow.  This oracle is therefore the BUILD'S OWN plain-C statement of the
+ * numerical specification in DESIGN.md section 3; it is pinned instead by
+ * independent known answers (tests/test_oracle_pins.py): the analytic Morse
+ * spectrum, the harmonic oscillator, a 50-digit mpmath replay of the same
+ * recurrence (tests/golden/), and scipy's tridiagonal eigen-solver.
+ *
+ * What the reference DOES fix, and what is followed here:
+ *   - the parameter set: MorsePotentialConfig{dissociation_energy,
+ *     equilibrium_bond_distance, well_width, min_r, max_r, point_count}
+ *     (potential_source.hpp:103-183) and VibwaAlgorithmConfig{mass_atom_0,
+ *     mass_atom_1, integration_step, min_distance_to_asymptote, min_level,
+ *     max_level} (algorithm_config.hpp:76-199);
+ *   - the output shape: level_count = max_level - min_level + 1 energies per
+ *     potential curve (algorithm_config.hpp:177,183-190).
+ *
+ * Build (see oracle/Makefile):  gcc -O3 -march=native -ffp-contract=off
+ * [-fopenmp].  Every floating-point operation below is a single IEEE-754
+ * binary64 operation (+, *, or an explicit fma()); -ffp-contract=off keeps
+ * the compiler from fusing anything else, so results are bit-identical to
+ * the CUDA kernels, which use __dadd_rn/__dmul_rn/__fma_rn in the same order.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_HBAR2_OVER_2 16.857629206 /* amu * Angstrom^2 * cm^-1 */
+#define ORC_T_MAX 0.5                 /* window rule: q_i - q_min <= T_MAX */
+#define ORC_RENORM_PERIOD 128u        /* exponent renormalisation period   */
+#define ORC_EB 16                     /* energies marched together (SIMD)  */
+
+static inline uint64_t d2u(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return u;
+}
+static inline double u2d(uint64_t u) {
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* N1. V_i = De * (1 - exp(-a (r_i - re)))^2 on r_i = rmin + i*h,
+ * h = (rmax - rmin)/(N-1).  Fills the slot left empty at
+ * potential_source.hpp:223-225. */
+void orc_morse_tabulate(double De, double re, double a, double rmin, double rmax, uint32_t N,
+                        double* V) {
+    const double h = (rmax - rmin) / (double)(N - 1);
+    for (uint32_t i = 0; i < N; i++) {
+        const double r = rmin + (double)i * h;
+        const double t = 1.0 - exp(-a * (r - re));
+        V[i] = (De * t) * t;
+    }
+}
+
+/* Lennard-Jones 12-6 shifted so that the minimum is 0 and the asymptote De. */
+void orc_lj_tabulate(double De, double re, double rmin, double rmax, uint32_t N, double* V) {
+    const double h = (rmax - rmin) / (double)(N - 1);
+    for (uint32_t i = 0; i < N; i++) {
+        const double r  = rmin + (double)i * h;
+        const double x  = re / r;
+        const double x2 = x * x;
+        const double x6 = (x2 * x2) * x2;
+        V[i] = De * ((x6 * x6 - 2.0 * x6) + 1.0);
+    }
+}
+
+/* s = h^2 * (2 mu / hbar^2) / 12 with mu = m0 m1/(m0+m1): maps an energy in
+ * cm^-1 to the dimensionless Numerov variable.  Masses are
+ * VibwaAlgorithmConfig::mass_atom_{0,1} (algorithm_config.hpp:78-79). */
+double orc_scale(double m0, double m1, double h) {
+    const double mu = (m0 * m1) / (m0 + m1);
+    const double c  = mu / ORC_HBAR2_OVER_2;
+    return ((h * h) * c) / 12.0;
+}
+
+/* Preparation: q_i = s V_i; integration window [i0, iend] around the minimum
+ * on which q_i - q_min <= T_MAX (so f_i = 1 - (q_i - e) > 0 for every
+ * admissible energy: the Sturm-sequence property needs it); coefficient pairs
+ * A_k = 2 + 10 q_{i0+k},  B_k = 1 - q_{i0+k},  k = 0 .. n_steps-1.
+ * AB must hold 2*N doubles (interleaved A,B).  Returns 0, or -1 when the
+ * table is unusable (non-finite values, or fewer than 2 steps). */
+int orc_prep(const double* V, uint32_t N, double s, double* AB, uint32_t* i0_out,
+             uint32_t* n_steps_out, double* vmin_out) {
+    if (N < 3) return -1;
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        if (!isfinite(V[i])) return -1;
+        if (s * V[i] < s * V[m]) m = i;
+    }
+    const double qmin = s * V[m];
+    const double thr  = qmin + ORC_T_MAX;
+    uint32_t     ilo  = 0;
+    for (uint32_t j = 0; j < m; j++)
+        if (s * V[j] > thr) ilo = j + 1;
+    uint32_t ihi = N - 1;
+    for (uint32_t j = N - 1; j > m; j--)
+        if (s * V[j] > thr) ihi = j - 1;
+    const uint32_t i0   = ilo < 1 ? 1 : ilo;
+    const uint32_t iend = (ihi + 1 < N - 1) ? ihi + 1 : N - 1;
+    if (iend < i0 + 2) return -1;
+    const uint32_t n = iend - i0;
+    for (uint32_t k = 0; k < n; k++) {
+        const double q = s * V[i0 + k];
+        AB[2 * k]      = 2.0 + 10.0 * q;
+        AB[2 * k + 1]  = 1.0 - q;
+    }
+    *i0_out      = i0;
+    *n_steps_out = n;
+    *vmin_out    = V[m];
+    return 0;
+}
+
+/* Exponent renormalisation: scale (Y, Yp) by the power of two that brings
+ * |Y| into [1,2); exact, so signs and all later bits are those of the
+ * unscaled recurrence.  Skipped when Y is zero or subnormal. */
+static inline void renorm(double* Y, double* Yp, int32_t* expo) {
+    const uint32_t ex = (uint32_t)(d2u(*Y) >> 52) & 0x7ffu;
+    if (ex != 0) {
+        const double sc = u2d((uint64_t)(2046u - ex) << 52);
+        *Y *= sc;
+        *Yp *= sc;
+        *expo += (int32_t)ex - 1023;
+    }
+}
+
+/* N2 + N3 for a block of up to ORC_EB energies: the division-free Numerov
+ * recurrence  Y_{k+1} = (A_k - 10e) Y_k - ((B_k + e)(B_{k-1} + e)) Y_{k-1}
+ * with Y_{-1}=0, Y_0=1; node = sign-bit flip between consecutive Y. */
+static void sweep_block(const double* AB, uint32_t n_steps, double s, const double* E, int nb,
+                        uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    double   e[ORC_EB], e10[ORC_EB], Y[ORC_EB], Yp[ORC_EB], fp[ORC_EB];
+    int64_t  cnt[ORC_EB];
+    int32_t  ex[ORC_EB];
+    for (int b = 0; b < ORC_EB; b++) {
+        const double Eb = E[b < nb ? b : nb - 1];
+        e[b]   = s * Eb;
+        e10[b] = 10.0 * e[b];
+        Y[b]   = 1.0;
+        Yp[b]  = 0.0;
+        fp[b]  = 1.0;
+        cnt[b] = 0;
+        ex[b]  = 0;
+    }
+    for (uint32_t k = 0; k < n_steps; k++) {
+        const double A = AB[2 * k], B = AB[2 * k + 1];
+#pragma omp simd
+        for (int b = 0; b < ORC_EB; b++) {
+            const double u  = A - e10[b];
+            const double f  = B + e[b];
+            const double g  = f * fp[b];
+            const double t  = g * Yp[b];
+            const double Yn = fma(u, Y[b], -t);
+            cnt[b] += (int64_t)((d2u(Yn) ^ d2u(Y[b])) >> 63);
+            Yp[b] = Y[b];
+            Y[b]  = Yn;
+            fp[b] = f;
+        }
+        if (((k + 1) % ORC_RENORM_PERIOD) == 0)
+            for (int b = 0; b < ORC_EB; b++) renorm(&Y[b], &Yp[b], &ex[b]);
+    }
+    for (int b = 0; b < nb; b++) {
+        renorm(&Y[b], &Yp[b], &ex[b]);
+        if (nodes) nodes[b] = (uint32_t)cnt[b];
+        if (tail_mant) tail_mant[b] = Y[b];
+        if (tail_exp) tail_exp[b] = ex[b];
+    }
+}
+
+/* Sweep explicit energies E[0..nE). Any output pointer may be NULL. */
+void orc_sweep(const double* AB, uint32_t n_steps, double s, const double* E, uint64_t nE,
+               uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < nblk; blk++) {
+        const uint64_t o  = (uint64_t)blk * ORC_EB;
+        const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
+        sweep_block(AB, n_steps, s, E + o, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+                    tail_exp ? tail_exp + o : 0);
+    }
+}
+
+/* Uniform grid E_j = E0 + j*dE, j = j0 .. j0+nE-1 (one multiply, one add). */
+void orc_sweep_uniform(const double* AB, uint32_t n_steps, double s, double E0, double dE,
+                       uint64_t j0, uint64_t nE, uint32_t* nodes, double* tail_mant,
+                       int32_t* tail_exp) {
+    const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < nblk; blk++) {
+        const uint64_t o  = (uint64_t)blk * ORC_EB;
+        const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
+        double         Eb[ORC_EB];
+        for (int b = 0; b < nb; b++) Eb[b] = E0 + (double)(j0 + o + (uint64_t)b) * dE;
+        sweep_block(AB, n_steps, s, Eb, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+                    tail_exp ? tail_exp + o : 0);
+    }
+}
+
+/* N5 + N6.  Locate levels vmin..vmax of one curve in [E_lo, E_hi]:
+ *   coarse:  n_coarse uniform energies, E_j = E_lo + j*dE, dE=(E_hi-E_lo)/(n_coarse-1);
+ *   bracket: j* = first j with nodes_j > v  ->  [E_{j*-1}, E_{j*}]
+ *            (level absent if nodes_last <= v or nodes_0 > v -> NaN);
+ *   refine:  rounds of M interior points E_m = lo + m*step, step=(hi-lo)/(M+1),
+ *            m* = first m with nodes_m > v (M+1 if none), new bracket
+ *            [E_{m*-1}, E_{m*}] with E_0 = lo, E_{M+1} = hi; a level is
+ *            converged when hi-lo <= rel_tol*max(|lo|,|hi|) or the bracket
+ *            stopped shrinking; at most max_rounds rounds;
+ *   result:  0.5*(lo+hi).
+ * All decisions are integer comparisons of node counts.  Returns the number of
+ * refinement rounds used; *steps_done gets grid-steps x energies executed. */
+int orc_solve_levels(const double* AB, uint32_t n_steps, double s, double E_lo, double E_hi,
+                     uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
+                     uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
+                     uint64_t* steps_done) {
+    const uint32_t nlev  = vmax - vmin + 1;
+    uint64_t       steps = 0;
+    uint32_t*      nodes = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_coarse > M ? n_coarse : M));
+    double*        lo    = (double*)malloc(sizeof(double) * nlev);
+    double*        hi    = (double*)malloc(sizeof(double) * nlev);
+    uint8_t*       act   = (uint8_t*)malloc(nlev);
+    const double   dE    = (E_hi - E_lo) / (double)(n_coarse - 1);
+
+    orc_sweep_uniform(AB, n_steps, s, E_lo, dE, 0, n_coarse, nodes, 0, 0);
+    steps += (uint64_t)n_steps * n_coarse;
+    if (n_below_hi) *n_below_hi = nodes[n_coarse - 1];
+    for (uint32_t l = 0; l < nlev; l++) {
+        const uint32_t v = vmin + l;
+        act[l]           = 0;
+        lo[l] = hi[l] = NAN;
+        if (nodes[n_coarse - 1] <= v || nodes[0] > v) continue;
+        uint32_t j = 1;
+        while (nodes[j] <= v) j++;
+        lo[l]  = E_lo + (double)(j - 1) * dE;
+        hi[l]  = E_lo + (double)j * dE;
+        act[l] = 1;
+    }
+    uint32_t round = 0;
+    for (; round < max_rounds; round++) {
+        int any = 0;
+        for (uint32_t l = 0; l < nlev; l++) {
+            if (!act[l]) continue;
+            const double w   = hi[l] - lo[l];
+            const double mag = fabs(lo[l]) > fabs(hi[l]) ? fabs(lo[l]) : fabs(hi[l]);
+            if (w <= rel_tol * mag) act[l] = 0;
+            else any = 1;
+        }
+        if (!any) break;
+        for (uint32_t l = 0; l < nlev; l++) {
+            if (!act[l]) continue;
+            const uint32_t v    = vmin + l;
+            const double   step = (hi[l] - lo[l]) / (double)(M + 1);
+            /* points m = 1..M are j = 1..M of the grid E0=lo, dE=step */
+            orc_sweep_uniform(AB, n_steps, s, lo[l], step, 1, M, nodes, 0, 0);
+            steps += (uint64_t)n_steps * M;
+            uint32_t m = 1;
+            while (m <= M && nodes[m - 1] <= v) m++;
+            const double nlo = (m == 1) ? lo[l] : lo[l] + (double)(m - 1) * step;
+            const double nhi = (m == M + 1) ? hi[l] : lo[l] + (double)m * step;
+            if (!((nhi - nlo) < (hi[l] - lo[l]))) act[l] = 0; /* no progress */
+            lo[l] = nlo;
+            hi[l] = nhi;
+        }
+    }
+    for (uint32_t l = 0; l < nlev; l++) {
+        levels[l] = 0.5 * (lo[l] + hi[l]);
+        if (widths) widths[l] = hi[l] - lo[l];
+    }
+    if (steps_done) *steps_done = steps;
+    free(nodes);
+    free(lo);
+    free(hi);
+    free(act);
+    return (int)round;
+}

@@ -1,0 +1,136 @@
+"""ctypes wrapper around oracle/numerov_oracle.c (test infrastructure only)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+
+
+def _cpu_tag() -> str:
+    """-march=native objects must not travel between hosts: key the build dir by CPU flags."""
+    import hashlib
+
+    flags = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = line
+                break
+    except OSError:
+        pass
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_BUILD = _HERE / "_build" / _cpu_tag()
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force: bool = False) -> None:
+    """Compile the oracle with gcc (a few seconds)."""
+    src = _HERE / "numerov_oracle.c"
+    libs = [_BUILD / "liboracle.so", _BUILD / "liboracle_omp.so"]
+    if not force and all(p.exists() and p.stat().st_mtime >= src.stat().st_mtime for p in libs):
+        return
+    subprocess.run(["make", "-s", "-C", str(_HERE), f"OUT={_BUILD}"] + (["-B"] if force else []),
+                   check=True)
+
+
+def _opt(a, dtype):
+    if a is None:
+        return None
+    assert a.dtype == dtype and a.flags.c_contiguous
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Scalar-order CPU statement of prep / sweep / level search.
+
+    ``omp=True`` loads the OpenMP build (same arithmetic, energies spread over
+    host threads); used for the timed CPU baseline.
+    """
+
+    def __init__(self, omp: bool = False):
+        build_oracle()
+        self.lib = C.CDLL(str(_BUILD / ("liboracle_omp.so" if omp else "liboracle.so")))
+        L = self.lib
+        L.orc_num_threads.restype = C.c_int
+        L.orc_scale.restype = C.c_double
+        L.orc_scale.argtypes = [C.c_double] * 3
+        L.orc_morse_tabulate.argtypes = [C.c_double] * 5 + [C.c_uint32, _f64p]
+        L.orc_lj_tabulate.argtypes = [C.c_double] * 4 + [C.c_uint32, _f64p]
+        L.orc_prep.restype = C.c_int
+        L.orc_prep.argtypes = [_f64p, C.c_uint32, C.c_double, _f64p, C.POINTER(C.c_uint32),
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+        L.orc_sweep.argtypes = [_f64p, C.c_uint32, C.c_double, _f64p, C.c_uint64,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sweep_uniform.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_solve_levels.restype = C.c_int
+        L.orc_solve_levels.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                       C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint64)]
+
+    @property
+    def threads(self) -> int:
+        return int(self.lib.orc_num_threads())
+
+    def scale(self, m0: float, m1: float, h: float) -> float:
+        return float(self.lib.orc_scale(m0, m1, h))
+
+    def morse(self, De, re, a, rmin, rmax, N) -> np.ndarray:
+        V = np.empty(N, dtype=np.float64)
+        self.lib.orc_morse_tabulate(De, re, a, rmin, rmax, N, V)
+        return V
+
+    def lj(self, De, re, rmin, rmax, N) -> np.ndarray:
+        V = np.empty(N, dtype=np.float64)
+        self.lib.orc_lj_tabulate(De, re, rmin, rmax, N, V)
+        return V
+
+    def prep(self, V: np.ndarray, s: float):
+        """-> (AB[n_steps,2], i0, n_steps, vmin)"""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        AB = np.empty(2 * V.size, dtype=np.float64)
+        i0, n, vmin = C.c_uint32(), C.c_uint32(), C.c_double()
+        rc = self.lib.orc_prep(V, V.size, s, AB, C.byref(i0), C.byref(n), C.byref(vmin))
+        if rc != 0:
+            raise ValueError("orc_prep: unusable potential table")
+        return AB[: 2 * n.value].copy(), i0.value, n.value, vmin.value
+
+    def sweep(self, AB: np.ndarray, s: float, E: np.ndarray, tails: bool = True):
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        n_steps = AB.size // 2
+        nodes = np.empty(E.size, dtype=np.uint32)
+        mant = np.empty(E.size, dtype=np.float64) if tails else None
+        expo = np.empty(E.size, dtype=np.int32) if tails else None
+        self.lib.orc_sweep(AB, n_steps, s, E, E.size, _opt(nodes, np.uint32),
+                           _opt(mant, np.float64), _opt(expo, np.int32))
+        return nodes, mant, expo
+
+    def sweep_uniform(self, AB, s, E0, dE, j0, nE, tails: bool = True):
+        n_steps = AB.size // 2
+        nodes = np.empty(nE, dtype=np.uint32)
+        mant = np.empty(nE, dtype=np.float64) if tails else None
+        expo = np.empty(nE, dtype=np.int32) if tails else None
+        self.lib.orc_sweep_uniform(AB, n_steps, s, E0, dE, j0, nE, _opt(nodes, np.uint32),
+                                   _opt(mant, np.float64), _opt(expo, np.int32))
+        return nodes, mant, expo
+
+    def solve_levels(self, AB, s, E_lo, E_hi, n_coarse, vmin, vmax, M, rel_tol=1e-12,
+                     max_rounds=8):
+        """-> (levels[nlev], widths[nlev], n_below_hi, rounds, steps)"""
+        n_steps = AB.size // 2
+        nlev = vmax - vmin + 1
+        levels = np.empty(nlev, dtype=np.float64)
+        widths = np.empty(nlev, dtype=np.float64)
+        nb, st = C.c_uint32(), C.c_uint64()
+        rounds = self.lib.orc_solve_levels(AB, n_steps, s, E_lo, E_hi, n_coarse, vmin, vmax, M,
+                                           rel_tol, max_rounds, levels, widths, C.byref(nb),
+                                           C.byref(st))
+        return levels, widths, nb.value, rounds, st.value

@@ -1,0 +1,139 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: node counts, tail mantissas/exponents and located
+level energies BIT-EXACT against the oracle on the same float64 inputs (the
+kernels use the same IEEE operations in the same order).  Accuracy against the
+analytic Morse spectrum is asserted at the tolerance the discretisation allows.
+"""
+import numpy as np
+import pytest
+
+from tests import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+
+
+def _check_sweep(oracle, ctx, V, s, E):
+    ctx.set_potentials(V, s)
+    ci = ctx.curve_info(0)
+    AB, i0, n, vmin = oracle.prep(V, s)
+    assert (ci.i0, ci.n_steps, ci.v_min) == (i0, n, vmin)
+    n_g, m_g, x_g = ctx.sweep(E)
+    n_o, m_o, x_o = oracle.sweep(AB, s, E)
+    assert np.array_equal(n_g[0], n_o), "node counts differ"
+    assert np.array_equal(x_g[0], x_o), "tail exponents differ"
+    assert _same_bits(m_g[0], m_o), "tail mantissas differ"
+    return n_o
+
+
+def test_c1_sweep_bit_exact(oracle, gpu_ctx):
+    w = W.c1()
+    E = np.linspace(w["E_lo"], w["E_hi"], w["nE"])
+    nodes = _check_sweep(oracle, gpu_ctx, w["V"], w["s"], E)
+    assert nodes[0] == 0 and nodes[-1] == 17  # 17 bound levels of the H2-like curve
+
+
+def test_c1_uniform_sweep_bit_exact(oracle, gpu_ctx):
+    w = W.c1()
+    gpu_ctx.set_potentials(w["V"], w["s"])
+    AB, *_ = oracle.prep(w["V"], w["s"])
+    nE = w["nE"]
+    n_g, m_g, x_g = gpu_ctx.sweep_uniform(w["E_lo"], w["E_hi"], nE)
+    dE = (w["E_hi"] - w["E_lo"]) / (nE - 1)
+    n_o, m_o, x_o = oracle.sweep_uniform(AB, w["s"], w["E_lo"], dE, 0, nE)
+    assert np.array_equal(n_g[0], n_o) and np.array_equal(x_g[0], x_o) and _same_bits(m_g[0], m_o)
+
+
+@pytest.mark.parametrize("N", [3, 4, 130, 1000, 1024, 1025, 1027, 4097, 5000, 16500])
+@pytest.mark.parametrize("nE", [1, 31, 257])
+def test_ragged_sizes(oracle, gpu_ctx, N, nE):
+    """Grid lengths around the tile (1024) and renormalisation (128) boundaries, ragged energy rows."""
+    rng = np.random.default_rng(N * 1000 + nE)
+    V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, N)
+    s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, N))
+    if N < 100:  # a coarse grid needs a shallow well to stay inside the validity window
+        V = V * 1e-3
+    hi = min(V[-1], V.min() + 0.45 / s)
+    E = np.sort(rng.uniform(V.min(), hi, nE))
+    _check_sweep(oracle, gpu_ctx, V, s, E)
+
+
+def test_reference_fixture_curve(oracle, gpu_ctx):
+    """The reference's own fixture: MorsePotentialConfig(5500, 0.6, 10, 0, 10, 16500), Sr masses
+    (python/test/test_device/test_gpu/test_libepseon_gpu.py:176-208).  V(0) ~ 9e8: the window rule
+    must skip the wall."""
+    N = 16500
+    V = W.morse(5500.0, 0.6, 10.0, 0.0, 10.0, N)
+    s = W.scale(87.62, 87.62, W.grid_h(0.0, 10.0, N))
+    E = np.linspace(0.0, 5499.9, 777)
+    nodes = _check_sweep(oracle, gpu_ctx, V, s, E)
+    assert gpu_ctx.curve_info(0).i0 > 1
+    assert nodes[-1] == len(W.morse_levels(5500.0, 10.0, 87.62, 87.62))
+
+
+def test_multi_curve_batch(oracle, gpu_ctx):
+    w = W.c4(nC=9, N=3000, nE=300)
+    gpu_ctx.set_potentials(w["V"], w["s"])
+    n_g, m_g, x_g = gpu_ctx.sweep_uniform(w["E_lo"], w["E_hi"], w["nE"])
+    for c in range(9):
+        AB, *_ = oracle.prep(w["V"][c], w["s"])
+        dE = (w["E_hi"][c] - w["E_lo"][c]) / (w["nE"] - 1)
+        n_o, m_o, x_o = oracle.sweep_uniform(AB, w["s"], w["E_lo"][c], dE, 0, w["nE"])
+        assert np.array_equal(n_g[c], n_o) and np.array_equal(x_g[c], x_o) and _same_bits(m_g[c], m_o)
+
+
+def test_c1_levels_bit_exact_and_analytic(oracle, gpu_ctx):
+    w = W.c1()
+    gpu_ctx.set_potentials(w["V"], w["s"])
+    AB, *_ = oracle.prep(w["V"], w["s"])
+    exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+    nlev = len(exact) + 2  # ask for two levels that do not exist
+    lev_g, wid_g, nb_g = gpu_ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, nlev - 1, 96, 1e-13, 12)
+    lev_o, wid_o, nb_o, rounds, steps = oracle.solve_levels(AB, w["s"], w["E_lo"], w["E_hi"], 1024, 0,
+                                                            nlev - 1, 96, 1e-13, 12)
+    assert nb_g[0] == nb_o == len(exact)
+    assert _same_bits(lev_g[0], lev_o), "level energies differ from the oracle"
+    assert _same_bits(wid_g[0], wid_o)
+    assert np.all(np.isnan(lev_g[0][len(exact):]))
+    rel = np.abs(lev_g[0][: len(exact)] - exact) / exact
+    assert rel.max() < 5e-8  # O(h^4) discretisation error at N = 10 000
+    assert rel[:4].max() < 1e-9
+
+
+def test_multi_curve_levels(oracle, gpu_ctx):
+    w = W.c4(nC=5, N=4000, nE=256)
+    gpu_ctx.set_potentials(w["V"], w["s"])
+    lev_g, wid_g, nb_g = gpu_ctx.solve_levels(w["E_lo"], w["E_hi"], 256, 2, 9, 64, 1e-12, 10)
+    for c in range(5):
+        AB, *_ = oracle.prep(w["V"][c], w["s"])
+        lev_o, wid_o, nb_o, *_ = oracle.solve_levels(AB, w["s"], w["E_lo"][c], w["E_hi"][c], 256, 2, 9, 64,
+                                                     1e-12, 10)
+        assert nb_g[c] == nb_o
+        assert _same_bits(lev_g[c], lev_o)
+
+
+def test_range_error(gpu_ctx):
+    from epseon_backend_b200.cabi import EpsError
+
+    N = 500  # reference C++ fixture size (cpp/gpu/test/test_libgpu.cpp:41-48)
+    V = W.morse(5500.0, 0.6, 10.0, 0.0, 10.0, N)
+    s = W.scale(87.62, 87.62, W.grid_h(0.0, 10.0, N))
+    gpu_ctx.set_potentials(V, s)
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.sweep(np.array([1.0e9]))
+    assert ei.value.code == 3
+
+
+def test_stats_and_steps(gpu_ctx):
+    w = W.c1()
+    gpu_ctx.set_potentials(w["V"], w["s"])
+    gpu_ctx.stats_reset()
+    gpu_ctx.sweep_uniform(w["E_lo"], w["E_hi"], 1000, tails=False)
+    st = gpu_ctx.stats()
+    assert st.sweep_launches == 1
+    assert st.grid_steps == gpu_ctx.curve_info(0).n_steps * 1000
+    assert st.sweep_ms > 0.0
