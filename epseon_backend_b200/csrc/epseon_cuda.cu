@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -58,8 +59,8 @@ struct eps_ctx {
 
     // resident potentials
     uint32_t                    nC = 0, N = 0;
-    uint64_t                    slot = 0;  // double2 per curve
-    DevBuf<double2>             d_AB;
+    uint64_t                    slot = 0;  // doubles per curve
+    DevBuf<double>              d_F;
     DevBuf<CurveDev>            d_curves;
     std::vector<eps_curve_info> curves;
 
@@ -81,6 +82,7 @@ struct eps_ctx {
     int         ev_used = 0;
     eps_stats   stats{};
     void*       d_flush = nullptr;
+    int         force_ept = 0, force_stride = 0;  // tuning overrides (EPS_FORCE_EPT / EPS_FORCE_STRIDE)
 };
 
 namespace {
@@ -123,14 +125,61 @@ int fold_events(eps_ctx* ctx) {
     return EPS_OK;
 }
 
-size_t sweep_smem_bytes() { return sizeof(double2) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
+size_t sweep_smem_bytes() { return sizeof(double) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
+
+template <int kEpt, int kStride, bool kTails>
+cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp) {
+    constexpr uint32_t per_cta = kConsumerWarps * 32 * kEpt;
+    const uint64_t chunks = (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
+    const uint64_t grid   = chunks * n_jobs;
+    if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
+    auto kern = numerov_sweep_kernel<kEpt, kStride, kTails>;
+    static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
+    if (configured_dev != ctx->dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()));
+        if (e != cudaSuccess) return e;
+        configured_dev = ctx->dev;
+    }
+    kern<<<static_cast<unsigned>(grid), kSweepThreads, sweep_smem_bytes(), ctx->stream>>>(
+        ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->d_nodes.p,
+        kTails ? ctx->d_mant.p : nullptr, kTails ? ctx->d_exp.p : nullptr, ctx->d_steps);
+    return cudaGetLastError();
+}
+
+template <int kEpt, int kStride>
+cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
+    return tails ? launch_sweep_variant<kEpt, kStride, true>(ctx, j, n, nE, E) : launch_sweep_variant<kEpt, kStride, false>(ctx, j, n, nE, E);
+}
+
+template <int kEpt>
+cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
+    if (stride == 32) return launch_sweep_t<kEpt, 32>(ctx, j, n, nE, E, tails);
+    if (stride == 8) return launch_sweep_t<kEpt, 8>(ctx, j, n, nE, E, tails);
+    return launch_sweep_t<kEpt, 1>(ctx, j, n, nE, E, tails);
+}
+
+// Energies per thread: two independent chains per thread saturate the FP64 pipe with only two
+// warps per scheduler (scripts/microbench.cu); one chain when the row is too short to fill a CTA.
+int pick_ept(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE) {
+    if (ctx->force_ept) return ctx->force_ept;
+    (void)n_jobs;
+    return nE > static_cast<uint32_t>(kConsumerWarps * 32) ? 2 : 1;
+}
+
+// Sign-sampling stride from theta_max^2 = 12 * t_max, t_max = max over rows of s*(E_max - V_min):
+// stride m is exact while m * theta_max < pi; selected with a factor-2 margin (m * theta_max < pi/2).
+int pick_stride(const eps_ctx* ctx, double t_max) {
+    if (ctx->force_stride) return ctx->force_stride;
+    if (!(t_max == t_max)) return 1;
+    if (t_max <= 2.0e-4) return 32;   // (pi/64)^2 / 12 = 2.008e-4
+    if (t_max <= 3.2e-3) return 8;    // (pi/16)^2 / 12 = 3.213e-3
+    return 1;
+}
 
 // Launch the sweep over n_jobs rows of nE energies each (jobs already on device).
+// t_max = max over the rows of s * (E_max - V_min) (see pick_stride).
 int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                 bool tails) {
-    const uint64_t chunks = (static_cast<uint64_t>(nE) + kEnergiesPerCta - 1) / kEnergiesPerCta;
-    const uint64_t grid   = chunks * n_jobs;
-    EPS_REQUIRE(ctx, grid > 0 && grid < (1ull << 31), EPS_ERR_INVALID, "sweep grid out of range");
+                 bool tails, double t_max) {
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
     if (tails) {
@@ -143,20 +192,18 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     }
     cudaEvent_t* pair = ctx->ev[ctx->ev_used++];
     EPS_CUDA(ctx, cudaEventRecord(pair[0], ctx->stream));
-    const size_t smem = sweep_smem_bytes();
-    if (tails)
-        numerov_sweep_kernel<true><<<static_cast<unsigned>(grid), kSweepThreads, smem, ctx->stream>>>(
-            ctx->d_AB.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE,
-            ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p, ctx->d_steps);
-    else
-        numerov_sweep_kernel<false><<<static_cast<unsigned>(grid), kSweepThreads, smem, ctx->stream>>>(
-            ctx->d_AB.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE,
-            ctx->d_nodes.p, nullptr, nullptr, ctx->d_steps);
-    EPS_CUDA(ctx, cudaGetLastError());
+    const int   ept    = pick_ept(ctx, n_jobs, nE);
+    const int   stride = pick_stride(ctx, t_max);
+    cudaError_t e = (ept == 2) ? launch_sweep_s<2>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails)
+                               : launch_sweep_s<1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    EPS_CUDA(ctx, e);
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
     return EPS_OK;
 }
+
+// t_max of a curve for trial energies up to E_max (see pick_stride).
+double curve_tmax(const eps_curve_info& ci, double E_max) { return ci.scale * (E_max - ci.v_min); }
 
 // Validity of a trial-energy range on a curve: |s (E - V_min)| <= T_MAX keeps every
 // f_i = 1 - (q_i - e) positive inside the window (Sturm property, bounded growth).
@@ -267,8 +314,11 @@ int eps_ctx_create(int device, eps_ctx** out) {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_steps), sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), 4096)) != cudaSuccess) return bail(e, "cudaMallocHost");
-    if ((e = cudaFuncSetAttribute(numerov_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()))) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
-    if ((e = cudaFuncSetAttribute(numerov_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()))) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    if (const char* fe = std::getenv("EPS_FORCE_EPT")) ctx->force_ept = std::atoi(fe) == 2 ? 2 : (std::atoi(fe) == 1 ? 1 : 0);
+    if (const char* fs = std::getenv("EPS_FORCE_STRIDE")) {
+        const int v = std::atoi(fs);
+        ctx->force_stride = (v == 1 || v == 8 || v == 32) ? v : 0;
+    }
     *out = ctx;
     return EPS_OK;
 }
@@ -277,7 +327,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
     if (!ctx) return EPS_OK;
     if (ctx->dev >= 0 && cudaSetDevice(ctx->dev) == cudaSuccess) {
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-        ctx->d_AB.release();
+        ctx->d_F.release();
         ctx->d_curves.release();
         ctx->d_jobs.release();
         ctx->d_jobs_ref.release();
@@ -315,8 +365,8 @@ int eps_sync(eps_ctx* ctx) {
     return EPS_OK;
 }
 
-// Preparation (spec DESIGN.md section 3.2, oracle orc_prep): q = s V, window
-// [i0, iend] around the minimum with q - q_min <= T_MAX, A = 2 + 10 q, B = 1 - q.
+// Preparation (spec DESIGN.md section 3.2): q = s V, window [i0, iend] around the
+// minimum with q - q_min <= T_MAX, coefficient table F_k = (1 - q_{i0+k}) / 12.
 int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
                        const double* scale) {
     if (int rc = bind(ctx)) return rc;
@@ -324,7 +374,7 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     EPS_REQUIRE(ctx, n_curves >= 1 && n_points >= 3, EPS_ERR_INVALID, "need >=1 curve of >=3 points");
     const uint32_t N    = n_points;
     const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
-    std::vector<double2>        ab(static_cast<size_t>(slot) * n_curves, make_double2(2.0, 1.0));
+    std::vector<double>         ab(static_cast<size_t>(slot) * n_curves, 1.0 / 12.0);
     std::vector<CurveDev>       cds(n_curves);
     std::vector<eps_curve_info> infos(n_curves);
     for (uint32_t c = 0; c < n_curves; c++) {
@@ -348,22 +398,21 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
         const uint32_t iend = (ihi + 1 < N - 1) ? ihi + 1 : N - 1;
         EPS_REQUIRE(ctx, iend >= i0 + 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
         const uint32_t n   = iend - i0;
-        double2*       dst = ab.data() + static_cast<size_t>(c) * slot;
+        double*        dst = ab.data() + static_cast<size_t>(c) * slot;
         for (uint32_t k = 0; k < n; k++) {
             const double q = s * v[i0 + k];
-            dst[k].x       = 2.0 + 10.0 * q;
-            dst[k].y       = 1.0 - q;
+            dst[k]         = (1.0 - q) / 12.0;
         }
         cds[c]   = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, v[m]};
         infos[c] = eps_curve_info{i0, n, s, v[m], v[N - 1]};
     }
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    EPS_CUDA(ctx, ctx->d_AB.reserve(ab.size()));
+    EPS_CUDA(ctx, ctx->d_F.reserve(ab.size()));
     EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_AB.p, ab.data(), ab.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_F.p, ab.data(), ab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_curves.p, cds.data(), cds.size() * sizeof(CurveDev), cudaMemcpyHostToDevice, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.h2d_bytes += ab.size() * sizeof(double2) + cds.size() * sizeof(CurveDev);
+    ctx->stats.h2d_bytes += ab.size() * sizeof(double) + cds.size() * sizeof(CurveDev);
     ctx->nC     = n_curves;
     ctx->N      = N;
     ctx->slot   = slot;
@@ -386,6 +435,7 @@ int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* node
     EPS_REQUIRE(ctx, E && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
     const uint32_t nE = static_cast<uint32_t>(n_energies);
     std::vector<Job> jobs(ctx->nC);
+    double           t_max = -1.0;
     for (uint32_t c = 0; c < ctx->nC; c++) {
         const double* row = E + static_cast<size_t>(c) * nE;
         double        mn = row[0], mx = row[0];
@@ -397,6 +447,7 @@ int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* node
         for (uint32_t j = 0; j < nE && finite; j++) finite = std::isfinite(row[j]);
         EPS_REQUIRE(ctx, finite && range_ok(ctx->curves[c], mn, mx), EPS_ERR_RANGE,
                     "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+        t_max   = std::max(t_max, curve_tmax(ctx->curves[c], mx));
         jobs[c] = Job{0.0, 0.0, static_cast<uint64_t>(c) * nE, c, 0, nE, 0, c, 0};
     }
     const size_t n = static_cast<size_t>(ctx->nC) * nE;
@@ -406,7 +457,7 @@ int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* node
     EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += n * sizeof(double) + jobs.size() * sizeof(Job);
     // jobs lives on the host stack of this call: make sure the copy is done before returning
-    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, ctx->d_E.p, tail_mant || tail_exp)) return rc;
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, ctx->d_E.p, tail_mant || tail_exp, t_max)) return rc;
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return fetch_sweep(ctx, n, nodes, tail_mant, tail_exp);
 }
@@ -417,9 +468,12 @@ int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint
     EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
     EPS_REQUIRE(ctx, E_lo && E_hi && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
     const uint32_t nE = static_cast<uint32_t>(n_energies);
-    for (uint32_t c = 0; c < ctx->nC; c++)
+    double t_max = -1.0;
+    for (uint32_t c = 0; c < ctx->nC; c++) {
         EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
                     "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+        t_max = std::max(t_max, curve_tmax(ctx->curves[c], std::max(E_lo[c], E_hi[c])));
+    }
     EPS_CUDA(ctx, ctx->d_Elo.reserve(ctx->nC));
     EPS_CUDA(ctx, ctx->d_Ehi.reserve(ctx->nC));
     EPS_CUDA(ctx, ctx->d_jobs.reserve(ctx->nC));
@@ -430,7 +484,7 @@ int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
     // E_lo/E_hi are pageable host memory: the async copies above are staged before return
-    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, nullptr, tail_mant || tail_exp)) return rc;
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, nullptr, tail_mant || tail_exp, t_max)) return rc;
     return fetch_sweep(ctx, static_cast<size_t>(ctx->nC) * nE, nodes, tail_mant, tail_exp);
 }
 
@@ -445,7 +499,9 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
     const uint64_t total64 = static_cast<uint64_t>(nC) * nlev;
     EPS_REQUIRE(ctx, total64 < (1ull << 31), EPS_ERR_INVALID, "too many (curve, level) pairs");
     const uint32_t total = static_cast<uint32_t>(total64);
+    double t_max = -1.0;
     for (uint32_t c = 0; c < nC; c++) {
+        t_max = std::max(t_max, curve_tmax(ctx->curves[c], E_hi[c]));
         EPS_REQUIRE(ctx, E_hi[c] >= E_lo[c], EPS_ERR_INVALID, "E_hi < E_lo");
         EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
                     "search range outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
@@ -470,7 +526,7 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
     const uint32_t nE = p->n_coarse;
     make_coarse_jobs_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, nC, nE, ctx->d_jobs.p);
     EPS_CUDA(ctx, cudaGetLastError());
-    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false)) return rc;
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false, t_max)) return rc;
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, total * sizeof(uint32_t), ctx->stream));
     {
         const uint32_t bpr = (nE + 255) / 256;
@@ -492,7 +548,7 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         ctx->stats.d2h_bytes += sizeof(uint32_t);
         const uint32_t n_active = ctx->h_pinned[0];
         if (n_active == 0) break;
-        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false)) return rc;
+        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false, t_max)) return rc;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_active * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;
         crossing_kernel<<<bpr * n_active, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);
@@ -564,7 +620,7 @@ int eps_l2_flush(eps_ctx* ctx) {
 int eps_fp64_probe(eps_ctx* ctx, double* tflops, float* ms_out) {
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, tflops, EPS_ERR_INVALID, "tflops is null");
-    const int    blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 13;
+    const int    blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 12;
     DevBuf<double> out;
     EPS_CUDA(ctx, out.reserve(static_cast<size_t>(blocks) * threads));
     float best = 1e30f;

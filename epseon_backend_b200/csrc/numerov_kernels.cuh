@@ -18,18 +18,17 @@
 
 namespace eps {
 
-constexpr int      kTile          = 1024;  // grid steps per shared-memory stage (16 KiB of (A,B))
+constexpr int      kTile          = 2048;  // grid steps per shared-memory stage (16 KiB of F_k)
 constexpr int      kStages        = 4;     // TMA ring depth
-constexpr int      kConsumerWarps = 8;     // 256 trial energies per CTA
+constexpr int      kConsumerWarps = 8;     // 256 * EPT trial energies per CTA
 constexpr int      kSweepThreads  = (kConsumerWarps + 1) * 32;  // + 1 TMA producer warp
-constexpr int      kEnergiesPerCta = kConsumerWarps * 32;
 constexpr int      kRenorm        = 128;   // exponent renormalisation period (steps)
 constexpr uint32_t kNone          = 0xffffffffu;
 
-// One potential curve resident in HBM: its (A_k, B_k) coefficient pairs live at
-// AB[ab_off .. ab_off + slot), slot a multiple of kTile, padded with (2, 1).
+// One potential curve resident in HBM: its coefficient table F_k = (1 - q_k)/12
+// lives at F[f_off .. f_off + slot), slot a multiple of kTile, padded with 1/12.
 struct CurveDev {
-    uint64_t ab_off;   // in double2 units
+    uint64_t f_off;    // in doubles
     uint32_t n_steps;  // recurrence steps
     uint32_t i0;
     double   s;        // energy scale
@@ -97,54 +96,63 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 // ---------------------------------------------------------------------------
-// Numerov recurrence pieces (spec: DESIGN.md section 3; oracle: sweep_block()).
+// Numerov recurrence pieces (spec: DESIGN.md section 3.3; oracle: sweep_block()).
 // ---------------------------------------------------------------------------
 struct Chain {
-    double Y, Yp, fp;  // Y_k, Y_{k-1}, f_{k-1}
+    double X, S;  // X_k, S_{k-1} = (f_{k-1}/12) X_{k-1}
 };
 
-// One step: u = A - 10e, f = B + e, g = f f_prev, t = g Y_prev, Y' = fma(u, Y, -t).
-// 5 FP64 instructions (2 DADD, 2 DMUL, 1 DFMA) -- counted as 7 FLOP.
-__device__ __forceinline__ void numerov_step(Chain& c, const double2 ab, const double e,
-                                             const double e10) {
-    const double u  = __dsub_rn(ab.x, e10);
-    const double f  = __dadd_rn(ab.y, e);
-    const double g  = __dmul_rn(f, c.fp);
-    const double t  = __dmul_rn(g, c.Yp);
-    const double Yn = __fma_rn(u, c.Y, -t);
-    c.Yp = c.Y;
-    c.Y  = Yn;
-    c.fp = f;
+// One step of the 4-operation X form (1 DADD, 1 DMUL, 2 DFMA = 6 FLOP):
+//   fp = F_k + e/12;  Q = fma(10, X, S);  X' = fma(-fp, Q, X);  S' = fp * X.
+__device__ __forceinline__ void numerov_step(Chain& c, const double Fk, const double ep) {
+    const double fp = __dadd_rn(Fk, ep);
+    const double Q  = __fma_rn(10.0, c.X, c.S);
+    const double Xn = __fma_rn(-fp, Q, c.X);
+    c.S = __dmul_rn(fp, c.X);
+    c.X = Xn;
 }
 
-// Scale (Y, Yp) by the power of two that brings |Y| into [1,2); exact.
+// Scale (X, S) by the power of two that brings |X| into [1,2); exact.
 __device__ __forceinline__ void renorm(Chain& c, int& expo) {
-    const uint32_t ex = (static_cast<uint32_t>(__double2hiint(c.Y)) >> 20) & 0x7ffu;
+    const uint32_t ex = (static_cast<uint32_t>(__double2hiint(c.X)) >> 20) & 0x7ffu;
     if (ex != 0) {
         const double sc = __hiloint2double(static_cast<int>((2046u - ex) << 20), 0);
-        c.Y  = __dmul_rn(c.Y, sc);
-        c.Yp = __dmul_rn(c.Yp, sc);
+        c.X = __dmul_rn(c.X, sc);
+        c.S = __dmul_rn(c.S, sc);
         expo += static_cast<int>(ex) - 1023;
     }
 }
 
 // ---------------------------------------------------------------------------
-// Many-energy sweep: one FP64 recurrence per thread, the curve's (A,B) table
-// streamed through a kStages-deep shared-memory ring by a TMA producer warp and
-// read by every consumer thread as a warp-broadcast LDS.128.
+// Many-energy sweep: kEpt independent FP64 recurrences per thread, the curve's
+// F table streamed through a kStages-deep shared-memory ring by a TMA producer
+// warp and read by every consumer thread as a warp-broadcast LDS.128 (2 steps).
 //   grid  = n_jobs * chunks_per_job CTAs,  CTA = 8 consumer warps + 1 producer
-//   smem  = kStages * kTile * 16 B ring + 2*kStages mbarriers
+//   smem  = kStages * kTile * 8 B ring + 2*kStages mbarriers
+// Energy j of a CTA's chunk sits in thread (j % 256), chain (j / 256), so the
+// result stores of every chain are coalesced.
+//
+// Node counting.  The FP64 pipe shares register-file bandwidth with every other
+// instruction (measured: one integer SHF per step costs 16 % of the DFMA rate),
+// so the sign of X is sampled every kStride steps.  That is EXACTLY the per-step
+// sign-flip count of the spec whenever two zeros of a solution are more than
+// kStride steps apart, which Sturm separation guarantees for
+//     kStride * theta_max < pi,   theta_max^2 = 12 * s * (E_max - V_min);
+// the host only selects kStride = 32 / 8 with a factor-2 margin on theta_max
+// (launch_sweep) and kStride = 1 (per-step bit mask) otherwise.
 // ---------------------------------------------------------------------------
-template <bool kTails>
+template <int kEpt, int kStride, bool kTails>
 __global__ void __launch_bounds__(kSweepThreads, 2)
-numerov_sweep_kernel(const double2* __restrict__ AB, const CurveDev* __restrict__ curves,
+numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
                      const Job* __restrict__ jobs, const uint32_t chunks_per_job,
                      const double* __restrict__ Eexp, const uint64_t out_stride,
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                      int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done) {
+    static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
+    constexpr uint32_t kPerCta = kConsumerWarps * 32 * kEpt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2*  ring  = reinterpret_cast<double2*>(smem_raw);
-    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double2) * kTile * kStages);
+    double*   ring  = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kStages);
     uint64_t* empty = full + kStages;
 
     const uint32_t job_idx = blockIdx.x / chunks_per_job;
@@ -156,7 +164,7 @@ numerov_sweep_kernel(const double2* __restrict__ AB, const CurveDev* __restrict_
     const uint32_t warp    = threadIdx.x >> 5;
     const uint32_t lane    = threadIdx.x & 31;
 
-    const uint32_t e_base = chunk * kEnergiesPerCta;
+    const uint32_t e_base = chunk * kPerCta;
     if (e_base >= job.nE) return;  // whole CTA past the end of the row (uniform)
 
     if (threadIdx.x == 0) {
@@ -171,39 +179,43 @@ numerov_sweep_kernel(const double2* __restrict__ AB, const CurveDev* __restrict_
     if (warp == kConsumerWarps) {
         // ===== TMA producer: one elected lane streams the curve through the ring =====
         if (lane == 0) {
-            const double2* src = AB + cv.ab_off;
+            const double* src = F + cv.f_off;
             for (uint32_t t = 0; t < n_tiles; t++) {
                 const uint32_t s = t % kStages;
                 if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) - 1) & 1);
-                mbar_arrive_expect_tx(&full[s], kTile * sizeof(double2));
+                mbar_arrive_expect_tx(&full[s], kTile * sizeof(double));
                 tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t) * kTile,
-                             kTile * sizeof(double2), &full[s]);
+                             kTile * sizeof(double), &full[s]);
             }
-            const uint32_t in_cta = min(job.nE - e_base, static_cast<uint32_t>(kEnergiesPerCta));
+            const uint32_t in_cta = min(job.nE - e_base, kPerCta);
             atomicAdd(steps_done, static_cast<unsigned long long>(n_steps) * in_cta);
         }
         return;
     }
 
-    // ===== consumers: one trial energy per thread =====
-    uint32_t j = e_base + warp * 32 + lane;
-    const bool live = j < job.nE;
-    if (!live) j = job.nE - 1;  // keep the warp converged; result discarded
-    double E;
-    if (Eexp != nullptr) E = Eexp[job.e_off + j];
-    else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
-    const double e   = __dmul_rn(cv.s, E);
-    const double e10 = __dmul_rn(10.0, e);
-
-    Chain    c{1.0, 0.0, 1.0};
-    int      expo     = 0;
-    uint32_t n_nodes  = 0;
-    uint32_t prevmask = 0;  // bit0 = sign of the latest Y of the previous 32-step group
+    // ===== consumers: kEpt trial energies per thread =====
+    Chain    c[kEpt];
+    double   ep[kEpt];
+    int      expo[kEpt];
+    uint32_t n_nodes[kEpt], prev[kEpt];
+#pragma unroll
+    for (int i = 0; i < kEpt; i++) {
+        uint32_t j = e_base + i * (kConsumerWarps * 32) + warp * 32 + lane;
+        if (j >= job.nE) j = job.nE - 1;  // keep the warp converged; result discarded
+        double E;
+        if (Eexp != nullptr) E = Eexp[job.e_off + j];
+        else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
+        ep[i]      = __ddiv_rn(__dmul_rn(cv.s, E), 12.0);
+        c[i]       = Chain{1.0, 0.0};
+        expo[i]    = 0;
+        n_nodes[i] = 0;
+        prev[i]    = 0;  // kStride==1: bit0 = sign of the last X; else: hi word of the last sampled X
+    }
 
     for (uint32_t t = 0; t < n_tiles; t++) {
         const uint32_t s = t % kStages;
         mbar_wait(&full[s], (t / kStages) & 1);
-        const double2* __restrict__ tile = ring + s * kTile;
+        const double* __restrict__ tile = ring + s * kTile;
         const uint32_t n_valid = min(static_cast<uint32_t>(kTile), n_steps - t * kTile);
         const uint32_t n_full  = n_valid / kRenorm;
 
@@ -212,37 +224,75 @@ numerov_sweep_kernel(const double2* __restrict__ AB, const CurveDev* __restrict_
         for (uint32_t r = 0; r < n_full; r++) {
 #pragma unroll 1
             for (int q = 0; q < kRenorm / 32; q++) {
-                uint32_t mask = 0;
+                uint32_t mask[kEpt];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    numerov_step(c, tile[k + i], e, e10);
-                    mask = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c.Y)), mask, 1);
+                for (int i = 0; i < kEpt; i++) mask[i] = 0;
+                const double2* __restrict__ t2 = reinterpret_cast<const double2*>(tile + k);
+#pragma unroll
+                for (int p = 0; p < 16; p++) {
+                    const double2 ff = t2[p];  // two consecutive grid steps, warp-broadcast
+#pragma unroll
+                    for (int i = 0; i < kEpt; i++) {
+                        numerov_step(c[i], ff.x, ep[i]);
+                        if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kEpt; i++) {
+                        numerov_step(c[i], ff.y, ep[i]);
+                        if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                    }
+                    if (kStride == 8 && (p & 3) == 3) {
+#pragma unroll
+                        for (int i = 0; i < kEpt; i++) {
+                            const uint32_t cur = static_cast<uint32_t>(__double2hiint(c[i].X));
+                            n_nodes[i] += (cur ^ prev[i]) >> 31;
+                            prev[i] = cur;
+                        }
+                    }
                 }
-                n_nodes += __popc(mask ^ __funnelshift_r(mask, prevmask, 1));
-                prevmask = mask;
+#pragma unroll
+                for (int i = 0; i < kEpt; i++) {
+                    if (kStride == 1) {
+                        n_nodes[i] += __popc(mask[i] ^ __funnelshift_r(mask[i], prev[i], 1));
+                        prev[i] = mask[i];
+                    } else if (kStride == 32) {
+                        const uint32_t cur = static_cast<uint32_t>(__double2hiint(c[i].X));
+                        n_nodes[i] += (cur ^ prev[i]) >> 31;
+                        prev[i] = cur;
+                    }
+                }
                 k += 32;
             }
-            renorm(c, expo);
+#pragma unroll
+            for (int i = 0; i < kEpt; i++) renorm(c[i], expo[i]);
         }
         // ragged tail of the last tile (< kRenorm steps): plain per-step counting
         for (; k < n_valid; k++) {
-            const uint32_t before = static_cast<uint32_t>(__double2hiint(c.Y));
-            numerov_step(c, tile[k], e, e10);
-            const uint32_t after = static_cast<uint32_t>(__double2hiint(c.Y));
-            n_nodes += (before ^ after) >> 31;
-            prevmask = after >> 31;
+            const double Fk = tile[k];
+#pragma unroll
+            for (int i = 0; i < kEpt; i++) {
+                const uint32_t before = static_cast<uint32_t>(__double2hiint(c[i].X));
+                numerov_step(c[i], Fk, ep[i]);
+                const uint32_t after = static_cast<uint32_t>(__double2hiint(c[i].X));
+                n_nodes[i] += (before ^ after) >> 31;
+                prev[i] = (kStride == 1) ? (after >> 31) : after;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
-    renorm(c, expo);
 
-    if (live) {
-        const uint64_t o = static_cast<uint64_t>(job_idx) * out_stride + j;
-        nodes_out[o] = n_nodes;
-        if (kTails) {
-            mant_out[o] = c.Y;
-            exp_out[o]  = expo;
+#pragma unroll
+    for (int i = 0; i < kEpt; i++) {
+        renorm(c[i], expo[i]);
+        const uint32_t j = e_base + i * (kConsumerWarps * 32) + warp * 32 + lane;
+        if (j < job.nE) {
+            const uint64_t o = static_cast<uint64_t>(job_idx) * out_stride + j;
+            nodes_out[o] = n_nodes[i];
+            if (kTails) {
+                mant_out[o] = c[i].X;
+                exp_out[o]  = expo[i];
+            }
         }
     }
 }
@@ -407,23 +457,20 @@ __global__ void finalize_levels_kernel(const double* __restrict__ lo, const doub
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* __restrict__ out, int iters,
                                                          double x, double y) {
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-           a6 = a0 + 6, a7 = a0 + 7;
-#pragma unroll 1
-    for (int i = 0; i < iters; i++) {
+    double a[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            a0 = __fma_rn(a0, x, y);
-            a1 = __fma_rn(a1, x, y);
-            a2 = __fma_rn(a2, x, y);
-            a3 = __fma_rn(a3, x, y);
-            a4 = __fma_rn(a4, x, y);
-            a5 = __fma_rn(a5, x, y);
-            a6 = __fma_rn(a6, x, y);
-            a7 = __fma_rn(a7, x, y);
-        }
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __fma_rn(a[i], x, y);
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
 }  // namespace eps

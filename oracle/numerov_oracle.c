@@ -104,11 +104,11 @@ double orc_scale(double m0, double m1, double h) {
 
 /* Preparation: q_i = s V_i; integration window [i0, iend] around the minimum
  * on which q_i - q_min <= T_MAX (so f_i = 1 - (q_i - e) > 0 for every
- * admissible energy: the Sturm-sequence property needs it); coefficient pairs
- * A_k = 2 + 10 q_{i0+k},  B_k = 1 - q_{i0+k},  k = 0 .. n_steps-1.
- * AB must hold 2*N doubles (interleaved A,B).  Returns 0, or -1 when the
- * table is unusable (non-finite values, or fewer than 2 steps). */
-int orc_prep(const double* V, uint32_t N, double s, double* AB, uint32_t* i0_out,
+ * admissible energy: the Sturm-sequence property needs it); coefficient table
+ * F_k = (1 - q_{i0+k}) / 12,  k = 0 .. n_steps-1  (so f_k/12 = F_k + e/12).
+ * F must hold N doubles.  Returns 0, or -1 when the table is unusable
+ * (non-finite values, or fewer than 2 steps). */
+int orc_prep(const double* V, uint32_t N, double s, double* F, uint32_t* i0_out,
              uint32_t* n_steps_out, double* vmin_out) {
     if (N < 3) return -1;
     uint32_t m = 0;
@@ -130,8 +130,7 @@ int orc_prep(const double* V, uint32_t N, double s, double* AB, uint32_t* i0_out
     const uint32_t n = iend - i0;
     for (uint32_t k = 0; k < n; k++) {
         const double q = s * V[i0 + k];
-        AB[2 * k]      = 2.0 + 10.0 * q;
-        AB[2 * k + 1]  = 1.0 - q;
+        F[k]           = (1.0 - q) / 12.0;
     }
     *i0_out      = i0;
     *n_steps_out = n;
@@ -139,77 +138,79 @@ int orc_prep(const double* V, uint32_t N, double s, double* AB, uint32_t* i0_out
     return 0;
 }
 
-/* Exponent renormalisation: scale (Y, Yp) by the power of two that brings
- * |Y| into [1,2); exact, so signs and all later bits are those of the
- * unscaled recurrence.  Skipped when Y is zero or subnormal. */
-static inline void renorm(double* Y, double* Yp, int32_t* expo) {
-    const uint32_t ex = (uint32_t)(d2u(*Y) >> 52) & 0x7ffu;
+/* Exponent renormalisation: scale (X, S) by the power of two that brings
+ * |X| into [1,2); exact, so signs and all later bits are those of the
+ * unscaled recurrence.  Skipped when X is zero or subnormal. */
+static inline void renorm(double* X, double* S, int32_t* expo) {
+    const uint32_t ex = (uint32_t)(d2u(*X) >> 52) & 0x7ffu;
     if (ex != 0) {
         const double sc = u2d((uint64_t)(2046u - ex) << 52);
-        *Y *= sc;
-        *Yp *= sc;
+        *X *= sc;
+        *S *= sc;
         *expo += (int32_t)ex - 1023;
     }
 }
 
-/* N2 + N3 for a block of up to ORC_EB energies: the division-free Numerov
- * recurrence  Y_{k+1} = (A_k - 10e) Y_k - ((B_k + e)(B_{k-1} + e)) Y_{k-1}
- * with Y_{-1}=0, Y_0=1; node = sign-bit flip between consecutive Y. */
-static void sweep_block(const double* AB, uint32_t n_steps, double s, const double* E, int nb,
+/* N2 + N3 for a block of up to ORC_EB energies.  Division-free Numerov in the
+ * 4-operation "X form" (DESIGN.md section 3.3):  with f_k = 1 - (q_k - e),
+ * the textbook recurrence  f_{k+1} psi_{k+1} = (12 - 10 f_k) psi_k - f_{k-1} psi_{k-1}
+ * becomes, for  X_k = psi_k f_k prod_{j<k} f_j / 12^k  and  S_k = (f_k/12) X_k,
+ *     fp   = F_k + e/12                    (1 add)
+ *     Q    = fma(10, X_k, S_{k-1})         (1 fma)
+ *     X'   = fma(-fp, Q, X_k)              (1 fma)
+ *     S_k  = fp * X_k                      (1 mul)
+ * X_k has the sign of psi_k while every f_j > 0; node = sign-bit flip between
+ * consecutive X.  Start: X = 1, S = 0 (psi = 0 one point to the left). */
+static void sweep_block(const double* F, uint32_t n_steps, double s, const double* E, int nb,
                         uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
-    double   e[ORC_EB], e10[ORC_EB], Y[ORC_EB], Yp[ORC_EB], fp[ORC_EB];
+    double   ep[ORC_EB], X[ORC_EB], S[ORC_EB];
     int64_t  cnt[ORC_EB];
     int32_t  ex[ORC_EB];
     for (int b = 0; b < ORC_EB; b++) {
         const double Eb = E[b < nb ? b : nb - 1];
-        e[b]   = s * Eb;
-        e10[b] = 10.0 * e[b];
-        Y[b]   = 1.0;
-        Yp[b]  = 0.0;
-        fp[b]  = 1.0;
+        ep[b]  = (s * Eb) / 12.0;
+        X[b]   = 1.0;
+        S[b]   = 0.0;
         cnt[b] = 0;
         ex[b]  = 0;
     }
     for (uint32_t k = 0; k < n_steps; k++) {
-        const double A = AB[2 * k], B = AB[2 * k + 1];
+        const double Fk = F[k];
 #pragma omp simd
         for (int b = 0; b < ORC_EB; b++) {
-            const double u  = A - e10[b];
-            const double f  = B + e[b];
-            const double g  = f * fp[b];
-            const double t  = g * Yp[b];
-            const double Yn = fma(u, Y[b], -t);
-            cnt[b] += (int64_t)((d2u(Yn) ^ d2u(Y[b])) >> 63);
-            Yp[b] = Y[b];
-            Y[b]  = Yn;
-            fp[b] = f;
+            const double fp = Fk + ep[b];
+            const double Q  = fma(10.0, X[b], S[b]);
+            const double Xn = fma(-fp, Q, X[b]);
+            S[b]            = fp * X[b];
+            cnt[b] += (int64_t)((d2u(Xn) ^ d2u(X[b])) >> 63);
+            X[b] = Xn;
         }
         if (((k + 1) % ORC_RENORM_PERIOD) == 0)
-            for (int b = 0; b < ORC_EB; b++) renorm(&Y[b], &Yp[b], &ex[b]);
+            for (int b = 0; b < ORC_EB; b++) renorm(&X[b], &S[b], &ex[b]);
     }
     for (int b = 0; b < nb; b++) {
-        renorm(&Y[b], &Yp[b], &ex[b]);
+        renorm(&X[b], &S[b], &ex[b]);
         if (nodes) nodes[b] = (uint32_t)cnt[b];
-        if (tail_mant) tail_mant[b] = Y[b];
+        if (tail_mant) tail_mant[b] = X[b];
         if (tail_exp) tail_exp[b] = ex[b];
     }
 }
 
 /* Sweep explicit energies E[0..nE). Any output pointer may be NULL. */
-void orc_sweep(const double* AB, uint32_t n_steps, double s, const double* E, uint64_t nE,
+void orc_sweep(const double* F, uint32_t n_steps, double s, const double* E, uint64_t nE,
                uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
     const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
 #pragma omp parallel for schedule(static)
     for (int64_t blk = 0; blk < nblk; blk++) {
         const uint64_t o  = (uint64_t)blk * ORC_EB;
         const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
-        sweep_block(AB, n_steps, s, E + o, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+        sweep_block(F, n_steps, s, E + o, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
                     tail_exp ? tail_exp + o : 0);
     }
 }
 
 /* Uniform grid E_j = E0 + j*dE, j = j0 .. j0+nE-1 (one multiply, one add). */
-void orc_sweep_uniform(const double* AB, uint32_t n_steps, double s, double E0, double dE,
+void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, double dE,
                        uint64_t j0, uint64_t nE, uint32_t* nodes, double* tail_mant,
                        int32_t* tail_exp) {
     const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
@@ -219,7 +220,7 @@ void orc_sweep_uniform(const double* AB, uint32_t n_steps, double s, double E0, 
         const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
         double         Eb[ORC_EB];
         for (int b = 0; b < nb; b++) Eb[b] = E0 + (double)(j0 + o + (uint64_t)b) * dE;
-        sweep_block(AB, n_steps, s, Eb, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+        sweep_block(F, n_steps, s, Eb, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
                     tail_exp ? tail_exp + o : 0);
     }
 }
@@ -236,7 +237,7 @@ void orc_sweep_uniform(const double* AB, uint32_t n_steps, double s, double E0, 
  *   result:  0.5*(lo+hi).
  * All decisions are integer comparisons of node counts.  Returns the number of
  * refinement rounds used; *steps_done gets grid-steps x energies executed. */
-int orc_solve_levels(const double* AB, uint32_t n_steps, double s, double E_lo, double E_hi,
+int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, double E_hi,
                      uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
                      uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
                      uint64_t* steps_done) {
@@ -248,7 +249,7 @@ int orc_solve_levels(const double* AB, uint32_t n_steps, double s, double E_lo, 
     uint8_t*       act   = (uint8_t*)malloc(nlev);
     const double   dE    = (E_hi - E_lo) / (double)(n_coarse - 1);
 
-    orc_sweep_uniform(AB, n_steps, s, E_lo, dE, 0, n_coarse, nodes, 0, 0);
+    orc_sweep_uniform(F, n_steps, s, E_lo, dE, 0, n_coarse, nodes, 0, 0);
     steps += (uint64_t)n_steps * n_coarse;
     if (n_below_hi) *n_below_hi = nodes[n_coarse - 1];
     for (uint32_t l = 0; l < nlev; l++) {
@@ -278,7 +279,7 @@ int orc_solve_levels(const double* AB, uint32_t n_steps, double s, double E_lo, 
             const uint32_t v    = vmin + l;
             const double   step = (hi[l] - lo[l]) / (double)(M + 1);
             /* points m = 1..M are j = 1..M of the grid E0=lo, dE=step */
-            orc_sweep_uniform(AB, n_steps, s, lo[l], step, 1, M, nodes, 0, 0);
+            orc_sweep_uniform(F, n_steps, s, lo[l], step, 1, M, nodes, 0, 0);
             steps += (uint64_t)n_steps * M;
             uint32_t m = 1;
             while (m <= M && nodes[m - 1] <= v) m++;

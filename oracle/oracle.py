@@ -94,18 +94,18 @@ class Oracle:
         return V
 
     def prep(self, V: np.ndarray, s: float):
-        """-> (AB[n_steps,2], i0, n_steps, vmin)"""
+        """-> (F[n_steps], i0, n_steps, vmin)"""
         V = np.ascontiguousarray(V, dtype=np.float64)
-        AB = np.empty(2 * V.size, dtype=np.float64)
+        AB = np.empty(V.size, dtype=np.float64)
         i0, n, vmin = C.c_uint32(), C.c_uint32(), C.c_double()
         rc = self.lib.orc_prep(V, V.size, s, AB, C.byref(i0), C.byref(n), C.byref(vmin))
         if rc != 0:
             raise ValueError("orc_prep: unusable potential table")
-        return AB[: 2 * n.value].copy(), i0.value, n.value, vmin.value
+        return AB[: n.value].copy(), i0.value, n.value, vmin.value
 
     def sweep(self, AB: np.ndarray, s: float, E: np.ndarray, tails: bool = True):
         E = np.ascontiguousarray(E, dtype=np.float64)
-        n_steps = AB.size // 2
+        n_steps = AB.size
         nodes = np.empty(E.size, dtype=np.uint32)
         mant = np.empty(E.size, dtype=np.float64) if tails else None
         expo = np.empty(E.size, dtype=np.int32) if tails else None
@@ -114,7 +114,7 @@ class Oracle:
         return nodes, mant, expo
 
     def sweep_uniform(self, AB, s, E0, dE, j0, nE, tails: bool = True):
-        n_steps = AB.size // 2
+        n_steps = AB.size
         nodes = np.empty(nE, dtype=np.uint32)
         mant = np.empty(nE, dtype=np.float64) if tails else None
         expo = np.empty(nE, dtype=np.int32) if tails else None
@@ -125,7 +125,7 @@ class Oracle:
     def solve_levels(self, AB, s, E_lo, E_hi, n_coarse, vmin, vmax, M, rel_tol=1e-12,
                      max_rounds=8):
         """-> (levels[nlev], widths[nlev], n_below_hi, rounds, steps)"""
-        n_steps = AB.size // 2
+        n_steps = AB.size
         nlev = vmax - vmin + 1
         levels = np.empty(nlev, dtype=np.float64)
         widths = np.empty(nlev, dtype=np.float64)

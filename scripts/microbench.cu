@@ -1,0 +1,120 @@
+// FP64-pipe microbenchmarks (tuning only; not part of the product).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mb scripts/microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITERS 4096
+
+// mode 0: DFMA, 8 chains, two shared (reused) operands:  a = fma(a, x, y)
+__global__ void __launch_bounds__(256) k_dfma_shared(double* out, double x, double y) {
+    double a[8];
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __fma_rn(a[i], x, y);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// mode 1: DFMA with three distinct, rotating register operands: a_i = fma(a_j, a_k, a_i)
+__global__ void __launch_bounds__(256) k_dfma_3reg(double* out, double x, double y) {
+    double a[8];
+    for (int i = 0; i < 8; i++) a[i] = 1.0 + threadIdx.x * 1e-9 + i * 1e-7;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __fma_rn(a[(i + 3) & 7], a[(i + 5) & 7], -a[i]);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s * x + y;
+}
+
+// mode 2: DADD only, 2 register operands, 8 chains
+__global__ void __launch_bounds__(256) k_dadd(double* out, double x, double y) {
+    double a[8];
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __dadd_rn(a[i], a[(i + 1) & 7]);
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s * x + y;
+}
+
+// mode 3: the Numerov X-form mix, E chains per thread, F from a register (no memory, no SHF)
+template <int E, bool SHF>
+__global__ void __launch_bounds__(256) k_mix(double* out, double F0, double ep0) {
+    double X[E], S[E], ep[E];
+    unsigned mask[E];
+    for (int i = 0; i < E; i++) { X[i] = 1.0; S[i] = 0.0; ep[i] = ep0 * (1 + i + threadIdx.x); mask[i] = 0; }
+    double F = F0;
+#pragma unroll 1
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const double fp = __dadd_rn(F, ep[i]);
+                const double Q  = __fma_rn(10.0, X[i], S[i]);
+                const double Xn = __fma_rn(-fp, Q, X[i]);
+                S[i] = __dmul_rn(fp, X[i]);
+                X[i] = Xn;
+                if (SHF) mask[i] = __funnelshift_l((unsigned)__double2hiint(Xn), mask[i], 1);
+            }
+        }
+        for (int i = 0; i < E; i++) { X[i] = X[i] * 4096.0 * 4096.0 * 4096.0 * 4096.0 * 4096.0; S[i] = S[i] * 4096.0 * 4096.0 * 4096.0 * 4096.0 * 4096.0; }
+    }
+    double s = 0;
+    for (int i = 0; i < E; i++) s += X[i] + S[i] + mask[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename K>
+void run(const char* name, K kern, double ops_per_thread, int blocks, int threads) {
+    double* out;
+    cudaMalloc(&out, sizeof(double) * blocks * threads);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(a);
+        kern<<<blocks, threads>>>(out, 0.08333, 1e-9);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r) best = best < ms ? best : ms;
+    }
+    const double inst = ops_per_thread * blocks * threads;  // FP64 thread-instructions
+    printf("%-28s blocks/SM=%d thr=%d  %8.3f ms  %7.3f T fp64-inst/s  (%.1f%% of 148*64*1.965GHz)\n", name,
+           blocks / 148, threads, best, inst / (best * 1e-3) / 1e12, 100.0 * inst / (best * 1e-3) / (148.0 * 64 * 1.965e9));
+    cudaFree(out);
+}
+
+int main() {
+    for (int bps : {1, 2, 4, 8}) {
+        run("dfma shared operands", k_dfma_shared, 64.0 * ITERS, 148 * bps, 256);
+        run("dfma 3 distinct regs", k_dfma_3reg, 64.0 * ITERS, 148 * bps, 256);
+        run("dadd 2 regs", k_dadd, 64.0 * ITERS, 148 * bps, 256);
+        run("mix E=1", k_mix<1, false>, 64.0 * ITERS, 148 * bps, 256);
+        run("mix E=2", k_mix<2, false>, 128.0 * ITERS, 148 * bps, 256);
+        run("mix E=4", k_mix<4, false>, 256.0 * ITERS, 148 * bps, 256);
+        run("mix E=2 +shf", k_mix<2, true>, 128.0 * ITERS, 148 * bps, 256);
+        run("mix E=4 +shf", k_mix<4, true>, 256.0 * ITERS, 148 * bps, 256);
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}

@@ -48,7 +48,7 @@ def test_c1_uniform_sweep_bit_exact(oracle, gpu_ctx):
     assert np.array_equal(n_g[0], n_o) and np.array_equal(x_g[0], x_o) and _same_bits(m_g[0], m_o)
 
 
-@pytest.mark.parametrize("N", [3, 4, 130, 1000, 1024, 1025, 1027, 4097, 5000, 16500])
+@pytest.mark.parametrize("N", [4, 7, 130, 1000, 1024, 1025, 1027, 4097, 5000, 16500])
 @pytest.mark.parametrize("nE", [1, 31, 257])
 def test_ragged_sizes(oracle, gpu_ctx, N, nE):
     """Grid lengths around the tile (1024) and renormalisation (128) boundaries, ragged energy rows."""
@@ -56,7 +56,7 @@ def test_ragged_sizes(oracle, gpu_ctx, N, nE):
     V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, N)
     s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, N))
     if N < 100:  # a coarse grid needs a shallow well to stay inside the validity window
-        V = V * 1e-3
+        V = V * 1e-4
     hi = min(V[-1], V.min() + 0.45 / s)
     E = np.sort(rng.uniform(V.min(), hi, nE))
     _check_sweep(oracle, gpu_ctx, V, s, E)
@@ -137,3 +137,31 @@ def test_stats_and_steps(gpu_ctx):
     assert st.sweep_launches == 1
     assert st.grid_steps == gpu_ctx.curve_info(0).n_steps * 1000
     assert st.sweep_ms > 0.0
+
+
+@pytest.mark.parametrize("ept", [1, 2])
+@pytest.mark.parametrize("stride", [1, 8, 32])
+def test_kernel_variants_bit_exact(oracle, ept, stride, monkeypatch):
+    """Every (energies-per-thread, sign-stride) kernel variant against the per-step oracle on C1
+    (t_max = 9e-5: all strides are inside their validity bound)."""
+    from epseon_backend_b200 import cabi
+
+    monkeypatch.setenv("EPS_FORCE_EPT", str(ept))
+    monkeypatch.setenv("EPS_FORCE_STRIDE", str(stride))
+    w = W.c1()
+    E = np.linspace(w["E_lo"], w["E_hi"], 1500)
+    with cabi.Context(0) as ctx:
+        _check_sweep(oracle, ctx, w["V"], w["s"], E)
+
+
+@pytest.mark.parametrize("N,expect", [(6800, "32"), (6700, "8"), (1720, "8"), (1690, "1")])
+def test_sign_stride_threshold(oracle, gpu_ctx, N, expect):
+    """Grids right at the stride-selection thresholds (t_max = 2.0e-4 and 3.2e-3): the subsampled
+    sign count must still equal the oracle's per-step count for a dense set of energies."""
+    V = W.morse(W.H2["De"], W.H2["re"], W.H2["a"], 0.2, 10.0, N)
+    s = W.scale(W.H2["m0"], W.H2["m1"], W.grid_h(0.2, 10.0, N))
+    t_max = s * (W.H2["De"] - 1.0)
+    assert {"32": t_max <= 2.0e-4, "8": 2.0e-4 < t_max <= 3.2e-3, "1": t_max > 3.2e-3}[expect]
+    rng = np.random.default_rng(N)
+    E = np.sort(rng.uniform(0.0, W.H2["De"] - 1.0, 4096))
+    _check_sweep(oracle, gpu_ctx, V, s, E)
