@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Numerov hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c5] [--impl reference]
+
+Metric: FP64 Numerov grid-steps x trial-energies per second (whole job, all ranks), plus
+time-to-all-levels.  One "step" = one complete pass of the hot path over the workload:
+
+  c2 (default; BASELINE.json configs[1]):  Morse (H2-like) potential, 100 000-point grid,
+      coarse sweep of 65 536 trial energies, bracketing, k-section refinement of all 17 bound
+      levels to 1e-10 relative.  At N GPUs each rank solves its own (slightly perturbed) curve
+      -- sharded by potential curve, no data-path collective, weak scaling -- and the located
+      levels (17 doubles per rank) are gathered to rank 0 over NCCL.
+  c5 (BASELINE.json configs[4]):  dense sweep of 2^24 trial energies on a 200 000-point grid,
+      energy-range sharded over the ranks (strong scaling); node-count checksums gathered.
+
+value  = steps executed by all ranks / max-over-ranks CUDA-event time, potentials resident in HBM.
+e2e    = same metric through the host-buffer C ABI (eps_set_potentials + eps_solve_levels with
+         host pointers: table upload and result download inside the timed region).
+roofline.bound = "fp64": the path is FP64-pipe bound; the denominator is
+         a DFMA probe measured in this process because MEASURED_PEAKS.json has no FP64 entry.
+cpu_baseline / --impl reference: the build's own CPU oracle (the reference repository has no
+         implementation of this path -- SURVEY.md section 0), OpenMP over all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from tests import workloads as W  # noqa: E402
+
+METRIC = "numerov_grid_steps_x_trial_energies_per_s"
+FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
+
+C2 = dict(N=100_000, n_coarse=65_536, refine_points=4096, rel_tol=1e-10, max_rounds=8, v_max=16)
+C5 = dict(N=200_000, nE=1 << 24)
+
+
+def rank_curve(rank: int):
+    """C2 curve of a rank: the H2-like Morse curve, parameters perturbed +-2 % for rank > 0."""
+    rng = np.random.default_rng(7000 + rank)
+    j = 1.0 + (0.02 * (2.0 * rng.random(3) - 1.0) if rank else np.zeros(3))
+    De, a, re = W.H2["De"] * j[0], W.H2["a"] * j[1], W.H2["re"] * j[2]
+    rmin, rmax, N = 0.2, 12.0, C2["N"]
+    V = W.morse(De, re, a, rmin, rmax, N)
+    s = W.scale(W.H2["m0"], W.H2["m1"], W.grid_h(rmin, rmax, N))
+    return V, s, 0.0, De - 1.0, (De, a)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz, mx, reasons, power = [], None, set(), []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                mhz.append(clk)
+                try:
+                    power.append(float(f[3]))
+                except ValueError:
+                    pass
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "samples": len(mhz),
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist, torch, world, rank, local
+    return None, None, 1, 0, 0
+
+
+def cpu_solve_c2(orc, V, s, E_lo, E_hi):
+    F, *_ = orc.prep(V, s)
+    t = time.perf_counter()
+    lev, wid, nb, rounds, steps = orc.solve_levels(F, s, E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"],
+                                                   C2["refine_points"], C2["rel_tol"], C2["max_rounds"])
+    return time.perf_counter() - t, steps, lev
+
+
+def run_reference(args) -> None:
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference
+    repository has none, so this times the build's oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import Oracle
+
+    orc = Oracle(omp=True)
+    if args.workload == "c5":
+        w = W.c5(C5["N"], C5["nE"])
+        F, *_ = orc.prep(w["V"], w["s"])
+        n_steps = F.size
+        nE = 1 << 16  # bounded sample of the 2^24-energy sweep; work is exactly linear in nE
+        dE = (w["E_hi"] - w["E_lo"]) / (C5["nE"] - 1)
+
+        def one():
+            t = time.perf_counter()
+            orc.sweep_uniform(F, w["s"], w["E_lo"], dE * (C5["nE"] // nE), 0, nE, tails=False)
+            return time.perf_counter() - t, n_steps * nE
+
+        sample = f"2^16 of the 2^24 energies (every 256th) on the 200k grid, {orc.threads} threads"
+        cfg = {"workload": "c5: dense sweep 2^24 energies x 200k-point grid (energy-range sharded)"}
+    else:
+        V, s, E_lo, E_hi, _ = rank_curve(0)
+
+        def one():
+            dt, steps, _ = cpu_solve_c2(orc, V, s, E_lo, E_hi)
+            return dt, steps
+
+        sample = f"full C2 solve (coarse 65536 + refinement of 17 levels), {orc.threads} threads"
+        cfg = {"workload": "c2: Morse 100k-point grid, 65536 trial energies, all 17 bound levels to 1e-10"}
+    for _ in range(args.warmup):
+        one()
+    tot_t = tot_s = 0.0
+    for _ in range(args.steps):
+        dt, st = one()
+        tot_t += dt
+        tot_s += st
+    val = tot_s / tot_t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": orc.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference repo has no implementation of this path; this is the build's CPU oracle (port)",
+    }))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=["c2", "c5"], default="c2")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import __graft_entry__ as ge
+
+    dist, torch, world, rank, local = dist_setup(args.gpus)
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from epseon_backend_b200 import cabi
+
+    ctx = cabi.Context(local)
+    sampler = ClockSampler(local)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if args.workload == "c2":
+        V, s, E_lo, E_hi, (De, a) = rank_curve(rank)
+        ctx.set_potentials(V, s)
+        n_steps = ctx.curve_info(0).n_steps
+
+        def step_resident():
+            return ctx.solve_levels(E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
+                                    C2["rel_tol"], C2["max_rounds"])
+
+        def step_e2e():
+            ctx.set_potentials(V, s)  # host table -> prep -> H2D
+            return step_resident()  # ... -> levels, widths, counts D2H
+
+        cfg = {"workload": "c2: Morse (H2-like) 100k-point grid, 65536 trial energies coarse sweep + k-section "
+                           "refinement of all 17 bound levels to 1e-10 rel.; one curve per GPU (curve-sharded)",
+               "grid_points": C2["N"], "trial_energies_coarse": C2["n_coarse"],
+               "refine_points_per_level": C2["refine_points"], "levels": C2["v_max"] + 1,
+               "l2": "flushed between timed steps (256 MiB memset)"}
+        scaling = "weak"
+    else:
+        w = W.c5(C5["N"], C5["nE"])
+        ctx.set_potentials(w["V"], w["s"])
+        n_steps = ctx.curve_info(0).n_steps
+        per = C5["nE"] // world
+        dE = (w["E_hi"] - w["E_lo"]) / (C5["nE"] - 1)
+        lo = w["E_lo"] + rank * per * dE
+        hi = w["E_lo"] + (rank * per + per - 1) * dE
+        V, s = w["V"], w["s"]
+
+        def step_resident():
+            return ctx.sweep_uniform(lo, hi, per, nodes=False, tails=False)
+
+        def step_e2e():
+            ctx.set_potentials(V, s)
+            n, _, _ = ctx.sweep_uniform(lo, hi, per, nodes=True, tails=False)  # 4 B/energy D2H
+            return n
+
+        cfg = {"workload": "c5: dense sweep of 2^24 trial energies on a 200k-point grid, energy-range sharded",
+               "grid_points": C5["N"], "trial_energies": C5["nE"], "l2": "flushed between timed steps (256 MiB memset)"}
+        scaling = "strong"
+
+    def gather_small(arr: np.ndarray):
+        """Gather a small per-rank result to rank 0 (the only inter-GPU traffic of the path)."""
+        if dist is None:
+            return [arr]
+        t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, out, dst=0)
+        return [o.cpu().numpy() for o in out] if rank == 0 else None
+
+    def result_digest(res) -> np.ndarray:
+        if args.workload == "c2":
+            return res[0][0]  # 17 level energies
+        return np.zeros(1)
+
+    # ---- warm-up, FP64 probe ----
+    for _ in range(args.warmup):
+        res = step_resident()
+    ctx.sync()
+    fp64_peak, _ = ctx.fp64_probe()
+
+    def timed_run(step_fn, k: int):
+        """K steps; CUDA events on the ctx stream around each step; L2 flushed between steps."""
+        ms_total, results = 0.0, None
+        for _ in range(k):
+            ctx.l2_flush()
+            barrier()
+            ctx.timer_start()
+            results = step_fn()
+            digest = gather_small(result_digest(results))
+            ms = ctx.timer_stop()
+            if dist is not None:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            ms_total += ms
+        return ms_total, results, digest
+
+    # ---- timed: resident ----
+    barrier()
+    ctx.stats_reset()
+    sampler.start()
+    t_wall0 = time.time()
+    ms_res, res, digest = timed_run(step_resident, args.steps)
+    t_wall1 = time.time()
+    st = ctx.stats()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    steps_rank = float(st.grid_steps)
+    if dist is not None:
+        t = torch.tensor([steps_rank], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        steps_all = float(t.item())
+    else:
+        steps_all = steps_rank
+    value = steps_all / (ms_res * 1e-3)
+    sweep_rate = steps_rank / (st.sweep_ms * 1e-3)  # this rank's dominant kernel, averaged over its launches
+    launches = int(st.sweep_launches + st.other_launches)
+
+    # ---- timed: end-to-end through the host-buffer C ABI ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ctx.stats_reset()
+    ms_e2e, _, _ = timed_run(step_e2e, args.steps)
+    st2 = ctx.stats()
+    steps2 = float(st2.grid_steps)
+    if dist is not None:
+        t = torch.tensor([steps2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        steps2 = float(t.item())
+    e2e_value = steps2 / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "time_to_all_levels_ms": ms_res / args.steps if args.workload == "c2" else None,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(st2.h2d_bytes // args.steps),
+                    "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps)},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp64", "kernel": "eps::numerov_sweep_kernel<2,32,false>",
+                "achieved": FLOP_PER_STEP * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": FLOP_PER_STEP * sweep_rate / 1e12 / fp64_peak,
+                "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_nominal": NOMINAL_FP64_TFLOPS,
+                "frac_of_nominal": FLOP_PER_STEP * sweep_rate / 1e12 / NOMINAL_FP64_TFLOPS,
+                "flop_per_step": FLOP_PER_STEP, "steps_per_s_kernel": sweep_rate,
+                "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
+                "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
+                "traffic": None,
+            },
+            "clocks": clocks,
+        }
+        if args.workload == "c2":
+            exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+            lev0 = digest[0]
+            line["levels_found"] = int(np.sum(np.isfinite(lev0)))
+            line["max_rel_err_vs_analytic_rank0"] = float(np.max(np.abs(lev0 - exact) / exact))
+        if not args.no_cpu_baseline:
+            from oracle import Oracle
+
+            orc = Oracle(omp=True)
+            if args.workload == "c2":
+                Vc, sc, El, Eh, _ = rank_curve(0)
+                dt, csteps, clev = cpu_solve_c2(orc, Vc, sc, El, Eh)
+                line["cpu_baseline"] = {"value": csteps / dt, "unit": "steps/s", "cores": orc.threads, "kind": "port",
+                                        "sample": "full C2 solve once (coarse 65536 + refinement), OpenMP oracle",
+                                        "seconds": dt,
+                                        "levels_bit_identical_to_gpu": bool(np.array_equal(
+                                            clev.view(np.uint64), digest[0].view(np.uint64)))}
+            else:
+                F, *_ = orc.prep(V, s)
+                nE = 1 << 16
+                t0 = time.perf_counter()
+                orc.sweep_uniform(F, s, w["E_lo"], dE * (C5["nE"] // nE), 0, nE, tails=False)
+                dt = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": F.size * nE / dt, "unit": "steps/s", "cores": orc.threads,
+                                        "kind": "port", "sample": "2^16 of the 2^24 energies (every 256th)",
+                                        "seconds": dt}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

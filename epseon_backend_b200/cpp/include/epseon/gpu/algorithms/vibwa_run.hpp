@@ -1,0 +1,107 @@
+// VibwaAlgorithm<FP>::run -- the hot path behind the reference's slot (vibwa.hpp:605-637).
+// C++ host code -> thin C ABI (include/epseon_cuda.h) -> sm_100a kernels.  No Vulkan, no PyTorch,
+// no CPU fallback: if the CUDA library cannot run, the task fails and says so in its status.
+#pragma once
+#include "epseon/gpu/algorithms/vibwa.hpp"
+#include "epseon/gpu/task_handle.hpp"
+
+#include "epseon_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace epseon::gpu::cpp {
+
+    namespace detail {
+        constexpr double kHbar2Over2 = 16.857629206; // amu * Angstrom^2 * cm^-1
+
+        struct CtxGuard {
+            eps_ctx* ctx = nullptr;
+            ~CtxGuard() {
+                if (ctx != nullptr) eps_ctx_destroy(ctx);
+            }
+        };
+
+        inline void check(int rc, eps_ctx* ctx, const char* what) {
+            if (rc != EPS_OK) throw std::runtime_error(std::string(what) + ": " + eps_last_error(ctx));
+        }
+    } // namespace detail
+
+    template <typename FP>
+    void VibwaAlgorithm<FP>::run(const std::stop_token& stop_token, TaskHandle<FP>* handle) {
+        if (stop_token.stop_requested()) return;
+
+        const TaskConfigurator<FP>& configurator = handle->getTaskConfigurator();
+        const auto                  hardware     = configurator.getHardwareConfig();
+        const auto                  source       = configurator.getPotentialSource();
+        const auto algorithm = std::dynamic_pointer_cast<VibwaAlgorithmConfig<FP>>(configurator.getAlgorithmConfig());
+        if (!algorithm) throw std::runtime_error("VibwaAlgorithm needs a VibwaAlgorithmConfig");
+        if (algorithm->getMaxLevel() < algorithm->getMinLevel()) throw std::runtime_error("max_level < min_level");
+
+        // ---- N1: tabulate V(r) on the host (double), one row per curve ----
+        handle->setStatus("tabulating potentials");
+        const auto                table = source->get_potential_data();
+        const std::vector<double> steps = source->get_grid_steps();
+        const uint32_t            nC    = static_cast<uint32_t>(table.size());
+        if (nC == 0) throw std::runtime_error("potential source holds no curves");
+        const uint32_t N = static_cast<uint32_t>(table.front().size());
+        if (hardware->getPotentialBufferSize() < N)
+            throw std::runtime_error("potential_buffer_size is smaller than the potential's point count");
+        std::vector<double> V(static_cast<size_t>(nC) * N), scale(nC);
+        const double m0 = algorithm->getMassAtom0(), m1 = algorithm->getMassAtom1();
+        const double mu = (m0 * m1) / (m0 + m1);
+        const double c  = mu / detail::kHbar2Over2;
+        for (uint32_t k = 0; k < nC; k++) {
+            if (table[k].size() != N) throw std::runtime_error("all curves must have the same point count");
+            for (uint32_t i = 0; i < N; i++) V[static_cast<size_t>(k) * N + i] = static_cast<double>(table[k][i]);
+            scale[k] = ((steps[k] * steps[k]) * c) / 12.0;
+        }
+        if (stop_token.stop_requested()) return;
+
+        // ---- device: resident coefficient tables ----
+        handle->setStatus("uploading potentials");
+        detail::CtxGuard guard;
+        detail::check(eps_ctx_create(handle->getDeviceInterface().getCudaOrdinal(), &guard.ctx), nullptr, "eps_ctx_create");
+        eps_ctx* ctx = guard.ctx;
+        detail::check(eps_set_potentials(ctx, V.data(), nC, N, scale.data()), ctx, "eps_set_potentials");
+
+        // ---- search window per curve: [V_min, V_last - min_distance_to_asymptote] ----
+        std::vector<double> E_lo(nC), E_hi(nC);
+        const double        margin = algorithm->getMinDistanceToAsymptote();
+        for (uint32_t k = 0; k < nC; k++) {
+            eps_curve_info info{};
+            detail::check(eps_get_curve_info(ctx, k, &info), ctx, "eps_get_curve_info");
+            E_lo[k] = info.v_min;
+            E_hi[k] = std::max(info.v_min, info.v_last - margin);
+        }
+        if (stop_token.stop_requested()) return;
+
+        // ---- N2..N6: coarse sweep, bracketing, k-section refinement ----
+        handle->setStatus("solving levels");
+        eps_solve_params p{};
+        p.v_min         = algorithm->getMinLevel();
+        p.v_max         = algorithm->getMaxLevel();
+        p.n_coarse      = std::clamp<uint32_t>(std::max<uint32_t>(hardware->getGroupSize(), 1024u), 1024u, 65536u);
+        p.refine_points = 256;
+        p.max_rounds    = 16;
+        p.rel_tol       = std::is_same_v<FP, float> ? 1e-8 : 1e-12;
+        const uint32_t        nlev = p.v_max - p.v_min + 1;
+        std::vector<double>   lev(static_cast<size_t>(nC) * nlev);
+        std::vector<uint32_t> below(nC);
+        detail::check(eps_timer_start(ctx), ctx, "eps_timer_start");
+        detail::check(eps_solve_levels(ctx, &p, E_lo.data(), E_hi.data(), lev.data(), nullptr, below.data()), ctx,
+                      "eps_solve_levels");
+        float ms = 0.f;
+        detail::check(eps_timer_stop(ctx, &ms), ctx, "eps_timer_stop");
+
+        std::vector<std::vector<FP>> out(nC, std::vector<FP>(nlev));
+        for (uint32_t k = 0; k < nC; k++)
+            for (uint32_t l = 0; l < nlev; l++) out[k][l] = static_cast<FP>(lev[static_cast<size_t>(k) * nlev + l]);
+        handle->setResults(std::move(out), std::move(below), ms);
+        handle->setStatus("done");
+    }
+} // namespace epseon::gpu::cpp

@@ -1,0 +1,108 @@
+// TaskConfigurator<FP> -- builder holding the three configuration objects of a task.
+// Reference: cpp/gpu/include/epseon/gpu/task_configurator/task_configurator.hpp:17-134 -- setters
+// deep-clone their argument (:88-113) and return *this for chaining; copies deep-clone (:56-85);
+// isConfigured() (:124-128).
+#pragma once
+#include "epseon/gpu/predecl.hpp"
+
+#include "epseon/gpu/task_configurator/algorithm_config.hpp"
+#include "epseon/gpu/task_configurator/hardware_config.hpp"
+#include "epseon/gpu/task_configurator/potential_source.hpp"
+
+#include <memory>
+#include <type_traits>
+#include <vector>
+
+namespace epseon::gpu::cpp {
+
+    template <typename FP>
+    class TaskConfigurator : public std::enable_shared_from_this<TaskConfigurator<FP>> {
+        static_assert(std::is_floating_point_v<FP>, "FP must be an floating-point type.");
+
+        std::shared_ptr<HardwareConfig<FP>>  hardware_config  = {};
+        std::shared_ptr<PotentialSource<FP>> potential_source = {};
+        std::shared_ptr<AlgorithmConfig<FP>> algorithm_config = {};
+
+        template <typename T>
+        static std::shared_ptr<T> clone_or_null(const std::shared_ptr<T>& p) {
+            return p ? p->shared_clone() : nullptr;
+        }
+
+      public:
+        TaskConfigurator() = default;
+        TaskConfigurator(std::shared_ptr<HardwareConfig<FP>> hardware_config_,
+                         std::shared_ptr<PotentialSource<FP>> potential_source_,
+                         std::shared_ptr<AlgorithmConfig<FP>> algorithm_config_) :
+            hardware_config(std::move(hardware_config_)),
+            potential_source(std::move(potential_source_)),
+            algorithm_config(std::move(algorithm_config_)) {}
+        TaskConfigurator(TaskConfigurator&& o) noexcept :
+            std::enable_shared_from_this<TaskConfigurator<FP>>(),
+            hardware_config(std::move(o.hardware_config)),
+            potential_source(std::move(o.potential_source)),
+            algorithm_config(std::move(o.algorithm_config)) {}
+        TaskConfigurator& operator=(TaskConfigurator&& o) noexcept {
+            if (this != &o) {
+                hardware_config  = std::move(o.hardware_config);
+                potential_source = std::move(o.potential_source);
+                algorithm_config = std::move(o.algorithm_config);
+            }
+            return *this;
+        }
+        TaskConfigurator(const TaskConfigurator& o) :
+            std::enable_shared_from_this<TaskConfigurator<FP>>(),
+            hardware_config(clone_or_null(o.hardware_config)),
+            potential_source(clone_or_null(o.potential_source)),
+            algorithm_config(clone_or_null(o.algorithm_config)) {}
+        TaskConfigurator& operator=(const TaskConfigurator& o) {
+            if (this != &o) {
+                hardware_config  = clone_or_null(o.hardware_config);
+                potential_source = clone_or_null(o.potential_source);
+                algorithm_config = clone_or_null(o.algorithm_config);
+            }
+            return *this;
+        }
+        ~TaskConfigurator() = default;
+
+        TaskConfigurator& setHardwareConfig(std::shared_ptr<HardwareConfig<FP>> cfg) {
+            hardware_config = cfg->shared_clone();
+            return *this;
+        }
+        [[nodiscard]] std::shared_ptr<HardwareConfig<FP>> getHardwareConfig() const { return hardware_config; }
+
+        TaskConfigurator& setPotentialSource(std::shared_ptr<PotentialSource<FP>> ps) {
+            potential_source = ps->shared_clone();
+            return *this;
+        }
+        [[nodiscard]] std::shared_ptr<PotentialSource<FP>> getPotentialSource() const { return potential_source; }
+
+        TaskConfigurator& setAlgorithmConfig(std::shared_ptr<AlgorithmConfig<FP>> ac) {
+            algorithm_config = ac->shared_clone();
+            return *this;
+        }
+        [[nodiscard]] std::shared_ptr<AlgorithmConfig<FP>> getAlgorithmConfig() const { return algorithm_config; }
+
+        [[nodiscard]] bool isConfigured() const {
+            return static_cast<bool>(hardware_config) && static_cast<bool>(potential_source) &&
+                   static_cast<bool>(algorithm_config);
+        }
+
+        [[nodiscard]] std::vector<ShaderBuffersRequirements<FP>> getShaderBufferRequirements() const {
+            return algorithm_config->getShaderBufferRequirements(*this);
+        }
+    };
+
+    template <typename FP>
+    std::vector<ShaderBuffersRequirements<FP>>
+    VibwaAlgorithmConfig<FP>::getShaderBufferRequirements(const TaskConfigurator<FP>& config) const {
+        const auto hw = config.getHardwareConfig();
+        ShaderBuffersRequirements<FP> one{};
+        one.stagingBuffersCount               = 1;
+        one.stagingBuffersElementCount        = hw->getPotentialBufferSize();
+        one.gpuOnlyStorageBuffersCount        = 5;
+        one.gpuOnlyStorageBuffersElementCount = hw->getPotentialBufferSize();
+        one.outputBuffersCount                = 1;
+        one.outputBuffersElementCount         = getLevelCount();
+        return std::vector<ShaderBuffersRequirements<FP>>(hw->getGroupSize(), one);
+    }
+} // namespace epseon::gpu::cpp

@@ -82,7 +82,7 @@ struct eps_ctx {
     int         ev_used = 0;
     eps_stats   stats{};
     void*       d_flush = nullptr;
-    int         force_ept = 0, force_stride = 0;  // tuning overrides (EPS_FORCE_EPT / EPS_FORCE_STRIDE)
+    int         force_ept = 0, force_stride = 0, force_warps = 0;  // tuning overrides (EPS_FORCE_EPT / EPS_FORCE_STRIDE)
 };
 
 namespace {
@@ -127,43 +127,46 @@ int fold_events(eps_ctx* ctx) {
 
 size_t sweep_smem_bytes() { return sizeof(double) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
 
-template <int kEpt, int kStride, bool kTails>
+template <int kEpt, int kWarps, int kStride, bool kTails>
 cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp) {
-    constexpr uint32_t per_cta = kConsumerWarps * 32 * kEpt;
+    constexpr uint32_t per_cta = kWarps * 32 * kEpt;
     const uint64_t chunks = (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
     const uint64_t grid   = chunks * n_jobs;
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
-    auto kern = numerov_sweep_kernel<kEpt, kStride, kTails>;
+    auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails>;
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
     if (configured_dev != ctx->dev) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()));
         if (e != cudaSuccess) return e;
         configured_dev = ctx->dev;
     }
-    kern<<<static_cast<unsigned>(grid), kSweepThreads, sweep_smem_bytes(), ctx->stream>>>(
+    kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
         ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->d_nodes.p,
         kTails ? ctx->d_mant.p : nullptr, kTails ? ctx->d_exp.p : nullptr, ctx->d_steps);
     return cudaGetLastError();
 }
 
-template <int kEpt, int kStride>
+template <int kEpt, int kWarps, int kStride>
 cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
-    return tails ? launch_sweep_variant<kEpt, kStride, true>(ctx, j, n, nE, E) : launch_sweep_variant<kEpt, kStride, false>(ctx, j, n, nE, E);
+    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true>(ctx, j, n, nE, E)
+                 : launch_sweep_variant<kEpt, kWarps, kStride, false>(ctx, j, n, nE, E);
 }
 
-template <int kEpt>
+template <int kEpt, int kWarps>
 cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
-    if (stride == 32) return launch_sweep_t<kEpt, 32>(ctx, j, n, nE, E, tails);
-    if (stride == 8) return launch_sweep_t<kEpt, 8>(ctx, j, n, nE, E, tails);
-    return launch_sweep_t<kEpt, 1>(ctx, j, n, nE, E, tails);
+    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails);
+    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails);
+    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails);
 }
 
-// Energies per thread: two independent chains per thread saturate the FP64 pipe with only two
-// warps per scheduler (scripts/microbench.cu); one chain when the row is too short to fill a CTA.
-int pick_ept(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE) {
-    if (ctx->force_ept) return ctx->force_ept;
+// CTA shape (energies per thread, consumer warps).  Register-file bandwidth is the binding
+// resource of the FP64 pipe on B200 (scripts/microbench.cu), so more chains per thread amortise
+// the F-table loads; rows too short to fill such CTAs fall back to smaller shapes.
+struct Shape { int ept, warps; };
+Shape pick_shape(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE) {
+    if (ctx->force_ept) return Shape{ctx->force_ept, ctx->force_warps ? ctx->force_warps : 8};
     (void)n_jobs;
-    return nE > static_cast<uint32_t>(kConsumerWarps * 32) ? 2 : 1;
+    return nE > 256u ? Shape{2, 8} : Shape{1, 8};
 }
 
 // Sign-sampling stride from theta_max^2 = 12 * t_max, t_max = max over rows of s*(E_max - V_min):
@@ -192,10 +195,14 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     }
     cudaEvent_t* pair = ctx->ev[ctx->ev_used++];
     EPS_CUDA(ctx, cudaEventRecord(pair[0], ctx->stream));
-    const int   ept    = pick_ept(ctx, n_jobs, nE);
+    const Shape sh     = pick_shape(ctx, n_jobs, nE);
     const int   stride = pick_stride(ctx, t_max);
-    cudaError_t e = (ept == 2) ? launch_sweep_s<2>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails)
-                               : launch_sweep_s<1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    cudaError_t e;
+    if (sh.ept == 4 && sh.warps == 4) e = launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    else if (sh.ept == 4) e = launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    else if (sh.ept == 2 && sh.warps == 4) e = launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    else if (sh.ept == 2) e = launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
+    else e = launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
     EPS_CUDA(ctx, e);
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
@@ -314,7 +321,11 @@ int eps_ctx_create(int device, eps_ctx** out) {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_steps), sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), 4096)) != cudaSuccess) return bail(e, "cudaMallocHost");
-    if (const char* fe = std::getenv("EPS_FORCE_EPT")) ctx->force_ept = std::atoi(fe) == 2 ? 2 : (std::atoi(fe) == 1 ? 1 : 0);
+    if (const char* fe = std::getenv("EPS_FORCE_EPT")) {
+        const int v = std::atoi(fe);
+        ctx->force_ept = (v == 1 || v == 2 || v == 4) ? v : 0;
+    }
+    if (const char* fw = std::getenv("EPS_FORCE_WARPS")) ctx->force_warps = std::atoi(fw) == 4 ? 4 : 8;
     if (const char* fs = std::getenv("EPS_FORCE_STRIDE")) {
         const int v = std::atoi(fs);
         ctx->force_stride = (v == 1 || v == 8 || v == 32) ? v : 0;
@@ -620,13 +631,13 @@ int eps_l2_flush(eps_ctx* ctx) {
 int eps_fp64_probe(eps_ctx* ctx, double* tflops, float* ms_out) {
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, tflops, EPS_ERR_INVALID, "tflops is null");
-    const int    blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 12;
+    const int    blocks = ctx->sm_count * 8, threads = 256, iters = kProbeIters;
     DevBuf<double> out;
     EPS_CUDA(ctx, out.reserve(static_cast<size_t>(blocks) * threads));
     float best = 1e30f;
-    for (int rep = 0; rep < 5; rep++) {
+    for (int rep = 0; rep < 12; rep++) {
         EPS_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
-        fp64_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, iters, 1.0000001, 1e-9);
+        fp64_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, 1.0000001, 1e-9);
         EPS_CUDA(ctx, cudaGetLastError());
         EPS_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
         EPS_CUDA(ctx, cudaEventSynchronize(ctx->t1));

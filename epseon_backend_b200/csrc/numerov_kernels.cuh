@@ -20,8 +20,8 @@ namespace eps {
 
 constexpr int      kTile          = 2048;  // grid steps per shared-memory stage (16 KiB of F_k)
 constexpr int      kStages        = 4;     // TMA ring depth
-constexpr int      kConsumerWarps = 8;     // 256 * EPT trial energies per CTA
-constexpr int      kSweepThreads  = (kConsumerWarps + 1) * 32;  // + 1 TMA producer warp
+// CTA shape of the sweep: kWarps consumer warps (template parameter) + 1 TMA producer warp,
+// 32 * kWarps * kEpt trial energies per CTA.
 constexpr int      kRenorm        = 128;   // exponent renormalisation period (steps)
 constexpr uint32_t kNone          = 0xffffffffu;
 
@@ -84,6 +84,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: poll with a back-off so the (otherwise idle) producer warp does not
+// steal issue slots from the consumer warps sharing its scheduler (profiles/: a bare
+// try_wait spin was 10 % of all executed instructions).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(2000);
+    }
+}
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA
 // engine; SASS: UBLKCP).  dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
@@ -127,9 +146,9 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // Many-energy sweep: kEpt independent FP64 recurrences per thread, the curve's
 // F table streamed through a kStages-deep shared-memory ring by a TMA producer
 // warp and read by every consumer thread as a warp-broadcast LDS.128 (2 steps).
-//   grid  = n_jobs * chunks_per_job CTAs,  CTA = 8 consumer warps + 1 producer
+//   grid  = n_jobs * chunks_per_job CTAs,  CTA = kWarps consumer warps + 1 producer
 //   smem  = kStages * kTile * 8 B ring + 2*kStages mbarriers
-// Energy j of a CTA's chunk sits in thread (j % 256), chain (j / 256), so the
+// Energy j of a CTA's chunk sits in thread (j % (32 kWarps)), chain (j / (32 kWarps)), so the
 // result stores of every chain are coalesced.
 //
 // Node counting.  The FP64 pipe shares register-file bandwidth with every other
@@ -141,15 +160,15 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // the host only selects kStride = 32 / 8 with a factor-2 margin on theta_max
 // (launch_sweep) and kStride = 1 (per-step bit mask) otherwise.
 // ---------------------------------------------------------------------------
-template <int kEpt, int kStride, bool kTails>
-__global__ void __launch_bounds__(kSweepThreads, 2)
+template <int kEpt, int kWarps, int kStride, bool kTails>
+__global__ void __launch_bounds__((kWarps + 1) * 32, (kEpt * kWarps >= 32) ? 1 : 2)
 numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
                      const Job* __restrict__ jobs, const uint32_t chunks_per_job,
                      const double* __restrict__ Eexp, const uint64_t out_stride,
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                      int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
-    constexpr uint32_t kPerCta = kConsumerWarps * 32 * kEpt;
+    constexpr uint32_t kPerCta = kWarps * 32 * kEpt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double*   ring  = reinterpret_cast<double*>(smem_raw);
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kStages);
@@ -170,19 +189,19 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&empty[s], kWarps);
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
+    if (warp == kWarps) {
         // ===== TMA producer: one elected lane streams the curve through the ring =====
         if (lane == 0) {
             const double* src = F + cv.f_off;
             for (uint32_t t = 0; t < n_tiles; t++) {
                 const uint32_t s = t % kStages;
-                if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) - 1) & 1);
+                if (t >= kStages) mbar_wait_backoff(&empty[s], ((t / kStages) - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], kTile * sizeof(double));
                 tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t) * kTile,
                              kTile * sizeof(double), &full[s]);
@@ -200,7 +219,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     uint32_t n_nodes[kEpt], prev[kEpt];
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
-        uint32_t j = e_base + i * (kConsumerWarps * 32) + warp * 32 + lane;
+        uint32_t j = e_base + i * (kWarps * 32) + warp * 32 + lane;
         if (j >= job.nE) j = job.nE - 1;  // keep the warp converged; result discarded
         double E;
         if (Eexp != nullptr) E = Eexp[job.e_off + j];
@@ -285,7 +304,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
         renorm(c[i], expo[i]);
-        const uint32_t j = e_base + i * (kConsumerWarps * 32) + warp * 32 + lane;
+        const uint32_t j = e_base + i * (kWarps * 32) + warp * 32 + lane;
         if (j < job.nE) {
             const uint64_t o = static_cast<uint64_t>(job_idx) * out_stride + j;
             nodes_out[o] = n_nodes[i];
@@ -455,13 +474,13 @@ __global__ void finalize_levels_kernel(const double* __restrict__ lo, const doub
 // DFMA-saturating probe: measures the FP64 (non-tensor) roofline denominator,
 // which MEASURED_PEAKS.json does not carry.  8 independent chains per thread.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fp64_probe_kernel(double* __restrict__ out, int iters,
-                                                         double x, double y) {
+constexpr int kProbeIters = 4096;
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* __restrict__ out, double x, double y) {
     double a[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
 #pragma unroll 1
-    for (int it = 0; it < iters; it++) {
+    for (int it = 0; it < kProbeIters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++)
 #pragma unroll

@@ -81,6 +81,77 @@ __global__ void __launch_bounds__(256) k_mix(double* out, double F0, double ep0)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mode 4: mix with the F operand read from shared memory as a warp-broadcast LDS.128 per 2 steps
+template <int E>
+__global__ void __launch_bounds__(256) k_mix_lds(double* out, double F0, double ep0) {
+    __shared__ double tile[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) tile[i] = F0 + 1e-12 * i;
+    __syncthreads();
+    double X[E], S[E], ep[E];
+    for (int i = 0; i < E; i++) { X[i] = 1.0; S[i] = 0.0; ep[i] = ep0 * (1 + i + threadIdx.x); }
+#pragma unroll 1
+    for (int it = 0; it < ITERS / 4; it++) {
+#pragma unroll 1
+        for (int k = 0; k < 128; k += 32) {
+            const double2* t2 = reinterpret_cast<const double2*>(tile + ((it * 128 + k) & 2047));
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const double2 ff = t2[p];
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                    const double fp = __dadd_rn(ff.x, ep[i]);
+                    const double Q  = __fma_rn(10.0, X[i], S[i]);
+                    const double Xn = __fma_rn(-fp, Q, X[i]);
+                    S[i] = __dmul_rn(fp, X[i]);
+                    X[i] = Xn;
+                }
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                    const double fp = __dadd_rn(ff.y, ep[i]);
+                    const double Q  = __fma_rn(10.0, X[i], S[i]);
+                    const double Xn = __fma_rn(-fp, Q, X[i]);
+                    S[i] = __dmul_rn(fp, X[i]);
+                    X[i] = Xn;
+                }
+            }
+        }
+        for (int i = 0; i < E; i++) { X[i] = X[i] * 1.3e130; S[i] = S[i] * 1.3e130; }
+    }
+    double s = 0;
+    for (int i = 0; i < E; i++) s += X[i] + S[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// mode 5: F streamed from __constant__ memory: LDCU -> uniform register -> DADD R, R, UR
+__constant__ double cF[8192];
+template <int E>
+__global__ void __launch_bounds__(256) k_const(double* out, double F0, double ep0) {
+    double X[E], S[E], ep[E];
+    for (int i = 0; i < E; i++) { X[i] = 1.0; S[i] = 0.0; ep[i] = ep0 * (1 + i + threadIdx.x) + F0 * 0; }
+#pragma unroll 1
+    for (int it = 0; it < ITERS * 16 / 8192; it++) {
+#pragma unroll 1
+        for (int k = 0; k < 8192; k += 32) {
+#pragma unroll
+            for (int p = 0; p < 32; p++) {
+                const double F = cF[k + p];
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                    const double fp = __dadd_rn(F, ep[i]);
+                    const double Q  = __fma_rn(10.0, X[i], S[i]);
+                    const double Xn = __fma_rn(-fp, Q, X[i]);
+                    S[i] = __dmul_rn(fp, X[i]);
+                    X[i] = Xn;
+                }
+            }
+            if ((k & 127) == 96) for (int i = 0; i < E; i++) { X[i] = X[i] * 1.3e130; S[i] = S[i] * 1.3e130; }
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < E; i++) s += X[i] + S[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename K>
 void run(const char* name, K kern, double ops_per_thread, int blocks, int threads) {
     double* out;
@@ -105,15 +176,35 @@ void run(const char* name, K kern, double ops_per_thread, int blocks, int thread
 }
 
 int main() {
-    for (int bps : {1, 2, 4, 8}) {
+    {
+        static double h[8192];
+        for (int i = 0; i < 8192; i++) h[i] = 0.08333 + 1e-12 * i;
+        cudaMemcpyToSymbol(cF, h, sizeof(h));
+    }
+    for (int bps : {1, 2, 8}) {
         run("dfma shared operands", k_dfma_shared, 64.0 * ITERS, 148 * bps, 256);
         run("dfma 3 distinct regs", k_dfma_3reg, 64.0 * ITERS, 148 * bps, 256);
         run("dadd 2 regs", k_dadd, 64.0 * ITERS, 148 * bps, 256);
         run("mix E=1", k_mix<1, false>, 64.0 * ITERS, 148 * bps, 256);
         run("mix E=2", k_mix<2, false>, 128.0 * ITERS, 148 * bps, 256);
         run("mix E=4", k_mix<4, false>, 256.0 * ITERS, 148 * bps, 256);
+        run("mix E=2 const/LDCU", k_const<2>, 128.0 * ITERS, 148 * bps, 256);
+        run("mix E=1 const/LDCU", k_const<1>, 64.0 * ITERS, 148 * bps, 256);
+        run("mix E=4 const/LDCU", k_const<4>, 256.0 * ITERS, 148 * bps, 256);
+        run("mix E=2 +lds", k_mix_lds<2>, 128.0 * 2 * ITERS, 148 * bps, 256);
+        run("mix E=1 +lds", k_mix_lds<1>, 128.0 * ITERS, 148 * bps, 256);
         run("mix E=2 +shf", k_mix<2, true>, 128.0 * ITERS, 148 * bps, 256);
         run("mix E=4 +shf", k_mix<4, true>, 256.0 * ITERS, 148 * bps, 256);
+    }
+    {   // sustained: 40 back-to-back launches of the pure-DFMA kernel, per-launch time
+        double* out; cudaMalloc(&out, sizeof(double) * 148 * 8 * 256);
+        cudaEvent_t ev[41]; for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0]);
+        for (int r = 0; r < 40; r++) { k_dfma_shared<<<148 * 8, 256>>>(out, 0.08333, 1e-9); cudaEventRecord(ev[r + 1]); }
+        cudaDeviceSynchronize();
+        printf("sustained dfma per-launch ms:");
+        for (int r = 0; r < 40; r++) { float ms; cudaEventElapsedTime(&ms, ev[r], ev[r + 1]); printf(" %.3f", ms); }
+        printf("\n");
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
