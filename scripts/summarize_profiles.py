@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Condense gpurun_out/ artefacts of one GPU call into tracked files under profiles/.
+
+    python scripts/summarize_profiles.py <tag> [--launches F.csv] [--rep F.ncu-rep] [--kernel REGEX]
+                                               [--copy FILE ...]
+
+  --launches  ncu `--metrics gpu__time_duration.sum` CSV  -> profiles/<tag>_launches.md
+              (per-kernel launch count, summed device time, share of the run)
+  --rep       ncu `--set full` report -> profiles/<tag>_ncu.md (key raw metrics per launch, stall
+              reasons, the most-sampled SASS lines); read here with `ncu -i` (no GPU needed)
+  --copy      small text artefacts (bench JSON lines, microbenchmark logs) copied verbatim
+"""
+from __future__ import annotations
+
+import argparse
+import collections
+import csv
+import io
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+PROF = ROOT / "profiles"
+
+RAW_KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "smsp__cycles_active.avg",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def launches_md(tag: str, path: Path) -> None:
+    rows = list(csv.reader(line for line in open(path) if line.startswith('"')))
+    hdr = rows[0]
+    ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ki].split("(")[0]
+        a = agg.setdefault(name, [0, 0.0, set()])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", ""))
+        a[2].add(f"{r[gi]}x{r[bi]}")
+    total = sum(a[1] for a in agg.values())
+    out = [f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`)", "",
+           f"source: `{path.name}`; {len(rows) - 1} launches, {total / 1e6:.3f} ms of device time "
+           "(cold-cache, serialised: compare shares, not absolutes)", "",
+           "| kernel | launches | total ms | share | grid x block |", "|---|---:|---:|---:|---|"]
+    for name, (n, ns, shapes) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        sh = ", ".join(sorted(shapes)[:3]) + (" ..." if len(shapes) > 3 else "")
+        out.append(f"| `{name}` | {n} | {ns / 1e6:.3f} | {100 * ns / total:.1f}% | {sh} |")
+    (PROF / f"{tag}_launches.md").write_text("\n".join(out) + "\n")
+
+
+def _ncu(rep: Path, page: str) -> list[list[str]]:
+    txt = subprocess.run(["ncu", "-i", str(rep), "--page", page, "--csv"], check=True, capture_output=True,
+                         text=True).stdout
+    return list(csv.reader(io.StringIO(txt)))
+
+
+def ncu_md(tag: str, rep: Path) -> None:
+    raw = _ncu(rep, "raw")
+    hdr, units, data = raw[0], raw[1], raw[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    out = [f"# {tag}: ncu `--set full --clock-control none --import-source on`", "", f"source: `{rep.name}` "
+           "(read with `ncu -i ... --page raw|source --csv`)", ""]
+    for r in data:
+        out += [f"## `{r[ix['Kernel Name']].split('(')[0]}`  grid {r[ix['Grid Size']]} block {r[ix['Block Size']]}", "",
+                "| metric | value | unit |", "|---|---:|---|"]
+        for k in RAW_KEYS:
+            if k in ix:
+                out.append(f"| {k} | {r[ix[k]]} | {units[ix[k]]} |")
+        out += ["", "stall reasons (warps per issue-active cycle):", "", "| reason | ratio |", "|---|---:|"]
+        st = []
+        for h, i in ix.items():
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                try:
+                    st.append((float(r[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        for v, name in sorted(st, reverse=True)[:8]:
+            out.append(f"| {name} | {v:.3f} |")
+        out.append("")
+    src = _ncu(rep, "source")
+    # first kernel only: header row is the one starting with "Address"
+    start = next(i for i, r in enumerate(src) if r and r[0] == "Address")
+    shdr = src[start]
+    six = {h: i for i, h in enumerate(shdr)}
+    body = []
+    for r in src[start + 1:]:
+        if not r or r[0] in ("Kernel Name", "Address"):
+            break
+        body.append(r)
+    tot = sum(int(r[six["# Samples"]]) for r in body)
+    out += [f"## most-sampled SASS of the first captured launch ({tot} samples, {len(body)} instructions)", "",
+            "| samples | executed | SASS | top stalls |", "|---:|---:|---|---|"]
+    stall_cols = [h for h in shdr if h.startswith("stall_") and "Not Issued" not in h]
+    for r in sorted(body, key=lambda r: -int(r[six["# Samples"]]))[:24]:
+        stalls = sorted(((int(r[six[c]]), c[6:]) for c in stall_cols if r[six[c]] not in ("0", "")), reverse=True)[:3]
+        out.append(f"| {r[six['# Samples']]} | {r[six['Instructions Executed']]} | `{r[six['Source']].strip()}` | "
+                   + ", ".join(f"{n}={v}" for v, n in stalls) + " |")
+    mix = collections.Counter()
+    for r in body:
+        op = r[six["Source"]].strip().split()
+        op = op[1] if op and op[0].startswith("@") else (op[0] if op else "?")
+        mix[op.split(".")[0]] += int(r[six["Instructions Executed"]])
+    tot_i = sum(mix.values())
+    out += ["", "executed warp-instruction mix: " + ", ".join(f"{k} {100 * v / tot_i:.1f}%" for k, v in mix.most_common(10))]
+    (PROF / f"{tag}_ncu.md").write_text("\n".join(out) + "\n")
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("tag")
+    ap.add_argument("--launches", type=Path)
+    ap.add_argument("--rep", type=Path)
+    ap.add_argument("--copy", type=Path, nargs="*", default=[])
+    a = ap.parse_args()
+    PROF.mkdir(exist_ok=True)
+    if a.launches:
+        launches_md(a.tag, a.launches)
+    if a.rep:
+        ncu_md(a.tag, a.rep)
+    for f in a.copy:
+        shutil.copy(f, PROF / f.name)
+
+
+if __name__ == "__main__":
+    main()
