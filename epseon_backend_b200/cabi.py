@@ -21,7 +21,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
-    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_timer_start", "eps_timer_stop",
+    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_wavefunctions", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
 ]
 
@@ -114,6 +114,7 @@ class Context:
         if rc != EPS_OK:
             raise EpsError(rc, (self.lib.eps_last_error(None) or b"").decode())
         self.n_curves = 0
+        self.n_points = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -142,6 +143,7 @@ class Context:
         self._ck(self.lib.eps_set_potentials(self.h, _ptr(V, np.float64), C.c_uint32(V.shape[0]),
                                              C.c_uint32(V.shape[1]), _ptr(scale, np.float64)))
         self.n_curves = V.shape[0]
+        self.n_points = V.shape[1]
 
     def curve_info(self, curve: int = 0) -> CurveInfo:
         ci = CurveInfo()
@@ -184,6 +186,18 @@ class Context:
                                            _ptr(hi, np.float64), _ptr(levels, np.float64),
                                            _ptr(widths, np.float64), _ptr(nb, np.uint32)))
         return levels, widths, nb
+
+    def wavefunctions(self, E, grid_step):
+        """E[nC, nlev] (NaN rows skipped) -> (psi[nC, nlev, N], match_index[nC, nlev])"""
+        E = np.ascontiguousarray(np.atleast_2d(E), dtype=np.float64)
+        assert E.shape[0] == self.n_curves
+        h = _vec(grid_step, self.n_curves)
+        N = self.n_points
+        psi = np.empty((self.n_curves, E.shape[1], N), dtype=np.float64)
+        mi = np.empty(E.shape, dtype=np.uint32)
+        self._ck(self.lib.eps_wavefunctions(self.h, _ptr(E, np.float64), C.c_uint32(E.shape[1]),
+                                            _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
+        return psi, mi
 
     def timer_start(self):
         self._ck(self.lib.eps_timer_start(self.h))

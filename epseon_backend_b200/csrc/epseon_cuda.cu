@@ -76,6 +76,11 @@ struct eps_ctx {
     DevBuf<uint32_t> d_state, d_jstar, d_nbelow, d_nactive;
     uint32_t*        h_pinned = nullptr;  // small pinned scratch (readbacks)
 
+    // wavefunction scratch
+    DevBuf<double>   d_wfE, d_wfraw, d_wfin, d_wfpsi, d_wfh;
+    DevBuf<int32_t>  d_wfbexp, d_wfinexp;
+    DevBuf<uint32_t> d_wfmatch;
+
     // measurement
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEvent_t ev[kEventPairs][2];
@@ -356,6 +361,14 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_jstar.release();
         ctx->d_nbelow.release();
         ctx->d_nactive.release();
+        ctx->d_wfE.release();
+        ctx->d_wfraw.release();
+        ctx->d_wfin.release();
+        ctx->d_wfpsi.release();
+        ctx->d_wfh.release();
+        ctx->d_wfbexp.release();
+        ctx->d_wfinexp.release();
+        ctx->d_wfmatch.release();
         if (ctx->d_steps) cudaFree(ctx->d_steps);
         if (ctx->d_flush) cudaFree(ctx->d_flush);
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -582,6 +595,59 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         ctx->stats.d2h_bytes += nC * sizeof(uint32_t);
     }
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EPS_OK;
+}
+
+int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
+                      double* psi, uint32_t* match_index) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
+    EPS_REQUIRE(ctx, E && grid_step && psi && n_levels >= 1, EPS_ERR_INVALID, "null argument / no levels");
+    const uint64_t items64 = static_cast<uint64_t>(ctx->nC) * n_levels;
+    EPS_REQUIRE(ctx, items64 < 65536ull * 16, EPS_ERR_INVALID, "too many (curve, level) pairs in one call");
+    const uint32_t items = static_cast<uint32_t>(items64);
+    for (uint32_t c = 0; c < ctx->nC; c++) {
+        EPS_REQUIRE(ctx, std::isfinite(grid_step[c]) && grid_step[c] > 0.0, EPS_ERR_INVALID, "grid_step must be positive");
+        for (uint32_t l = 0; l < n_levels; l++) {
+            const double e = E[static_cast<size_t>(c) * n_levels + l];
+            if (e != e) continue;
+            EPS_REQUIRE(ctx, range_ok(ctx->curves[c], e, e), EPS_ERR_RANGE,
+                        "level energy outside the validity window |s (E - V_min)| <= 0.5");
+        }
+    }
+    const uint32_t bstride = static_cast<uint32_t>(ctx->slot / kRenorm) + 8;
+    const size_t   n_psi   = static_cast<size_t>(items) * ctx->N;
+    EPS_REQUIRE(ctx, n_psi * sizeof(double) <= (64ull << 30), EPS_ERR_NOMEM, "wavefunction output above 64 GiB: split the call");
+    EPS_CUDA(ctx, ctx->d_wfE.reserve(items));
+    EPS_CUDA(ctx, ctx->d_wfh.reserve(ctx->nC));
+    EPS_CUDA(ctx, ctx->d_wfraw.reserve(static_cast<size_t>(items) * ctx->slot));
+    EPS_CUDA(ctx, ctx->d_wfbexp.reserve(static_cast<size_t>(items) * 2 * bstride));
+    EPS_CUDA(ctx, ctx->d_wfmatch.reserve(items));
+    EPS_CUDA(ctx, ctx->d_wfin.reserve(items));
+    EPS_CUDA(ctx, ctx->d_wfinexp.reserve(items));
+    EPS_CUDA(ctx, ctx->d_wfpsi.reserve(n_psi));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_wfE.p, E, items * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_wfh.p, grid_step, ctx->nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (items + static_cast<uint64_t>(ctx->nC)) * sizeof(double);
+    wavefunction_march_kernel<<<dim3(items, 2), kWfThreads, 0, ctx->stream>>>(
+        ctx->d_F.p, ctx->d_curves.p, ctx->d_wfE.p, n_levels, ctx->slot, bstride, ctx->d_wfraw.p, ctx->d_wfbexp.p,
+        ctx->d_wfmatch.p, ctx->d_wfin.p, ctx->d_wfinexp.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    wavefunction_finish_kernel<<<items, kWfThreads, 0, ctx->stream>>>(
+        ctx->d_curves.p, n_levels, ctx->N, ctx->d_wfh.p, ctx->slot, bstride, ctx->d_wfraw.p, ctx->d_wfbexp.p,
+        ctx->d_wfmatch.p, ctx->d_wfin.p, ctx->d_wfinexp.p, ctx->d_wfpsi.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches += 2;
+    EPS_CUDA(ctx, cudaMemcpyAsync(psi, ctx->d_wfpsi.p, n_psi * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n_psi * sizeof(double);
+    if (match_index) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(match_index, ctx->d_wfmatch.p, items * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += items * sizeof(uint32_t);
+    }
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (match_index)  // report the matching point as an index of the full r grid
+        for (uint32_t it = 0; it < items; it++)
+            if (match_index[it] != kNone) match_index[it] += ctx->curves[it / n_levels].i0;
     return EPS_OK;
 }
 

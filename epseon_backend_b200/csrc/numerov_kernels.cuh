@@ -13,6 +13,7 @@
 // contracts or re-associates, so node counts AND tails are bit-identical to
 // the oracle.
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -468,6 +469,203 @@ __global__ void finalize_levels_kernel(const double* __restrict__ lo, const doub
     if (idx >= total) return;
     levels[idx] = __dmul_rn(0.5, __dadd_rn(lo[idx], hi[idx]));
     widths[idx] = __dsub_rn(hi[idx], lo[idx]);
+}
+
+// ---------------------------------------------------------------------------
+// N7: wavefunctions of located levels (spec DESIGN.md section 3.6; oracle:
+// orc_wavefunction).  Few (curve, level) items, each a strictly serial three-term
+// recurrence u_{k+1} = fma(c_k, u_k, -u_{k-1}), c_k = 1/fp_k - 10, so the design
+// keeps ONE dependent DFMA per grid step on the critical path: the 256 threads of
+// the CTA turn a 1024-step tile of the F table into (c_k, r_k = 1/fp_k) in shared
+// memory (the FP64 divisions run in parallel, off the chain), one thread marches
+// the tile, and all threads form psi_k = u_k r_k and store it coalesced.
+//   grid = (n_items, 2): blockIdx.y = 0 outward (k = 0..m), 1 inward (k = n-1..m).
+// ---------------------------------------------------------------------------
+constexpr int kWfTile    = 1024;
+constexpr int kWfThreads = 256;
+
+__device__ __forceinline__ void renorm_pair(double& a, double& b, int& expo) {
+    const uint32_t ex = (static_cast<uint32_t>(__double2hiint(a)) >> 20) & 0x7ffu;
+    if (ex != 0) {
+        const double sc = __hiloint2double(static_cast<int>((2046u - ex) << 20), 0);
+        a = __dmul_rn(a, sc);
+        b = __dmul_rn(b, sc);
+        expo += static_cast<int>(ex) - 1023;
+    }
+}
+
+// raw[item][k]: psi_k in the scale of its 128-block; bexp[item][dir][block]: cumulative
+// exponent of that block; match[item]: m (kNone: no classically allowed point);
+// in_at_m[item]: the inward branch's value at m, in_exp_m[item] its block exponent.
+__global__ void __launch_bounds__(kWfThreads)
+wavefunction_march_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
+                          const double* __restrict__ E, uint32_t n_lev, uint64_t raw_stride,
+                          uint32_t bexp_stride, double* __restrict__ raw, int32_t* __restrict__ bexp,
+                          uint32_t* __restrict__ match, double* __restrict__ in_at_m,
+                          int32_t* __restrict__ in_exp_m) {
+    __shared__ double   c_s[kWfTile];  // c_k, overwritten by u_k during the march
+    __shared__ double   r_s[kWfTile];
+    __shared__ int32_t  e_s[kWfTile / kRenorm];
+    __shared__ uint32_t red[kWfThreads / 32];
+    __shared__ uint32_t m_sh;
+
+    const uint32_t item = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x;
+    const CurveDev cv   = curves[item / n_lev];
+    const double   En   = E[item];
+    const uint32_t n    = cv.n_steps;
+    const double*  Fc   = F + cv.f_off;
+    const double   ep   = __ddiv_rn(__dmul_rn(cv.s, En), 12.0);
+
+    // m = max{k : F_k + ep > 1/12} (+1 so that 0 means "none")
+    uint32_t best = 0;
+    if (En == En && n >= 3)
+        for (uint32_t k = tid; k < n; k += kWfThreads)
+            if (__dadd_rn(Fc[k], ep) > 1.0 / 12.0) best = k + 1;
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t b = 0;
+        for (int w = 0; w < kWfThreads / 32; w++) b = max(b, red[w]);
+        m_sh = b;
+    }
+    __syncthreads();
+    if (m_sh == 0) {
+        if (tid == 0 && dir == 0) match[item] = kNone;
+        return;
+    }
+    uint32_t m = m_sh - 1;
+    m          = m < 1 ? 1 : m;
+    m          = m > n - 2 ? n - 2 : m;
+    if (tid == 0 && dir == 0) match[item] = m;
+
+    const uint32_t count = dir == 0 ? m + 1 : n - m;
+    double*        out   = raw + static_cast<uint64_t>(item) * raw_stride;
+    int32_t*       bx    = bexp + (static_cast<uint64_t>(item) * 2 + dir) * bexp_stride;
+    double         u_cur = 0.0, u_prev = 0.0;  // live in thread 0 only
+    int            cum   = 0;
+
+    for (uint32_t j0 = 0; j0 < count; j0 += kWfTile) {
+        const uint32_t nj = min(static_cast<uint32_t>(kWfTile), count - j0);
+        for (uint32_t jj = tid; jj < nj; jj += kWfThreads) {
+            const uint32_t k  = dir == 0 ? j0 + jj : n - 1 - (j0 + jj);
+            const double   fp = __dadd_rn(Fc[k], ep);
+            const double   r  = __ddiv_rn(1.0, fp);
+            r_s[jj]           = r;
+            c_s[jj]           = __dsub_rn(r, 10.0);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (j0 == 0) {
+                const uint32_t k0 = dir == 0 ? 0 : n - 1;
+                u_cur             = __dadd_rn(Fc[k0], ep);
+            }
+            for (uint32_t b0 = 0; b0 < nj; b0 += kRenorm) {
+                if (j0 + b0 > 0) renorm_pair(u_cur, u_prev, cum);
+                e_s[b0 / kRenorm] = cum;
+                const uint32_t nb = min(static_cast<uint32_t>(kRenorm), nj - b0);
+#pragma unroll 8
+                for (uint32_t q = 0; q < nb; q++) {
+                    const double c  = c_s[b0 + q];
+                    c_s[b0 + q]     = u_cur;
+                    const double un = __fma_rn(c, u_cur, -u_prev);
+                    u_prev          = u_cur;
+                    u_cur           = un;
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t jj = tid; jj < nj; jj += kWfThreads) {
+            const uint32_t k = dir == 0 ? j0 + jj : n - 1 - (j0 + jj);
+            const double   a = __dmul_rn(c_s[jj], r_s[jj]);
+            if (dir == 1 && k == m) {
+                in_at_m[item]  = a;
+                in_exp_m[item] = e_s[jj / kRenorm];
+            } else {
+                out[k] = a;
+            }
+        }
+        if (tid < (nj + kRenorm - 1) / kRenorm) bx[j0 / kRenorm + tid] = e_s[tid];
+        __syncthreads();
+    }
+}
+
+// Matching, common binary scale, normalisation; psi[item][0..n_points) on the full grid.
+__global__ void __launch_bounds__(kWfThreads)
+wavefunction_finish_kernel(const CurveDev* __restrict__ curves, uint32_t n_lev, uint32_t n_points,
+                           const double* __restrict__ grid_step, uint64_t raw_stride,
+                           uint32_t bexp_stride, const double* __restrict__ raw,
+                           const int32_t* __restrict__ bexp, const uint32_t* __restrict__ match,
+                           const double* __restrict__ in_at_m, const int32_t* __restrict__ in_exp_m,
+                           double* __restrict__ psi) {
+    __shared__ int    red_i[kWfThreads / 32];
+    __shared__ double red_d[kWfThreads / 32];
+    __shared__ int    emax_sh;
+    __shared__ double nrm_sh;
+    const uint32_t item = blockIdx.x, tid = threadIdx.x;
+    const uint32_t curve = item / n_lev;
+    const CurveDev cv    = curves[curve];
+    const uint32_t n = cv.n_steps, i0 = cv.i0, m = match[item];
+    double*        dst = psi + static_cast<uint64_t>(item) * n_points;
+    if (m == kNone) {
+        for (uint32_t i = tid; i < n_points; i += kWfThreads) dst[i] = 0.0;
+        return;
+    }
+    const double*  a_raw = raw + static_cast<uint64_t>(item) * raw_stride;
+    const int32_t* bx_o  = bexp + static_cast<uint64_t>(item) * 2 * bexp_stride;
+    const int32_t* bx_i  = bx_o + bexp_stride;
+    const int      c_out_m = bx_o[m / kRenorm], c_in_m = in_exp_m[item];
+    const double   a_in = in_at_m[item];
+    const double   rho  = (a_in != 0.0) ? __ddiv_rn(a_raw[m], a_in) : 1.0;
+
+    auto value = [&](uint32_t k, int& c) -> double {
+        if (k <= m) {
+            c = bx_o[k / kRenorm];
+            return a_raw[k];
+        }
+        c = bx_i[(n - 1 - k) / kRenorm] - c_in_m + c_out_m;
+        return __dmul_rn(a_raw[k], rho);
+    };
+    // largest binary exponent
+    int emax = INT_MIN;
+    for (uint32_t k = tid; k < n; k += kWfThreads) {
+        int          c;
+        const double a = value(k, c);
+        if (a != 0.0) emax = max(emax, c + ilogb(a));
+    }
+    for (int o = 16; o > 0; o >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    if ((tid & 31) == 0) red_i[tid >> 5] = emax;
+    __syncthreads();
+    if (tid == 0) {
+        int e = INT_MIN;
+        for (int w = 0; w < kWfThreads / 32; w++) e = max(e, red_i[w]);
+        emax_sh = e;
+    }
+    __syncthreads();
+    emax = emax_sh;
+    // common scale + sum of squares
+    double sum = 0.0;
+    for (uint32_t k = tid; k < n; k += kWfThreads) {
+        int          c;
+        const double a  = value(k, c);
+        long long    sh = static_cast<long long>(c) - emax;
+        if (sh < -2200) sh = -2200;
+        const double v = scalbn(a, static_cast<int>(sh));
+        dst[i0 + k]    = v;
+        sum            = __fma_rn(v, v, sum);
+    }
+    for (int o = 16; o > 0; o >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    if ((tid & 31) == 0) red_d[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kWfThreads / 32; w++) t = __dadd_rn(t, red_d[w]);
+        nrm_sh = __dsqrt_rn(__dmul_rn(grid_step[curve], t));
+    }
+    __syncthreads();
+    const double nrm = nrm_sh;
+    for (uint32_t i = tid; i < n_points; i += kWfThreads)
+        dst[i] = (i >= i0 && i < i0 + n) ? __ddiv_rn(dst[i], nrm) : 0.0;
 }
 
 // ---------------------------------------------------------------------------

@@ -142,6 +142,17 @@ int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint
 int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo,
                      const double* E_hi, double* levels, double* widths, uint32_t* n_below);
 
+/* ---- normalised wavefunctions of located levels (N7; the reference plans no such
+ * output -- additive).  E[n_curves][n_levels] (host; NaN entries give
+ * a zero row), grid_step[n_curves] = h of every curve (for the norm
+ * integral h * sum psi^2 = 1).  Outputs (host):
+ *   psi[n_curves][n_levels][n_points]  on the full r grid (zero outside the
+ *     integration window), positive on the first lobe;
+ *   match_index[n_curves][n_levels]    grid index of the outward/inward matching
+ *     point, UINT32_MAX for skipped rows (may be NULL). */
+int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
+                      double* psi, uint32_t* match_index);
+
 /* ---- measurement helpers (bench.py / tests) ------------------------------- */
 int eps_timer_start(eps_ctx* ctx);
 int eps_timer_stop(eps_ctx* ctx, float* ms);

@@ -301,3 +301,82 @@ int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, d
     free(act);
     return (int)round;
 }
+
+/* N7.  Normalised wavefunction of one level at energy E on the integration
+ * window (psi[0..n_steps), psi_k = psi(r_{i0+k}); Dirichlet zeros at k = -1 and
+ * k = n_steps).  DESIGN.md section 3.6:
+ *   fp_k = F_k + e/12,  r_k = 1/fp_k,  c_k = r_k - 10;
+ *   the Numerov variable u_k = fp_k psi_k obeys  u_{k+1} = fma(c_k, u_k, -u_{k-1});
+ *   outward march k = 0..m from (u_{-1}, u_0) = (0, fp_0), inward march
+ *   k = n-1..m from (u_n, u_{n-1}) = (0, fp_{n-1}), psi_k = u_k * r_k;
+ *   m = outer classical turning point = max{k : fp_k > 1/12}, clamped to [1, n-2];
+ *   (u_cur, u_prev) rescaled by an exact power of two every 128 march steps,
+ *   the cumulative exponent kept per 128-block;
+ *   the inward branch is scaled by psi_out(m)/psi_in(m); all values are
+ *   referred to the largest binary exponent, then  psi /= sqrt(h * sum psi^2).
+ * The outward branch starts positive, so psi > 0 on its first lobe.
+ * Returns m, or -1 when E lies below the whole table (psi filled with zeros). */
+int64_t orc_wavefunction(const double* F, uint32_t n_steps, double s, double E, double h,
+                         double* psi) {
+    const uint32_t n  = n_steps;
+    const double   ep = (s * E) / 12.0;
+    int64_t        m  = -1;
+    for (uint32_t k = 0; k < n; k++) psi[k] = 0.0;
+    if (!(E == E) || n < 3) return -1;
+    for (uint32_t k = 0; k < n; k++)
+        if (F[k] + ep > 1.0 / 12.0) m = k;
+    if (m < 0) return -1;
+    if (m < 1) m = 1;
+    if (m > (int64_t)n - 2) m = (int64_t)n - 2;
+    int32_t* cexp = (int32_t*)malloc(sizeof(int32_t) * n);
+    double   a_in_m = 0.0;
+    int32_t  c_in_m = 0, c_out_m = 0;
+    for (int dir = 0; dir < 2; dir++) {
+        const uint32_t count = dir == 0 ? (uint32_t)m + 1 : n - (uint32_t)m;
+        double         u_cur = 0.0, u_prev = 0.0;
+        int32_t        cum = 0;
+        for (uint32_t j = 0; j < count; j++) {
+            const uint32_t k  = dir == 0 ? j : n - 1 - j;
+            const double   fp = F[k] + ep;
+            const double   r  = 1.0 / fp;
+            const double   c  = r - 10.0;
+            if (j == 0) u_cur = fp;
+            if (j > 0 && (j % ORC_RENORM_PERIOD) == 0) renorm(&u_cur, &u_prev, &cum);
+            const double a = u_cur * r;
+            if (dir == 1 && k == (uint32_t)m) {
+                a_in_m = a;
+                c_in_m = cum;
+            } else {
+                psi[k]  = a;
+                cexp[k] = cum;
+            }
+            if (dir == 0 && k == (uint32_t)m) c_out_m = cum;
+            const double un = fma(c, u_cur, -u_prev);
+            u_prev          = u_cur;
+            u_cur           = un;
+        }
+    }
+    const double rho = (a_in_m != 0.0) ? psi[m] / a_in_m : 1.0;
+    int32_t      emax = INT32_MIN;
+    for (uint32_t k = 0; k < n; k++) {
+        if (k > (uint32_t)m) {
+            psi[k]  = psi[k] * rho;
+            cexp[k] = cexp[k] - c_in_m + c_out_m;
+        }
+        if (psi[k] != 0.0) {
+            const int32_t e = cexp[k] + (int32_t)ilogb(psi[k]);
+            if (e > emax) emax = e;
+        }
+    }
+    double sum = 0.0;
+    for (uint32_t k = 0; k < n; k++) {
+        int64_t sh = (int64_t)cexp[k] - (int64_t)emax;
+        if (sh < -2200) sh = -2200;
+        psi[k] = scalbn(psi[k], (int)sh);
+        sum    = fma(psi[k], psi[k], sum);
+    }
+    const double nrm = sqrt(h * sum);
+    for (uint32_t k = 0; k < n; k++) psi[k] = psi[k] / nrm;
+    free(cexp);
+    return m;
+}

@@ -75,6 +75,8 @@ class Oracle:
                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                        C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64)]
+        L.orc_wavefunction.restype = C.c_int64
+        L.orc_wavefunction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, _f64p]
 
     @property
     def threads(self) -> int:
@@ -134,3 +136,9 @@ class Oracle:
                                            rel_tol, max_rounds, levels, widths, C.byref(nb),
                                            C.byref(st))
         return levels, widths, nb.value, rounds, st.value
+
+    def wavefunction(self, AB, s, E, h):
+        """-> (psi[n_steps] on the integration window, match index m or -1)"""
+        psi = np.empty(AB.size, dtype=np.float64)
+        m = self.lib.orc_wavefunction(AB, AB.size, s, float(E), float(h), psi)
+        return psi, int(m)
