@@ -14,7 +14,7 @@ LIB_DIR = PKG / "lib"
 CUDA_LIB = LIB_DIR / "libepseon_cuda.so"
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
 ]
 GXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"

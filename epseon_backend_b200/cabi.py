@@ -21,7 +21,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
-    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_wavefunctions", "eps_timer_start", "eps_timer_stop",
+    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_wavefunctions", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
 ]
 
@@ -198,6 +198,17 @@ class Context:
         self._ck(self.lib.eps_wavefunctions(self.h, _ptr(E, np.float64), C.c_uint32(E.shape[1]),
                                             _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
         return psi, mi
+
+    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT = 1, 2
+    CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED = 1, 2
+
+    def set_option(self, option: int, value: int) -> None:
+        self._ck(self.lib.eps_set_option(self.h, C.c_int(option), C.c_int64(value)))
+
+    def counter(self, which: int) -> int:
+        v = C.c_uint64()
+        self._ck(self.lib.eps_get_counter(self.h, C.c_int(which), C.byref(v)))
+        return v.value
 
     def timer_start(self):
         self._ck(self.lib.eps_timer_start(self.h))

@@ -76,6 +76,17 @@ struct eps_ctx {
     DevBuf<uint32_t> d_state, d_jstar, d_nbelow, d_nactive;
     uint32_t*        h_pinned = nullptr;  // small pinned scratch (readbacks)
 
+    // transfer-matrix (scan) path scratch + policy
+    DevBuf<double>   d_segXA, d_segSA, d_segXB, d_segSB, d_fixm, d_fixE;
+    DevBuf<int32_t>  d_segeA, d_segeB, d_fixe;
+    DevBuf<uint32_t> d_segnA, d_fixn, d_nflag;
+    DevBuf<uint2>    d_flagged;
+    DevBuf<Job>      d_jobs_fix;
+    uint32_t         n_tiles_max  = 0;   // over the resident curves
+    int64_t          opt_scan_segments = 0;  // 0 auto, 1 never, >= 2 forced segment count
+    int64_t          opt_scan_exact    = 1;  // 1: eps_solve_levels also recomputes flagged energies sequentially
+    uint64_t         scan_launches = 0, scan_flagged = 0;
+
     // wavefunction scratch
     DevBuf<double>   d_wfE, d_wfraw, d_wfin, d_wfpsi, d_wfh;
     DevBuf<int32_t>  d_wfbexp, d_wfinexp;
@@ -132,13 +143,20 @@ int fold_events(eps_ctx* ctx) {
 
 size_t sweep_smem_bytes() { return sizeof(double) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
 
-template <int kEpt, int kWarps, int kStride, bool kTails>
-cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp) {
-    constexpr uint32_t per_cta = kWarps * 32 * kEpt;
+struct SweepOut {  // device pointers of one sweep's results
+    uint32_t* nodes;
+    double*   mant;
+    int32_t*  expo;
+};
+
+template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan>
+cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
+                                 const SweepOut& out, uint32_t n_seg, uint32_t tiles_per_seg, const SegOut& so) {
+    constexpr uint32_t per_cta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
     const uint64_t chunks = (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
-    const uint64_t grid   = chunks * n_jobs;
+    const uint64_t grid   = chunks * n_jobs * (kScan ? n_seg : 1u);
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
-    auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails>;
+    auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan>;
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
     if (configured_dev != ctx->dev) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()));
@@ -146,22 +164,23 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
         configured_dev = ctx->dev;
     }
     kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
-        ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->d_nodes.p,
-        kTails ? ctx->d_mant.p : nullptr, kTails ? ctx->d_exp.p : nullptr, ctx->d_steps);
+        ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
+        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so);
     return cudaGetLastError();
 }
 
 template <int kEpt, int kWarps, int kStride>
-cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
-    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true>(ctx, j, n, nE, E)
-                 : launch_sweep_variant<kEpt, kWarps, kStride, false>(ctx, j, n, nE, E);
+cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
+    const SegOut none{};
+    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true, false>(ctx, j, n, nE, E, out, 1, 0, none)
+                 : launch_sweep_variant<kEpt, kWarps, kStride, false, false>(ctx, j, n, nE, E, out, 1, 0, none);
 }
 
 template <int kEpt, int kWarps>
-cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails) {
-    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails);
-    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails);
-    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails);
+cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
+    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails, out);
+    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails, out);
+    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails, out);
 }
 
 // CTA shape (energies per thread, consumer warps).  Register-file bandwidth is the binding
@@ -184,15 +203,116 @@ int pick_stride(const eps_ctx* ctx, double t_max) {
     return 1;
 }
 
+cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
+                              bool tails, int stride, const SweepOut& out) {
+    const Shape sh = pick_shape(ctx, n_jobs, nE);
+    if (sh.ept == 4 && sh.warps == 4) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    if (sh.ept == 4) return launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    if (sh.ept == 2 && sh.warps == 4) return launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    if (sh.ept == 2) return launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    return launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+}
+
+// Transfer-matrix (scan) policy.  A sweep of E_tot = n_jobs * nE energies occupies
+// ceil(E_tot / 512) SMs with the sequential kernel; when that leaves most of the GPU idle on a
+// long grid, the grid is cut into n_seg segments of whole tiles so that about two 256-energy CTAs
+// run per SM.  The scan path executes 7 instead of 4 FP64 instructions per (energy, step) and
+// gains n_seg-fold parallelism.  Returns 1 for "sequential".
+constexpr uint32_t kScanMinTiles = 32;   // auto mode: grids of >= 65 536 steps only
+constexpr uint32_t kScanMaxSeg   = 64;
+uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool tails) {
+    const uint32_t n_tiles = ctx->n_tiles_max;
+    if (ctx->opt_scan_segments == 1 || n_tiles < 2) return 1;
+    if (ctx->opt_scan_segments >= 2)
+        return static_cast<uint32_t>(std::min<int64_t>({ctx->opt_scan_segments, n_tiles, kScanMaxSeg}));
+    if (tails || n_tiles < kScanMinTiles) return 1;  // tails: only the sequential march reproduces the oracle's bits
+    const uint64_t e_tot = static_cast<uint64_t>(n_jobs) * nE;
+    if ((e_tot + 511) / 512 >= static_cast<uint64_t>(ctx->sm_count) / 2) return 1;
+    const uint64_t ctas256 = static_cast<uint64_t>(n_jobs) * ((nE + 255) / 256);
+    const uint64_t s       = std::min<uint64_t>({2ull * ctx->sm_count / ctas256, n_tiles, kScanMaxSeg});
+    return s >= 3 ? static_cast<uint32_t>(s) : 1u;
+}
+
+int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp, bool tails,
+                int stride, uint32_t n_seg, bool fix_flagged, const SweepOut& out) {
+    const uint32_t tiles_per_seg = (ctx->n_tiles_max + n_seg - 1) / n_seg;
+    const size_t   n_so          = static_cast<size_t>(n_jobs) * n_seg * nE;
+    EPS_CUDA(ctx, ctx->d_segXA.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segSA.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segXB.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segSB.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segeA.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segeB.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_segnA.reserve(n_so));
+    EPS_CUDA(ctx, ctx->d_nflag.reserve(1));
+    const uint32_t cap = 1u << 16;
+    EPS_CUDA(ctx, ctx->d_flagged.reserve(cap));
+    const SegOut so{ctx->d_segXA.p, ctx->d_segSA.p, ctx->d_segXB.p, ctx->d_segSB.p, ctx->d_segeA.p, ctx->d_segeB.p, ctx->d_segnA.p};
+    cudaError_t e;
+    if (stride == 32) e = launch_sweep_variant<2, 8, 32, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    else if (stride == 8) e = launch_sweep_variant<2, 8, 8, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    else e = launch_sweep_variant<2, 8, 1, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    EPS_CUDA(ctx, e);
+    EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nflag.p, 0, sizeof(uint32_t), ctx->stream));
+    segment_combine_kernel<<<dim3((nE + 127) / 128, n_jobs), 128, 0, ctx->stream>>>(
+        so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
+        ctx->d_nflag.p, ctx->d_flagged.p, cap);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    ctx->scan_launches++;
+    if (!fix_flagged) return EPS_OK;
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_nflag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += sizeof(uint32_t);
+    const uint32_t n_flag = ctx->h_pinned[8];
+    if (n_flag == 0) return EPS_OK;
+    ctx->scan_flagged += n_flag;
+    if (n_flag > cap) {  // pathological: every energy ill-conditioned -> redo the whole sweep sequentially
+        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out));
+        return EPS_OK;
+    }
+    EPS_CUDA(ctx, ctx->d_jobs_fix.reserve(n_flag));
+    EPS_CUDA(ctx, ctx->d_fixn.reserve(n_flag));
+    EPS_CUDA(ctx, ctx->d_fixm.reserve(n_flag));
+    EPS_CUDA(ctx, ctx->d_fixe.reserve(n_flag));
+    EPS_CUDA(ctx, ctx->d_fixE.reserve(n_flag));
+    // one curve resident: pack the flagged energies into ONE explicit-energy row (512 per CTA);
+    // several curves: one single-energy row per flagged item (rare, small)
+    const bool packed = ctx->nC == 1;
+    make_fixup_jobs_kernel<<<(n_flag + 127) / 128, 128, 0, ctx->stream>>>(d_jobs, d_Eexp, ctx->d_flagged.p, n_flag, packed ? 1 : 0,
+                                                                         ctx->d_jobs_fix.p, ctx->d_fixE.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    const SweepOut fix{ctx->d_fixn.p, ctx->d_fixm.p, ctx->d_fixe.p};
+    if (packed) EPS_CUDA(ctx, launch_sequential(ctx, ctx->d_jobs_fix.p, 1, n_flag, ctx->d_fixE.p, tails, stride, fix));
+    else EPS_CUDA(ctx, launch_sequential(ctx, ctx->d_jobs_fix.p, n_flag, 1, nullptr, tails, stride, fix));
+    scatter_fixup_kernel<<<(n_flag + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_flagged.p, n_flag, nE, ctx->d_fixn.p, ctx->d_fixm.p, ctx->d_fixe.p,
+                                                                       out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches += 2;
+    return EPS_OK;
+}
+
 // Launch the sweep over n_jobs rows of nE energies each (jobs already on device).
-// t_max = max over the rows of s * (E_max - V_min) (see pick_stride).
+// t_max = max over the rows of s * (E_max - V_min) (see pick_stride).  fix_flagged: on the scan
+// path, recompute ill-conditioned energies with the sequential kernel (one host sync).
 int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                 bool tails, double t_max) {
+                 bool tails, double t_max, bool fix_flagged = true) {
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
     if (tails) {
         EPS_CUDA(ctx, ctx->d_mant.reserve(n_out));
         EPS_CUDA(ctx, ctx->d_exp.reserve(n_out));
+    }
+    const uint32_t n_seg = pick_segments(ctx, n_jobs, nE, tails);
+    if (n_seg >= 2) {  // reserve before the timed region
+        const size_t n_so = n_out * n_seg;
+        EPS_CUDA(ctx, ctx->d_segXA.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segSA.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segXB.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segSB.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segeA.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segeB.reserve(n_so));
+        EPS_CUDA(ctx, ctx->d_segnA.reserve(n_so));
     }
     if (ctx->ev_used == kEventPairs) {
         int rc = fold_events(ctx);
@@ -200,15 +320,13 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     }
     cudaEvent_t* pair = ctx->ev[ctx->ev_used++];
     EPS_CUDA(ctx, cudaEventRecord(pair[0], ctx->stream));
-    const Shape sh     = pick_shape(ctx, n_jobs, nE);
-    const int   stride = pick_stride(ctx, t_max);
-    cudaError_t e;
-    if (sh.ept == 4 && sh.warps == 4) e = launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
-    else if (sh.ept == 4) e = launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
-    else if (sh.ept == 2 && sh.warps == 4) e = launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
-    else if (sh.ept == 2) e = launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
-    else e = launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails);
-    EPS_CUDA(ctx, e);
+    const int      stride = pick_stride(ctx, t_max);
+    const SweepOut out{ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p};
+    if (n_seg >= 2) {
+        if (int rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out)) return rc;
+    } else {
+        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out));
+    }
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
     return EPS_OK;
@@ -361,6 +479,10 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_jstar.release();
         ctx->d_nbelow.release();
         ctx->d_nactive.release();
+        ctx->d_segXA.release(); ctx->d_segSA.release(); ctx->d_segXB.release(); ctx->d_segSB.release();
+        ctx->d_fixm.release(); ctx->d_fixE.release(); ctx->d_segeA.release(); ctx->d_segeB.release(); ctx->d_fixe.release();
+        ctx->d_segnA.release(); ctx->d_fixn.release(); ctx->d_nflag.release(); ctx->d_flagged.release();
+        ctx->d_jobs_fix.release();
         ctx->d_wfE.release();
         ctx->d_wfraw.release();
         ctx->d_wfin.release();
@@ -441,6 +563,8 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     ctx->N      = N;
     ctx->slot   = slot;
     ctx->curves = std::move(infos);
+    ctx->n_tiles_max = 0;
+    for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
     return EPS_OK;
 }
 
@@ -550,7 +674,7 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
     const uint32_t nE = p->n_coarse;
     make_coarse_jobs_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, nC, nE, ctx->d_jobs.p);
     EPS_CUDA(ctx, cudaGetLastError());
-    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false, t_max)) return rc;
+    if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false, t_max, ctx->opt_scan_exact != 0)) return rc;
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, total * sizeof(uint32_t), ctx->stream));
     {
         const uint32_t bpr = (nE + 255) / 256;
@@ -572,7 +696,7 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         ctx->stats.d2h_bytes += sizeof(uint32_t);
         const uint32_t n_active = ctx->h_pinned[0];
         if (n_active == 0) break;
-        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false, t_max)) return rc;
+        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false, t_max, ctx->opt_scan_exact != 0)) return rc;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_active * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;
         crossing_kernel<<<bpr * n_active, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);
@@ -649,6 +773,29 @@ int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const do
         for (uint32_t it = 0; it < items; it++)
             if (match_index[it] != kNone) match_index[it] += ctx->curves[it / n_levels].i0;
     return EPS_OK;
+}
+
+int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return fail(nullptr, EPS_ERR_INVALID, "null context");
+    switch (option) {
+        case EPS_OPT_SCAN_SEGMENTS:
+            EPS_REQUIRE(ctx, value >= 0 && value <= 4096, EPS_ERR_INVALID, "scan segments: 0 (auto), 1 (off) or a count");
+            ctx->opt_scan_segments = value;
+            return EPS_OK;
+        case EPS_OPT_SCAN_EXACT:
+            ctx->opt_scan_exact = value != 0;
+            return EPS_OK;
+        default: return fail(ctx, EPS_ERR_INVALID, "unknown option");
+    }
+}
+
+int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value) {
+    if (!ctx || !value) return fail(ctx, EPS_ERR_INVALID, "null argument");
+    switch (counter) {
+        case EPS_CNT_SCAN_LAUNCHES: *value = ctx->scan_launches; return EPS_OK;
+        case EPS_CNT_SCAN_FLAGGED: *value = ctx->scan_flagged; return EPS_OK;
+        default: return fail(ctx, EPS_ERR_INVALID, "unknown counter");
+    }
 }
 
 int eps_timer_start(eps_ctx* ctx) {

@@ -160,27 +160,51 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 //     kStride * theta_max < pi,   theta_max^2 = 12 * s * (E_max - V_min);
 // the host only selects kStride = 32 / 8 with a factor-2 margin on theta_max
 // (launch_sweep) and kStride = 1 (per-step bit mask) otherwise.
+//
+// kScan (transfer-matrix mode, N4): the grid is cut into n_seg segments of whole tiles and a
+// CTA marches ONE segment for kWarps*32 energies; each thread carries the two basis solutions
+// A = (X,S) = (1,0) and B = (0,1) of its energy (kEpt == 2, shared fp), i.e. the columns of the
+// segment's 2x2 transfer matrix, plus the sign-flip count of A.  segment_combine_kernel chains
+// the segments.  Results go to SegOut instead of nodes/tails.
 // ---------------------------------------------------------------------------
-template <int kEpt, int kWarps, int kStride, bool kTails>
+struct SegOut {
+    double*   XA;  // [row][seg][energy] column A = P (1,0)^T: (XA, SA), exponent eA
+    double*   SA;
+    double*   XB;  // column B = P (0,1)^T
+    double*   SB;
+    int32_t*  eA;
+    int32_t*  eB;
+    uint32_t* nA;  // sign flips of X along column A
+};
+
+template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan>
 __global__ void __launch_bounds__((kWarps + 1) * 32, (kEpt * kWarps >= 32) ? 1 : 2)
 numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
                      const Job* __restrict__ jobs, const uint32_t chunks_per_job,
                      const double* __restrict__ Eexp, const uint64_t out_stride,
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
-                     int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done) {
+                     int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done,
+                     const uint32_t n_seg, const uint32_t tiles_per_seg, const SegOut seg_out) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
-    constexpr uint32_t kPerCta = kWarps * 32 * kEpt;
+    static_assert(!kScan || (kEpt == 2 && !kTails), "scan mode: two basis chains per energy");
+    constexpr uint32_t kPerCta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
+    constexpr int      kCnt    = kScan ? 1 : kEpt;  // chains whose sign flips are counted
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double*   ring  = reinterpret_cast<double*>(smem_raw);
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kStages);
     uint64_t* empty = full + kStages;
 
-    const uint32_t job_idx = blockIdx.x / chunks_per_job;
-    const uint32_t chunk   = blockIdx.x - job_idx * chunks_per_job;
+    const uint32_t seg     = kScan ? blockIdx.x % n_seg : 0u;
+    const uint32_t cta     = kScan ? blockIdx.x / n_seg : blockIdx.x;
+    const uint32_t job_idx = cta / chunks_per_job;
+    const uint32_t chunk   = cta - job_idx * chunks_per_job;
     const Job      job     = jobs[job_idx];
     const CurveDev cv      = curves[job.curve];
     const uint32_t n_steps = cv.n_steps;
-    const uint32_t n_tiles = (n_steps + kTile - 1) / kTile;
+    const uint32_t n_tiles_all = (n_steps + kTile - 1) / kTile;
+    const uint32_t t_begin = kScan ? min(seg * tiles_per_seg, n_tiles_all) : 0u;
+    const uint32_t t_end   = kScan ? min(t_begin + tiles_per_seg, n_tiles_all) : n_tiles_all;
+    const uint32_t n_tiles = t_end - t_begin;  // tiles this CTA marches (may be 0: identity segment)
     const uint32_t warp    = threadIdx.x >> 5;
     const uint32_t lane    = threadIdx.x & 31;
 
@@ -204,11 +228,12 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                 const uint32_t s = t % kStages;
                 if (t >= kStages) mbar_wait_backoff(&empty[s], ((t / kStages) - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], kTile * sizeof(double));
-                tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t) * kTile,
+                tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t_begin + t) * kTile,
                              kTile * sizeof(double), &full[s]);
             }
-            const uint32_t in_cta = min(job.nE - e_base, kPerCta);
-            atomicAdd(steps_done, static_cast<unsigned long long>(n_steps) * in_cta);
+            const uint32_t in_cta   = min(job.nE - e_base, kPerCta);
+            const uint32_t my_steps = min(t_end * kTile, n_steps) - min(t_begin * kTile, n_steps);
+            atomicAdd(steps_done, static_cast<unsigned long long>(my_steps) * in_cta);
         }
         return;
     }
@@ -220,13 +245,13 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     uint32_t n_nodes[kEpt], prev[kEpt];
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
-        uint32_t j = e_base + i * (kWarps * 32) + warp * 32 + lane;
+        uint32_t j = e_base + (kScan ? 0 : i) * (kWarps * 32) + warp * 32 + lane;
         if (j >= job.nE) j = job.nE - 1;  // keep the warp converged; result discarded
         double E;
         if (Eexp != nullptr) E = Eexp[job.e_off + j];
         else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
         ep[i]      = __ddiv_rn(__dmul_rn(cv.s, E), 12.0);
-        c[i]       = Chain{1.0, 0.0};
+        c[i]       = (kScan && i == 1) ? Chain{0.0, 1.0} : Chain{1.0, 0.0};
         expo[i]    = 0;
         n_nodes[i] = 0;
         prev[i]    = 0;  // kStride==1: bit0 = sign of the last X; else: hi word of the last sampled X
@@ -236,7 +261,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         const uint32_t s = t % kStages;
         mbar_wait(&full[s], (t / kStages) & 1);
         const double* __restrict__ tile = ring + s * kTile;
-        const uint32_t n_valid = min(static_cast<uint32_t>(kTile), n_steps - t * kTile);
+        const uint32_t n_valid = min(static_cast<uint32_t>(kTile), n_steps - (t_begin + t) * kTile);
         const uint32_t n_full  = n_valid / kRenorm;
 
         uint32_t k = 0;
@@ -253,17 +278,17 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                     const double2 ff = t2[p];  // two consecutive grid steps, warp-broadcast
 #pragma unroll
                     for (int i = 0; i < kEpt; i++) {
-                        numerov_step(c[i], ff.x, ep[i]);
-                        if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        numerov_step(c[i], ff.x, ep[kScan ? 0 : i]);
+                        if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                     }
 #pragma unroll
                     for (int i = 0; i < kEpt; i++) {
-                        numerov_step(c[i], ff.y, ep[i]);
-                        if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        numerov_step(c[i], ff.y, ep[kScan ? 0 : i]);
+                        if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                     }
                     if (kStride == 8 && (p & 3) == 3) {
 #pragma unroll
-                        for (int i = 0; i < kEpt; i++) {
+                        for (int i = 0; i < kCnt; i++) {
                             const uint32_t cur = static_cast<uint32_t>(__double2hiint(c[i].X));
                             n_nodes[i] += (cur ^ prev[i]) >> 31;
                             prev[i] = cur;
@@ -271,7 +296,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < kEpt; i++) {
+                for (int i = 0; i < kCnt; i++) {
                     if (kStride == 1) {
                         n_nodes[i] += __popc(mask[i] ^ __funnelshift_r(mask[i], prev[i], 1));
                         prev[i] = mask[i];
@@ -292,7 +317,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
             for (int i = 0; i < kEpt; i++) {
                 const uint32_t before = static_cast<uint32_t>(__double2hiint(c[i].X));
-                numerov_step(c[i], Fk, ep[i]);
+                numerov_step(c[i], Fk, ep[kScan ? 0 : i]);
                 const uint32_t after = static_cast<uint32_t>(__double2hiint(c[i].X));
                 n_nodes[i] += (before ^ after) >> 31;
                 prev[i] = (kStride == 1) ? (after >> 31) : after;
@@ -302,6 +327,21 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
+    if constexpr (kScan) {
+        renorm(c[0], expo[0]);
+        renorm(c[1], expo[1]);
+        const uint32_t j = e_base + warp * 32 + lane;
+        if (j < job.nE) {
+            const uint64_t o = (static_cast<uint64_t>(job_idx) * n_seg + seg) * out_stride + j;
+            seg_out.XA[o] = c[0].X;
+            seg_out.SA[o] = c[0].S;
+            seg_out.XB[o] = c[1].X;
+            seg_out.SB[o] = c[1].S;
+            seg_out.eA[o] = expo[0];
+            seg_out.eB[o] = expo[1];
+            seg_out.nA[o] = n_nodes[0];
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
         renorm(c[i], expo[i]);
@@ -315,6 +355,108 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
             }
         }
     }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// N4 combine: chains the segment transfer matrices of one trial energy.
+//   v_{s+1} = P_s v_s,  v_0 = (X,S) = (1,0);   nodes += nA_s + sign(S_s) * (D_b - D_a)
+// with D_a = [X_s < 0] (column A starts at +1) and D_b = [sign X_{s+1} != sign XA_s]:
+// zeros of two solutions of a Sturm recurrence interlace and the 2x2 determinant keeps its
+// sign, so the flip count of ANY solution over a segment differs from column A's by the
+// change of "v and A lie on opposite sides of X = 0", signed by the orientation sign(S_s).
+// No second pass over the grid is needed.  Alongside, an absolute error bound on (X,S) is
+// propagated (err' = (|XA|+|XB|) err + 2^-30 (|XA X| + |XB S|)); an energy whose final
+// |X| is not 2^10 above the bound -- heavy cancellation somewhere on the way, i.e. E within
+// ~1e-6 level spacings of an eigenvalue -- is appended to `flagged` so the caller can recompute
+// it with the sequential kernel.
+// One thread per (row, energy); segments are a serial loop of n_seg 2x2 mat-vecs (n_seg <= 64:
+// a parallel prefix would save nothing next to the n_steps/n_seg marches it follows).
+// ---------------------------------------------------------------------------
+__global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ jobs, uint32_t n_jobs,
+                                       uint32_t n_seg, uint64_t out_stride,
+                                       uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
+                                       int32_t* __restrict__ exp_out, uint32_t* __restrict__ n_flagged,
+                                       uint2* __restrict__ flagged, uint32_t flagged_cap) {
+    const uint32_t row = blockIdx.y;
+    const uint32_t j   = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_jobs || j >= jobs[row].nE) return;
+    double   X = 1.0, S = 0.0, err = 0.0;
+    int      ex = 0;
+    uint32_t nodes = 0;
+    for (uint32_t sgm = 0; sgm < n_seg; sgm++) {
+        const uint64_t o  = (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + j;
+        const double   XA = so.XA[o], SA = so.SA[o];
+        int            sh = so.eB[o] - so.eA[o];
+        sh                = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+        const double XB = scalbn(so.XB[o], sh), SB = scalbn(so.SB[o], sh);
+        const double Xn = __fma_rn(XA, X, __dmul_rn(XB, S));
+        const double Sn = __fma_rn(SA, X, __dmul_rn(SB, S));
+        const int    Da = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
+        const int    Db = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
+                                            static_cast<uint32_t>(__double2hiint(XA))) >> 31);
+        const int    sg = S > 0.0 ? 1 : (S < 0.0 ? -1 : 0);
+        nodes += so.nA[o] + static_cast<uint32_t>(sg * (Db - Da));
+        err = __fma_rn(fabs(XA) + fabs(XB), err, 9.313225746154785e-10 * (fabs(__dmul_rn(XA, X)) + fabs(__dmul_rn(XB, S))));
+        X   = Xn;
+        S   = Sn;
+        ex += so.eA[o];
+        const uint32_t e11 = (static_cast<uint32_t>(__double2hiint(X)) >> 20) & 0x7ffu;
+        if (e11 != 0) {
+            const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
+            X   = __dmul_rn(X, sc);
+            S   = __dmul_rn(S, sc);
+            err = __dmul_rn(err, sc);
+            ex += static_cast<int>(e11) - 1023;
+        }
+    }
+    const uint64_t o = static_cast<uint64_t>(row) * out_stride + j;
+    nodes_out[o]     = nodes;
+    if (mant_out) mant_out[o] = X;
+    if (exp_out) exp_out[o] = ex;
+    if (!(err * 1024.0 < fabs(X))) {
+        const uint32_t pos = atomicAdd(n_flagged, 1u);
+        if (pos < flagged_cap) flagged[pos] = make_uint2(row, j);
+    }
+}
+
+// Fix-up of flagged energies: one single-energy Job per flagged (row, j), E reproduced with the
+// very operations the sweep uses, so the sequential kernel returns the oracle's bits for it.
+__global__ void make_fixup_jobs_kernel(const Job* __restrict__ jobs, const double* __restrict__ Eexp,
+                                       const uint2* __restrict__ flagged, uint32_t n, int packed,
+                                       Job* __restrict__ out, double* __restrict__ E_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Job    jb = jobs[flagged[i].x];
+    const uint32_t j = flagged[i].y;
+    double       E;
+    if (Eexp != nullptr) E = Eexp[jb.e_off + j];
+    else E = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(jb.j0) + j), jb.dE));
+    E_out[i] = E;
+    if (packed && i > 0) return;
+    Job f;
+    f.E0    = packed ? 0.0 : E;
+    f.dE    = 0.0;
+    f.e_off = 0;
+    f.curve = jb.curve;
+    f.j0    = 0;
+    f.nE    = packed ? n : 1;
+    f.level = jb.level;
+    f.slot  = jb.slot;
+    f.pad   = 0;
+    out[i]  = f;
+}
+
+__global__ void scatter_fixup_kernel(const uint2* __restrict__ flagged, uint32_t n, uint64_t out_stride,
+                                     const uint32_t* __restrict__ fn, const double* __restrict__ fm,
+                                     const int32_t* __restrict__ fe, uint32_t* __restrict__ nodes_out,
+                                     double* __restrict__ mant_out, int32_t* __restrict__ exp_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t o = static_cast<uint64_t>(flagged[i].x) * out_stride + flagged[i].y;
+    nodes_out[o]     = fn[i];
+    if (mant_out) mant_out[o] = fm[i];
+    if (exp_out) exp_out[o] = fe[i];
 }
 
 // ---------------------------------------------------------------------------

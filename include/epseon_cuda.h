@@ -142,6 +142,21 @@ int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint
 int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo,
                      const double* E_hi, double* levels, double* widths, uint32_t* n_below);
 
+/* ---- options / counters.
+ * EPS_OPT_SCAN_SEGMENTS: transfer-matrix (scan) path of the sweep for the few-energy, long-grid
+ *   regime: 0 = automatic (default), 1 = never, n >= 2 = always cut the grid into n segments.
+ *   On the scan path node counts equal the sequential march's (energies whose result is
+ *   ill-conditioned are detected and recomputed sequentially); tails agree to rounding.
+ * EPS_OPT_SCAN_EXACT: 1 (default) = eps_solve_levels also recomputes flagged energies
+ *   sequentially, so levels carry the sequential march's bits (late refinement rounds, whose
+ *   energies all crowd an eigenvalue, then run at sequential speed); 0 = it does not: faster,
+ *   and the levels agree with the sequential ones to the rounding-noise floor of the FP64
+ *   recurrence (a few 1e-9 relative). */
+enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2 };
+enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2 };
+int eps_set_option(eps_ctx* ctx, int option, int64_t value);
+int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);
+
 /* ---- normalised wavefunctions of located levels (N7; the reference plans no such
  * output -- additive).  E[n_curves][n_levels] (host; NaN entries give
  * a zero row), grid_step[n_curves] = h of every curve (for the norm
