@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the Numerov hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4|c5] [--impl reference]
 
 Metric: FP64 Numerov grid-steps x trial-energies per second (whole job, all ranks), plus
 time-to-all-levels.  One "step" = one complete pass of the hot path over the workload:
@@ -11,6 +11,11 @@ time-to-all-levels.  One "step" = one complete pass of the hot path over the wor
       levels to 1e-10 relative.  At N GPUs each rank solves its own (slightly perturbed) curve
       -- sharded by potential curve, no data-path collective, weak scaling -- and the located
       levels (17 doubles per rank) are gathered to rank 0 over NCCL.
+  c3 (BASELINE.json configs[2]):  tabulated "ab initio" curve (64 knots, natural cubic spline
+      resampled to 1 000 000 points), sweep of 4096 trial energies -- the few-energy / long-grid
+      regime served by the transfer-matrix scan path; replicas at N > 1 (it does not shard).
+  c4 (BASELINE.json configs[3]):  4096 perturbed Morse / LJ curves x 1024 coarse energies each,
+      levels 0..7 refined to 1e-10; curves sharded over the ranks (strong scaling).
   c5 (BASELINE.json configs[4]):  dense sweep of 2^24 trial energies on a 200 000-point grid,
       energy-range sharded over the ranks (strong scaling); node-count checksums gathered.
 
@@ -45,6 +50,8 @@ FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 D
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 
 C2 = dict(N=100_000, n_coarse=65_536, refine_points=4096, rel_tol=1e-10, max_rounds=8, v_max=16)
+C3 = dict(N=1_000_000, nE=4096)
+C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=64, rel_tol=1e-10, max_rounds=8, v_max=7)
 C5 = dict(N=200_000, nE=1 << 24)
 
 
@@ -154,6 +161,31 @@ def run_reference(args) -> None:
 
         sample = f"2^16 of the 2^24 energies (every 256th) on the 200k grid, {orc.threads} threads"
         cfg = {"workload": "c5: dense sweep 2^24 energies x 200k-point grid (energy-range sharded)"}
+    elif args.workload == "c3":
+        w = W.c3(C3["N"], C3["nE"])
+        F, *_ = orc.prep(w["V"], w["s"])
+        dE = (w["E_hi"] - w["E_lo"]) / (C3["nE"] - 1)
+
+        def one():
+            t = time.perf_counter()
+            orc.sweep_uniform(F, w["s"], w["E_lo"], dE, 0, C3["nE"], tails=False)
+            return time.perf_counter() - t, F.size * C3["nE"]
+
+        sample = f"the full C3 sweep (4096 energies x 1M-point grid), {orc.threads} threads"
+        cfg = {"workload": "c3: tabulated curve, 1M-point grid, sweep of 4096 trial energies"}
+    elif args.workload == "c4":
+        w = W.c4(64, C4["N"], C4["n_coarse"])
+
+        def one():
+            t, steps = time.perf_counter(), 0
+            for c in range(64):
+                F, *_ = orc.prep(w["V"][c], w["s"])
+                steps += orc.solve_levels(F, w["s"], w["E_lo"][c], w["E_hi"][c], C4["n_coarse"], 0, C4["v_max"],
+                                          C4["refine_points"], C4["rel_tol"], C4["max_rounds"])[4]
+            return time.perf_counter() - t, steps
+
+        sample = f"64 of the 4096 curves (full level solve each), {orc.threads} threads"
+        cfg = {"workload": "c4: 4096 perturbed Morse/LJ curves x 1024 energies, levels 0..7 to 1e-10"}
     else:
         V, s, E_lo, E_hi, _ = rank_curve(0)
 
@@ -174,7 +206,7 @@ def run_reference(args) -> None:
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
-        "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "higher_is_better": True, "scaling": "strong" if args.workload in ("c4", "c5") else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": orc.threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,7 +219,7 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=["c2", "c5"], default="c2")
+    ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5"], default="c2")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -233,6 +265,48 @@ def main() -> None:
                "refine_points_per_level": C2["refine_points"], "levels": C2["v_max"] + 1,
                "l2": "flushed between timed steps (256 MiB memset)"}
         scaling = "weak"
+    elif args.workload == "c3":
+        w = W.c3(C3["N"], C3["nE"])
+        V, s = w["V"], w["s"]
+        ctx.set_potentials(V, s)
+        n_steps = ctx.curve_info(0).n_steps
+        dE = (w["E_hi"] - w["E_lo"]) / (C3["nE"] - 1)
+
+        def step_resident():
+            return ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=False, tails=False)
+
+        def step_e2e():
+            ctx.set_potentials(V, s)
+            n, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
+            return n
+
+        cfg = {"workload": "c3: tabulated curve (64 knots, natural cubic spline) resampled to a 1M-point grid, sweep of "
+                           "4096 trial energies through the transfer-matrix scan path; replicas at N > 1",
+               "grid_points": C3["N"], "trial_energies": C3["nE"], "l2": "flushed between timed steps (256 MiB memset)"}
+        scaling = "weak"
+    elif args.workload == "c4":
+        w = W.c4(C4["nC"], C4["N"], C4["n_coarse"])
+        per = C4["nC"] // world
+        sl = slice(rank * per, (rank + 1) * per)
+        V, s = np.ascontiguousarray(w["V"][sl]), w["s"]
+        E_lo4, E_hi4 = np.ascontiguousarray(w["E_lo"][sl]), np.ascontiguousarray(w["E_hi"][sl])
+        ctx.set_potentials(V, s)
+        n_steps = ctx.curve_info(0).n_steps
+
+        def step_resident():
+            return ctx.solve_levels(E_lo4, E_hi4, C4["n_coarse"], 0, C4["v_max"], C4["refine_points"], C4["rel_tol"],
+                                    C4["max_rounds"])
+
+        def step_e2e():
+            ctx.set_potentials(V, s)
+            return step_resident()
+
+        cfg = {"workload": "c4: 4096 perturbed Morse/LJ curves x 1024 coarse energies, levels 0..7 refined to 1e-10 "
+                           "rel.; curves sharded over the ranks",
+               "curves": C4["nC"], "grid_points": C4["N"], "trial_energies_coarse": C4["n_coarse"],
+               "refine_points_per_level": C4["refine_points"], "levels": C4["v_max"] + 1,
+               "l2": "flushed between timed steps (256 MiB memset)"}
+        scaling = "strong"
     else:
         w = W.c5(C5["N"], C5["nE"])
         ctx.set_potentials(w["V"], w["s"])
@@ -267,6 +341,8 @@ def main() -> None:
     def result_digest(res) -> np.ndarray:
         if args.workload == "c2":
             return res[0][0]  # 17 level energies
+        if args.workload == "c4":
+            return res[0]  # [curves of this rank][8] level energies
         return np.zeros(1)
 
     # ---- warm-up, FP64 probe ----
@@ -331,7 +407,7 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "time_to_all_levels_ms": ms_res / args.steps if args.workload == "c2" else None,
+            "time_to_all_levels_ms": ms_res / args.steps if args.workload in ("c2", "c4") else None,
             "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(st2.h2d_bytes // args.steps),
                     "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps)},
@@ -367,6 +443,28 @@ def main() -> None:
                                         "seconds": dt,
                                         "levels_bit_identical_to_gpu": bool(np.array_equal(
                                             clev.view(np.uint64), digest[0].view(np.uint64)))}
+            elif args.workload == "c3":
+                F, *_ = orc.prep(V, s)
+                t0 = time.perf_counter()
+                n_cpu, _, _ = orc.sweep_uniform(F, s, w["E_lo"], dE, 0, C3["nE"], tails=False)
+                dt = time.perf_counter() - t0
+                n_gpu, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
+                line["cpu_baseline"] = {"value": F.size * C3["nE"] / dt, "unit": "steps/s", "cores": orc.threads,
+                                        "kind": "port", "sample": "the full C3 sweep once, OpenMP oracle", "seconds": dt,
+                                        "nodes_bit_identical_to_gpu": bool(np.array_equal(n_cpu, n_gpu[0]))}
+                line["scan"] = {"launches": ctx.counter(ctx.CNT_SCAN_LAUNCHES), "flagged": ctx.counter(ctx.CNT_SCAN_FLAGGED)}
+            elif args.workload == "c4":
+                t0, csteps, same = time.perf_counter(), 0, True
+                for c in range(64):
+                    F, *_ = orc.prep(V[c], s)
+                    lv, _, _, _, st_c = orc.solve_levels(F, s, E_lo4[c], E_hi4[c], C4["n_coarse"], 0, C4["v_max"],
+                                                         C4["refine_points"], C4["rel_tol"], C4["max_rounds"])
+                    csteps += st_c
+                    same &= bool(np.array_equal(lv.view(np.uint64), digest[0][c].view(np.uint64)))
+                dt = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": csteps / dt, "unit": "steps/s", "cores": orc.threads, "kind": "port",
+                                        "sample": "64 of the 4096 curves (full level solve each), OpenMP oracle",
+                                        "seconds": dt, "levels_bit_identical_to_gpu": same}
             else:
                 F, *_ = orc.prep(V, s)
                 nE = 1 << 16

@@ -162,16 +162,19 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // (launch_sweep) and kStride = 1 (per-step bit mask) otherwise.
 //
 // kScan (transfer-matrix mode, N4): the grid is cut into n_seg segments of whole tiles and a
-// CTA marches ONE segment for kWarps*32 energies; each thread carries the two basis solutions
-// A = (X,S) = (1,0) and B = (0,1) of its energy (kEpt == 2, shared fp), i.e. the columns of the
-// segment's 2x2 transfer matrix, plus the sign-flip count of A.  segment_combine_kernel chains
-// the segments.  Results go to SegOut instead of nodes/tails.
+// CTA marches ONE segment for kWarps*32 energies; each thread carries two basis solutions of
+// its energy (kEpt == 2, shared fp): A from (X,S) = (1,1) ("flat": psi_a = psi_{a-1}) and B from
+// (0,1) ("unit slope"), plus the sign-flip count of A.  The segment's transfer matrix is stored in
+// the coordinates (X, D = S - X): consecutive values of a smooth solution are nearly equal, so
+// the naive (X,S) columns (1,0)/(0,1) would make every combination a cancellation of two
+// columns ~n_steps/n_seg times larger than the result (measured: 150x larger tail error).
+// segment_combine_kernel chains the segments.  Results go to SegOut instead of nodes/tails.
 // ---------------------------------------------------------------------------
 struct SegOut {
-    double*   XA;  // [row][seg][energy] column A = P (1,0)^T: (XA, SA), exponent eA
-    double*   SA;
+    double*   XA;  // [row][seg][energy] column A = P (1,1)^T: X and D = S - X, exponent eA
+    double*   SA;  //   (holds D_A)
     double*   XB;  // column B = P (0,1)^T
-    double*   SB;
+    double*   SB;  //   (holds D_B)
     int32_t*  eA;
     int32_t*  eB;
     uint32_t* nA;  // sign flips of X along column A
@@ -251,7 +254,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         if (Eexp != nullptr) E = Eexp[job.e_off + j];
         else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
         ep[i]      = __ddiv_rn(__dmul_rn(cv.s, E), 12.0);
-        c[i]       = (kScan && i == 1) ? Chain{0.0, 1.0} : Chain{1.0, 0.0};
+        c[i]       = kScan ? (i == 1 ? Chain{0.0, 1.0} : Chain{1.0, 1.0}) : Chain{1.0, 0.0};
         expo[i]    = 0;
         n_nodes[i] = 0;
         prev[i]    = 0;  // kStride==1: bit0 = sign of the last X; else: hi word of the last sampled X
@@ -334,9 +337,9 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         if (j < job.nE) {
             const uint64_t o = (static_cast<uint64_t>(job_idx) * n_seg + seg) * out_stride + j;
             seg_out.XA[o] = c[0].X;
-            seg_out.SA[o] = c[0].S;
+            seg_out.SA[o] = __dsub_rn(c[0].S, c[0].X);
             seg_out.XB[o] = c[1].X;
-            seg_out.SB[o] = c[1].S;
+            seg_out.SB[o] = __dsub_rn(c[1].S, c[1].X);
             seg_out.eA[o] = expo[0];
             seg_out.eB[o] = expo[1];
             seg_out.nA[o] = n_nodes[0];
@@ -359,17 +362,19 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// N4 combine: chains the segment transfer matrices of one trial energy.
-//   v_{s+1} = P_s v_s,  v_0 = (X,S) = (1,0);   nodes += nA_s + sign(S_s) * (D_b - D_a)
-// with D_a = [X_s < 0] (column A starts at +1) and D_b = [sign X_{s+1} != sign XA_s]:
-// zeros of two solutions of a Sturm recurrence interlace and the 2x2 determinant keeps its
-// sign, so the flip count of ANY solution over a segment differs from column A's by the
-// change of "v and A lie on opposite sides of X = 0", signed by the orientation sign(S_s).
-// No second pass over the grid is needed.  Alongside, an absolute error bound on (X,S) is
-// propagated (err' = (|XA|+|XB|) err + 2^-30 (|XA X| + |XB S|)); an energy whose final
-// |X| is not 2^10 above the bound -- heavy cancellation somewhere on the way, i.e. E within
-// ~1e-6 level spacings of an eigenvalue -- is appended to `flagged` so the caller can recompute
-// it with the sequential kernel.
+// N4 combine: chains the segment transfer matrices of one trial energy, in (X, D = S - X)
+// coordinates:   v_{s+1} = P_s v_s,  v_0 = (X,S) = (1,0) i.e. (X,D) = (1,-1);
+//     nodes += nA_s + sign(D_s) * (D_b - D_a),
+// D_a = [X_s < 0] (column A starts at X = +1), D_b = [sign X_{s+1} != sign XA_s].  Zeros of two
+// solutions of a Sturm recurrence interlace and det[A, v] = D_s keeps its sign along the
+// segment, so the flip count of ANY solution differs from column A's only by the change of "v
+// and A lie on opposite sides of X = 0", signed by the orientation.  No second pass over the
+// grid is needed.
+// Guard: rho estimates the relative error of v's direction; a combine that cancels (both
+// components shrink by c = max(|X'|/mag_X, |D'|/mag_D) -- the solution decays across the
+// segment) amplifies it, rho' = (rho + 2^-34) / c; for the last segment only the X component
+// counts.  Energies ending with rho >= 2^-10 (E within ~1e-6 level spacings of an eigenvalue,
+// where the tail is a pure cancellation) are appended to `flagged` for the sequential kernel.
 // One thread per (row, energy); segments are a serial loop of n_seg 2x2 mat-vecs (n_seg <= 64:
 // a parallel prefix would save nothing next to the n_steps/n_seg marches it follows).
 // ---------------------------------------------------------------------------
@@ -381,32 +386,44 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
     const uint32_t row = blockIdx.y;
     const uint32_t j   = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_jobs || j >= jobs[row].nE) return;
-    double   X = 1.0, S = 0.0, err = 0.0;
+    constexpr double kEta = 5.820766091346741e-11;  // 2^-34
+    double   X = 1.0, D = -1.0, rho = 0.0;
     int      ex = 0;
     uint32_t nodes = 0;
     for (uint32_t sgm = 0; sgm < n_seg; sgm++) {
         const uint64_t o  = (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + j;
-        const double   XA = so.XA[o], SA = so.SA[o];
+        const double   XA = so.XA[o], DA = so.SA[o];
         int            sh = so.eB[o] - so.eA[o];
         sh                = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
-        const double XB = scalbn(so.XB[o], sh), SB = scalbn(so.SB[o], sh);
-        const double Xn = __fma_rn(XA, X, __dmul_rn(XB, S));
-        const double Sn = __fma_rn(SA, X, __dmul_rn(SB, S));
-        const int    Da = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
-        const int    Db = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
+        const double XB = scalbn(so.XB[o], sh), DB = scalbn(so.SB[o], sh);
+        const double pX = __dmul_rn(XB, D), pD = __dmul_rn(DB, D);
+        const double Xn = __fma_rn(XA, X, pX);
+        const double Dn = __fma_rn(DA, X, pD);
+        const int    fa = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
+        const int    fb = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
                                             static_cast<uint32_t>(__double2hiint(XA))) >> 31);
-        const int    sg = S > 0.0 ? 1 : (S < 0.0 ? -1 : 0);
-        nodes += so.nA[o] + static_cast<uint32_t>(sg * (Db - Da));
-        err = __fma_rn(fabs(XA) + fabs(XB), err, 9.313225746154785e-10 * (fabs(__dmul_rn(XA, X)) + fabs(__dmul_rn(XB, S))));
-        X   = Xn;
-        S   = Sn;
+        const int    sg = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
+        nodes += so.nA[o] + static_cast<uint32_t>(sg * (fb - fa));
+        const double magX = fabs(__dmul_rn(XA, X)) + fabs(pX), magD = fabs(__dmul_rn(DA, X)) + fabs(pD);
+        const double cX = magX > 0.0 ? fabs(Xn) / magX : 1.0, cD = magD > 0.0 ? fabs(Dn) / magD : 1.0;
+        const double c  = (sgm + 1 == n_seg) ? cX : fmax(cX, cD);
+        rho             = (rho + kEta) / c;  // c == 0 -> inf -> flagged
+        X               = Xn;
+        D               = Dn;
         ex += so.eA[o];
+        uint32_t e11 = (static_cast<uint32_t>(__double2hiint(X)) >> 20) & 0x7ffu;
+        if (e11 == 0) e11 = (static_cast<uint32_t>(__double2hiint(D)) >> 20) & 0x7ffu;
+        if (e11 != 0 && sgm + 1 < n_seg) {
+            const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
+            X = __dmul_rn(X, sc);
+            D = __dmul_rn(D, sc);
+            ex += static_cast<int>(e11) - 1023;
+        }
+    }
+    {   // tail in the sweep's (mantissa in [1,2), exponent) form
         const uint32_t e11 = (static_cast<uint32_t>(__double2hiint(X)) >> 20) & 0x7ffu;
         if (e11 != 0) {
-            const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
-            X   = __dmul_rn(X, sc);
-            S   = __dmul_rn(S, sc);
-            err = __dmul_rn(err, sc);
+            X = __dmul_rn(X, __hiloint2double(static_cast<int>((2046u - e11) << 20), 0));
             ex += static_cast<int>(e11) - 1023;
         }
     }
@@ -414,7 +431,7 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
     nodes_out[o]     = nodes;
     if (mant_out) mant_out[o] = X;
     if (exp_out) exp_out[o] = ex;
-    if (!(err * 1024.0 < fabs(X))) {
+    if (!(rho < 9.765625e-4)) {
         const uint32_t pos = atomicAdd(n_flagged, 1u);
         if (pos < flagged_cap) flagged[pos] = make_uint2(row, j);
     }
