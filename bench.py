@@ -116,6 +116,15 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU legs run on
+    rank 0 only and are meant to use the whole box)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def dist_setup(n_gpus: int):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -146,7 +155,7 @@ def run_reference(args) -> None:
         return
     from oracle import Oracle
 
-    orc = Oracle(omp=True)
+    orc = Oracle(omp=True, threads=host_threads())
     if args.workload == "c5":
         w = W.c5(C5["N"], C5["nE"])
         F, *_ = orc.prep(w["V"], w["s"])
@@ -311,18 +320,19 @@ def main() -> None:
         w = W.c5(C5["N"], C5["nE"])
         ctx.set_potentials(w["V"], w["s"])
         n_steps = ctx.curve_info(0).n_steps
-        per = C5["nE"] // world
-        dE = (w["E_hi"] - w["E_lo"]) / (C5["nE"] - 1)
-        lo = w["E_lo"] + rank * per * dE
-        hi = w["E_lo"] + (rank * per + per - 1) * dE
+        from epseon_backend_b200 import multi
+
+        sl = multi.curve_shard(C5["nE"], world, rank)  # contiguous slice of the global energy grid
+        j0, per = sl.start, sl.stop - sl.start
+        dE = float(multi.global_step(w["E_lo"], w["E_hi"], C5["nE"]))
         V, s = w["V"], w["s"]
 
         def step_resident():
-            return ctx.sweep_uniform(lo, hi, per, nodes=False, tails=False)
+            return ctx.sweep_grid(w["E_lo"], dE, j0, per, nodes=False, tails=False)
 
         def step_e2e():
             ctx.set_potentials(V, s)
-            n, _, _ = ctx.sweep_uniform(lo, hi, per, nodes=True, tails=False)  # 4 B/energy D2H
+            n, _, _ = ctx.sweep_grid(w["E_lo"], dE, j0, per, nodes=True, tails=False)  # 4 B/energy D2H
             return n
 
         cfg = {"workload": "c5: dense sweep of 2^24 trial energies on a 200k-point grid, energy-range sharded",
@@ -345,9 +355,10 @@ def main() -> None:
             return res[0]  # [curves of this rank][8] level energies
         return np.zeros(1)
 
-    # ---- warm-up, FP64 probe ----
+    # ---- warm-up (incl. the NCCL communicator behind the result gather), FP64 probe ----
     for _ in range(args.warmup):
         res = step_resident()
+        gather_small(result_digest(res))
     ctx.sync()
     fp64_peak, _ = ctx.fp64_probe()
 
@@ -434,7 +445,7 @@ def main() -> None:
         if not args.no_cpu_baseline:
             from oracle import Oracle
 
-            orc = Oracle(omp=True)
+            orc = Oracle(omp=True, threads=host_threads())
             if args.workload == "c2":
                 Vc, sc, El, Eh, _ = rank_curve(0)
                 dt, csteps, clev = cpu_solve_c2(orc, Vc, sc, El, Eh)

@@ -21,7 +21,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
-    "eps_sweep", "eps_sweep_uniform", "eps_solve_levels", "eps_wavefunctions", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
+    "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
 ]
 
@@ -172,6 +172,31 @@ class Context:
                                             C.c_uint64(nE), _ptr(n, np.uint32), _ptr(m, np.float64),
                                             _ptr(x, np.int32)))
         return n, m, x
+
+    def sweep_grid(self, E0, dE, j0: int, nE: int, nodes: bool = True, tails: bool = True):
+        """Affine grid E_j = E0 + (j0 + j) dE (a slice of a global uniform grid)."""
+        a, b = _vec(E0, self.n_curves), _vec(dE, self.n_curves)
+        n, m, x = self._outs(nE, nodes, tails)
+        self._ck(self.lib.eps_sweep_grid(self.h, _ptr(a, np.float64), _ptr(b, np.float64), C.c_uint32(j0),
+                                         C.c_uint64(nE), _ptr(n, np.uint32), _ptr(m, np.float64),
+                                         _ptr(x, np.int32)))
+        return n, m, x
+
+    def solve_levels_grid(self, E0, dE, j0: int, n_coarse: int, v_min: int, v_max: int, refine_points: int,
+                          rel_tol: float = 1e-12, max_rounds: int = 8):
+        """-> (levels[nC, nlev], widths[nC, nlev], n_last[nC], n_first[nC])"""
+        a, b = _vec(E0, self.n_curves), _vec(dE, self.n_curves)
+        nlev = v_max - v_min + 1
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        levels = np.empty((self.n_curves, nlev), dtype=np.float64)
+        widths = np.empty((self.n_curves, nlev), dtype=np.float64)
+        nl = np.empty(self.n_curves, dtype=np.uint32)
+        nf = np.empty(self.n_curves, dtype=np.uint32)
+        self._ck(self.lib.eps_solve_levels_grid(self.h, C.byref(p), _ptr(a, np.float64), _ptr(b, np.float64),
+                                                C.c_uint32(j0), _ptr(levels, np.float64),
+                                                _ptr(widths, np.float64), _ptr(nl, np.uint32),
+                                                _ptr(nf, np.uint32)))
+        return levels, widths, nl, nf
 
     def solve_levels(self, E_lo, E_hi, n_coarse: int, v_min: int, v_max: int, refine_points: int,
                      rel_tol: float = 1e-12, max_rounds: int = 8):

@@ -151,10 +151,11 @@ struct SweepOut {  // device pointers of one sweep's results
 
 template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan>
 cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                                 const SweepOut& out, uint32_t n_seg, uint32_t tiles_per_seg, const SegOut& so) {
+                                 const SweepOut& out, uint32_t n_seg, uint32_t tiles_per_seg, const SegOut& so,
+                                 uint32_t pack_log2 = 0) {
     constexpr uint32_t per_cta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
-    const uint64_t chunks = (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
-    const uint64_t grid   = chunks * n_jobs * (kScan ? n_seg : 1u);
+    const uint64_t chunks = pack_log2 ? 1 : (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
+    const uint64_t grid   = pack_log2 ? ((n_jobs + (1u << pack_log2) - 1) >> pack_log2) : chunks * n_jobs * (kScan ? n_seg : 1u);
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
     auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan>;
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
@@ -165,22 +166,24 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     }
     kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
         ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
-        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so);
+        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2);
     return cudaGetLastError();
 }
 
 template <int kEpt, int kWarps, int kStride>
-cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
+cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out,
+                           uint32_t pack_log2) {
     const SegOut none{};
-    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true, false>(ctx, j, n, nE, E, out, 1, 0, none)
-                 : launch_sweep_variant<kEpt, kWarps, kStride, false, false>(ctx, j, n, nE, E, out, 1, 0, none);
+    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true, false>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2)
+                 : launch_sweep_variant<kEpt, kWarps, kStride, false, false>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2);
 }
 
 template <int kEpt, int kWarps>
-cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
-    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails, out);
-    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails, out);
-    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails, out);
+cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out,
+                           uint32_t pack_log2) {
+    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails, out, pack_log2);
+    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails, out, pack_log2);
+    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails, out, pack_log2);
 }
 
 // CTA shape (energies per thread, consumer warps).  Register-file bandwidth is the binding
@@ -203,14 +206,23 @@ int pick_stride(const eps_ctx* ctx, double t_max) {
     return 1;
 }
 
+// Rows-per-CTA packing of short rows (2^g rows of nE <= 512 >> g energies in one 512-energy CTA);
+// only for callers that lay their rows out [curve][level padded to 2^g] (pack_rows > 1).
+uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows) {
+    uint32_t g = 0;
+    while ((2u << g) <= pack_rows && (512u >> (g + 1)) >= nE) g++;
+    return g;
+}
+
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                              bool tails, int stride, const SweepOut& out) {
+                              bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0) {
+    if (pack_log2) return launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     const Shape sh = pick_shape(ctx, n_jobs, nE);
-    if (sh.ept == 4 && sh.warps == 4) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
-    if (sh.ept == 4) return launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
-    if (sh.ept == 2 && sh.warps == 4) return launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
-    if (sh.ept == 2) return launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
-    return launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    if (sh.ept == 4 && sh.warps == 4) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
+    if (sh.ept == 4) return launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
+    if (sh.ept == 2 && sh.warps == 4) return launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
+    if (sh.ept == 2) return launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
+    return launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
 }
 
 // Transfer-matrix (scan) policy.  A sweep of E_tot = n_jobs * nE energies occupies
@@ -220,7 +232,7 @@ cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, 
 // gains n_seg-fold parallelism.  Returns 1 for "sequential".
 constexpr uint32_t kScanMinTiles = 32;   // auto mode: grids of >= 65 536 steps only
 constexpr uint32_t kScanMaxSeg   = 64;
-uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool tails) {
+uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool tails) {  // n_jobs: rows that carry energies
     const uint32_t n_tiles = ctx->n_tiles_max;
     if (ctx->opt_scan_segments == 1 || n_tiles < 2) return 1;
     if (ctx->opt_scan_segments >= 2)
@@ -296,14 +308,14 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
 // t_max = max over the rows of s * (E_max - V_min) (see pick_stride).  fix_flagged: on the scan
 // path, recompute ill-conditioned energies with the sequential kernel (one host sync).
 int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                 bool tails, double t_max, bool fix_flagged = true) {
+                 bool tails, double t_max, bool fix_flagged = true, uint32_t n_rows_active = 0, uint32_t pack_rows = 1) {
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
     if (tails) {
         EPS_CUDA(ctx, ctx->d_mant.reserve(n_out));
         EPS_CUDA(ctx, ctx->d_exp.reserve(n_out));
     }
-    const uint32_t n_seg = pick_segments(ctx, n_jobs, nE, tails);
+    const uint32_t n_seg = pick_segments(ctx, n_rows_active ? n_rows_active : n_jobs, nE, tails);
     if (n_seg >= 2) {  // reserve before the timed region
         const size_t n_so = n_out * n_seg;
         EPS_CUDA(ctx, ctx->d_segXA.reserve(n_so));
@@ -325,7 +337,8 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     if (n_seg >= 2) {
         if (int rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out)) return rc;
     } else {
-        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out));
+        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out,
+                                        ctx->force_ept ? 0 : pack_log2_for(nE, pack_rows)));
     }
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
@@ -610,70 +623,92 @@ int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* node
     return fetch_sweep(ctx, n, nodes, tail_mant, tail_exp);
 }
 
-int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint64_t n_energies,
-                      uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
-    if (int rc = bind(ctx)) return rc;
-    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
-    EPS_REQUIRE(ctx, E_lo && E_hi && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
-    const uint32_t nE = static_cast<uint32_t>(n_energies);
-    double t_max = -1.0;
-    for (uint32_t c = 0; c < ctx->nC; c++) {
-        EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
-                    "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
-        t_max = std::max(t_max, curve_tmax(ctx->curves[c], std::max(E_lo[c], E_hi[c])));
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Coarse grid of one call: E_j = A[c] + (j0 + j) * B[c] (grid) or A = E_lo, B = E_hi (uniform).
+struct GridSpec {
+    const double* A;
+    const double* B;
+    bool          grid;
+    uint32_t      j0;
+};
+
+// First / last trial energy of row c, for the validity check and the stride choice.
+void grid_ends(const GridSpec& g, uint32_t c, uint32_t nE, double& e_first, double& e_last) {
+    if (!g.grid) {
+        e_first = g.A[c];
+        e_last  = g.B[c];
+    } else {
+        e_first = g.A[c] + static_cast<double>(g.j0) * g.B[c];
+        e_last  = g.A[c] + static_cast<double>(static_cast<uint64_t>(g.j0) + nE - 1) * g.B[c];
     }
-    EPS_CUDA(ctx, ctx->d_Elo.reserve(ctx->nC));
-    EPS_CUDA(ctx, ctx->d_Ehi.reserve(ctx->nC));
-    EPS_CUDA(ctx, ctx->d_jobs.reserve(ctx->nC));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Elo.p, E_lo, ctx->nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Ehi.p, E_hi, ctx->nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += 2ull * ctx->nC * sizeof(double);
-    make_coarse_jobs_kernel<<<(ctx->nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, ctx->nC, nE, ctx->d_jobs.p);
+}
+
+int upload_coarse_jobs(eps_ctx* ctx, const GridSpec& g, uint32_t nE, double& t_max) {
+    const uint32_t nC = ctx->nC;
+    t_max = -1.0;
+    for (uint32_t c = 0; c < nC; c++) {
+        double a, b;
+        grid_ends(g, c, nE, a, b);
+        EPS_REQUIRE(ctx, range_ok(ctx->curves[c], a, b), EPS_ERR_RANGE,
+                    "trial energy outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+        t_max = std::max(t_max, curve_tmax(ctx->curves[c], std::max(a, b)));
+    }
+    EPS_CUDA(ctx, ctx->d_Elo.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_Ehi.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_jobs.reserve(nC));
+    // A/B are pageable host memory: the async copies are staged before the call returns
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Elo.p, g.A, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Ehi.p, g.B, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += 2ull * nC * sizeof(double);
+    make_coarse_jobs_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, nC, nE, g.grid ? 1 : 0, g.j0, ctx->d_jobs.p);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
-    // E_lo/E_hi are pageable host memory: the async copies above are staged before return
+    return EPS_OK;
+}
+
+int sweep_rows(eps_ctx* ctx, const GridSpec& g, uint64_t n_energies, uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
+    EPS_REQUIRE(ctx, g.A && g.B && n_energies >= 1 && n_energies < (1ull << 32), EPS_ERR_INVALID, "bad energies");
+    const uint32_t nE = static_cast<uint32_t>(n_energies);
+    double         t_max;
+    if (int rc = upload_coarse_jobs(ctx, g, nE, t_max)) return rc;
     if (int rc = launch_sweep(ctx, ctx->d_jobs.p, ctx->nC, nE, nullptr, tail_mant || tail_exp, t_max)) return rc;
     return fetch_sweep(ctx, static_cast<size_t>(ctx->nC) * nE, nodes, tail_mant, tail_exp);
 }
 
-int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo, const double* E_hi,
-                     double* levels, double* widths, uint32_t* n_below) {
+int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, double* levels, double* widths,
+               uint32_t* n_below, uint32_t* n_first) {
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
-    EPS_REQUIRE(ctx, p && E_lo && E_hi && levels, EPS_ERR_INVALID, "null argument");
+    EPS_REQUIRE(ctx, p && g.A && g.B && levels, EPS_ERR_INVALID, "null argument");
     EPS_REQUIRE(ctx, p->v_max >= p->v_min, EPS_ERR_INVALID, "v_max < v_min");
     EPS_REQUIRE(ctx, p->n_coarse >= 2 && p->refine_points >= 1, EPS_ERR_INVALID, "n_coarse >= 2 and refine_points >= 1 required");
     const uint32_t nC = ctx->nC, nlev = p->v_max - p->v_min + 1, M = p->refine_points;
     const uint64_t total64 = static_cast<uint64_t>(nC) * nlev;
     EPS_REQUIRE(ctx, total64 < (1ull << 31), EPS_ERR_INVALID, "too many (curve, level) pairs");
     const uint32_t total = static_cast<uint32_t>(total64);
-    double t_max = -1.0;
+    const uint32_t nE    = p->n_coarse;
     for (uint32_t c = 0; c < nC; c++) {
-        t_max = std::max(t_max, curve_tmax(ctx->curves[c], E_hi[c]));
-        EPS_REQUIRE(ctx, E_hi[c] >= E_lo[c], EPS_ERR_INVALID, "E_hi < E_lo");
-        EPS_REQUIRE(ctx, range_ok(ctx->curves[c], E_lo[c], E_hi[c]), EPS_ERR_RANGE,
-                    "search range outside the validity window |s (E - V_min)| <= 0.5 (grid too coarse)");
+        double a, b;
+        grid_ends(g, c, nE, a, b);
+        EPS_REQUIRE(ctx, b >= a, EPS_ERR_INVALID, "E_hi < E_lo");
     }
-    EPS_CUDA(ctx, ctx->d_Elo.reserve(nC));
-    EPS_CUDA(ctx, ctx->d_Ehi.reserve(nC));
-    EPS_CUDA(ctx, ctx->d_jobs.reserve(nC));
-    EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(total));
     EPS_CUDA(ctx, ctx->d_lo.reserve(total));
     EPS_CUDA(ctx, ctx->d_hi.reserve(total));
     EPS_CUDA(ctx, ctx->d_levels.reserve(total));
     EPS_CUDA(ctx, ctx->d_widths.reserve(total));
     EPS_CUDA(ctx, ctx->d_state.reserve(total));
     EPS_CUDA(ctx, ctx->d_jstar.reserve(total));
-    EPS_CUDA(ctx, ctx->d_nbelow.reserve(nC));
+    EPS_CUDA(ctx, ctx->d_nbelow.reserve(2ull * nC));
     EPS_CUDA(ctx, ctx->d_nactive.reserve(1));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Elo.p, E_lo, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Ehi.p, E_hi, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += 2ull * nC * sizeof(double);
 
     // ---- coarse sweep + bracketing ----
-    const uint32_t nE = p->n_coarse;
-    make_coarse_jobs_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Elo.p, ctx->d_Ehi.p, nC, nE, ctx->d_jobs.p);
-    EPS_CUDA(ctx, cudaGetLastError());
+    double t_max;
+    if (int rc = upload_coarse_jobs(ctx, g, nE, t_max)) return rc;
     if (int rc = launch_sweep(ctx, ctx->d_jobs.p, nC, nE, nullptr, false, t_max, ctx->opt_scan_exact != 0)) return rc;
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, total * sizeof(uint32_t), ctx->stream));
     {
@@ -681,14 +716,21 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         crossing_kernel<<<bpr * nC, 256, 0, ctx->stream>>>(ctx->d_nodes.p, nE, nE, bpr, ctx->d_jobs.p, 1, p->v_min, nlev, ctx->d_jstar.p);
         EPS_CUDA(ctx, cudaGetLastError());
         bracket_init_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_nodes.p, nE, ctx->d_jobs.p, ctx->d_jstar.p, nC, p->v_min, nlev,
-                                                                         ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, ctx->d_nbelow.p);
+                                                                         ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, ctx->d_nbelow.p,
+                                                                         ctx->d_nbelow.p + nC);
         EPS_CUDA(ctx, cudaGetLastError());
-        ctx->stats.other_launches += 3;
+        ctx->stats.other_launches += 2;
     }
-    // ---- k-section refinement rounds ----
+    // ---- k-section refinement rounds (dense rows [curve][level padded to the CTA packing]) ----
+    const uint32_t pack_rows = 1u << pack_log2_for(M, 512);
+    const uint32_t nlev_pad  = (nlev + pack_rows - 1) / pack_rows * pack_rows;
+    const uint32_t n_rows    = nC * nlev_pad;
+    EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_rows));
+    EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_rows, total)));
     for (uint32_t round = 0; round < p->max_rounds; round++) {
-        check_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
-                                                          ctx->d_jobs_ref.p, ctx->d_nactive.p);
+        EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nactive.p, 0, sizeof(uint32_t), ctx->stream));
+        make_refine_jobs_kernel<<<(n_rows + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, nC, nlev, nlev_pad, p->v_min,
+                                                                              p->rel_tol, M, ctx->d_jobs_ref.p, ctx->d_nactive.p);
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches++;
         EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -696,12 +738,12 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         ctx->stats.d2h_bytes += sizeof(uint32_t);
         const uint32_t n_active = ctx->h_pinned[0];
         if (n_active == 0) break;
-        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_active, M, nullptr, false, t_max, ctx->opt_scan_exact != 0)) return rc;
-        EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_active * sizeof(uint32_t), ctx->stream));
+        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows)) return rc;
+        EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_rows * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;
-        crossing_kernel<<<bpr * n_active, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);
+        crossing_kernel<<<bpr * n_rows, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);
         EPS_CUDA(ctx, cudaGetLastError());
-        bracket_update_kernel<<<(n_active + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_jobs_ref.p, ctx->d_jstar.p, n_active, M, ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p);
+        bracket_update_kernel<<<(n_rows + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_jobs_ref.p, ctx->d_jstar.p, n_rows, M, ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p);
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches += 2;
     }
@@ -718,8 +760,39 @@ int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo
         EPS_CUDA(ctx, cudaMemcpyAsync(n_below, ctx->d_nbelow.p, nC * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += nC * sizeof(uint32_t);
     }
+    if (n_first) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(n_first, ctx->d_nbelow.p + nC, nC * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += nC * sizeof(uint32_t);
+    }
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint64_t n_energies,
+                      uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    return sweep_rows(ctx, GridSpec{E_lo, E_hi, false, 0}, n_energies, nodes, tail_mant, tail_exp);
+}
+
+int eps_sweep_grid(eps_ctx* ctx, const double* E0, const double* dE, uint32_t j0, uint64_t n_energies,
+                   uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    if (ctx && n_energies + j0 >= (1ull << 32)) return fail(ctx, EPS_ERR_INVALID, "j0 + n_energies must stay below 2^32");
+    return sweep_rows(ctx, GridSpec{E0, dE, true, j0}, n_energies, nodes, tail_mant, tail_exp);
+}
+
+int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo, const double* E_hi,
+                     double* levels, double* widths, uint32_t* n_below) {
+    return solve_rows(ctx, p, GridSpec{E_lo, E_hi, false, 0}, levels, widths, n_below, nullptr);
+}
+
+int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double* E0, const double* dE,
+                          uint32_t j0, double* levels, double* widths, uint32_t* n_last, uint32_t* n_first) {
+    if (ctx && p && static_cast<uint64_t>(p->n_coarse) + j0 >= (1ull << 32))
+        return fail(ctx, EPS_ERR_INVALID, "j0 + n_coarse must stay below 2^32");
+    return solve_rows(ctx, p, GridSpec{E0, dE, true, j0}, levels, widths, n_last, n_first);
 }
 
 int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,

@@ -161,6 +161,12 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // the host only selects kStride = 32 / 8 with a factor-2 margin on theta_max
 // (launch_sweep) and kStride = 1 (per-step bit mask) otherwise.
 //
+// Row packing (pack_log2 = g > 0, sequential mode): rows shorter than the CTA (refinement rounds
+// with few points per level) are packed 2^g to a CTA, every row in a slot of kPerCta >> g
+// energies; the caller lays the rows out so that the 2^g rows of a CTA share one curve
+// (jobs[] dense by [curve][level], level count padded to a multiple of 2^g, nE = 0 for idle
+// rows), so the CTA still streams ONE table.  chunks_per_job is 1 in that mode.
+//
 // kScan (transfer-matrix mode, N4): the grid is cut into n_seg segments of whole tiles and a
 // CTA marches ONE segment for kWarps*32 energies; each thread carries two basis solutions of
 // its energy (kEpt == 2, shared fp): A from (X,S) = (1,1) ("flat": psi_a = psi_{a-1}) and B from
@@ -187,7 +193,8 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                      const double* __restrict__ Eexp, const uint64_t out_stride,
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                      int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done,
-                     const uint32_t n_seg, const uint32_t tiles_per_seg, const SegOut seg_out) {
+                     const uint32_t n_seg, const uint32_t tiles_per_seg, const SegOut seg_out,
+                     const uint32_t pack_log2) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
     static_assert(!kScan || (kEpt == 2 && !kTails), "scan mode: two basis chains per energy");
     constexpr uint32_t kPerCta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
@@ -199,10 +206,11 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 
     const uint32_t seg     = kScan ? blockIdx.x % n_seg : 0u;
     const uint32_t cta     = kScan ? blockIdx.x / n_seg : blockIdx.x;
-    const uint32_t job_idx = cta / chunks_per_job;
-    const uint32_t chunk   = cta - job_idx * chunks_per_job;
+    const uint32_t job_idx = (cta / chunks_per_job) << pack_log2;  // first row of this CTA
+    const uint32_t chunk   = cta - (cta / chunks_per_job) * chunks_per_job;
     const Job      job     = jobs[job_idx];
     const CurveDev cv      = curves[job.curve];
+    const uint32_t slot_sz = kPerCta >> pack_log2;                 // energies per packed row slot
     const uint32_t n_steps = cv.n_steps;
     const uint32_t n_tiles_all = (n_steps + kTile - 1) / kTile;
     const uint32_t t_begin = kScan ? min(seg * tiles_per_seg, n_tiles_all) : 0u;
@@ -212,7 +220,15 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     const uint32_t lane    = threadIdx.x & 31;
 
     const uint32_t e_base = chunk * kPerCta;
-    if (e_base >= job.nE) return;  // whole CTA past the end of the row (uniform)
+    uint32_t       cta_energies;  // valid trial energies of this CTA
+    if (pack_log2 == 0) {
+        if (e_base >= job.nE) return;  // whole CTA past the end of the row (uniform)
+        cta_energies = min(job.nE - e_base, kPerCta);
+    } else {
+        cta_energies = 0;
+        for (uint32_t r = 0; r < (1u << pack_log2); r++) cta_energies += min(jobs[job_idx + r].nE, slot_sz);
+        if (cta_energies == 0) return;  // every packed row idle (uniform)
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -234,7 +250,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                 tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t_begin + t) * kTile,
                              kTile * sizeof(double), &full[s]);
             }
-            const uint32_t in_cta   = min(job.nE - e_base, kPerCta);
+            const uint32_t in_cta   = cta_energies;
             const uint32_t my_steps = min(t_end * kTile, n_steps) - min(t_begin * kTile, n_steps);
             atomicAdd(steps_done, static_cast<unsigned long long>(my_steps) * in_cta);
         }
@@ -248,11 +264,13 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     uint32_t n_nodes[kEpt], prev[kEpt];
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
-        uint32_t j = e_base + (kScan ? 0 : i) * (kWarps * 32) + warp * 32 + lane;
-        if (j >= job.nE) j = job.nE - 1;  // keep the warp converged; result discarded
+        const uint32_t t  = (kScan ? 0 : i) * (kWarps * 32) + warp * 32 + lane;  // energy slot in the CTA
+        const Job      jb = pack_log2 ? jobs[job_idx + t / slot_sz] : job;
+        uint32_t       j  = pack_log2 ? t % slot_sz : e_base + t;
+        if (j >= jb.nE) j = jb.nE ? jb.nE - 1 : 0;  // keep the warp converged; result discarded
         double E;
-        if (Eexp != nullptr) E = Eexp[job.e_off + j];
-        else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
+        if (Eexp != nullptr) E = Eexp[jb.e_off + j];
+        else E = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(jb.j0) + j), jb.dE));
         ep[i]      = __ddiv_rn(__dmul_rn(cv.s, E), 12.0);
         c[i]       = kScan ? (i == 1 ? Chain{0.0, 1.0} : Chain{1.0, 1.0}) : Chain{1.0, 0.0};
         expo[i]    = 0;
@@ -348,9 +366,12 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
         renorm(c[i], expo[i]);
-        const uint32_t j = e_base + i * (kWarps * 32) + warp * 32 + lane;
-        if (j < job.nE) {
-            const uint64_t o = static_cast<uint64_t>(job_idx) * out_stride + j;
+        const uint32_t t   = i * (kWarps * 32) + warp * 32 + lane;
+        const uint32_t row = pack_log2 ? job_idx + t / slot_sz : job_idx;
+        const uint32_t j   = pack_log2 ? t % slot_sz : e_base + t;
+        const uint32_t lim = pack_log2 ? min(jobs[row].nE, slot_sz) : job.nE;
+        if (j < lim) {
+            const uint64_t o = static_cast<uint64_t>(row) * out_stride + j;
             nodes_out[o] = n_nodes[i];
             if (kTails) {
                 mant_out[o] = c[i].X;
@@ -481,18 +502,21 @@ __global__ void scatter_fixup_kernel(const uint2* __restrict__ flagged, uint32_t
 // counts, so they reproduce the oracle's orc_solve_levels exactly.
 // ---------------------------------------------------------------------------
 
-// Row c of the coarse sweep: E_j = E_lo[c] + j*dE.
+// Row c of the coarse sweep: E_j = E_lo[c] + j*dE with dE = (E_hi-E_lo)/(nE-1) (grid == 0), or the
+// caller's affine grid E_j = E0[c] + (j0 + j) * dE[c] (grid == 1: a rank's slice of a global
+// grid, reproducing the global grid's energies bit for bit).
 __global__ void make_coarse_jobs_kernel(const double* __restrict__ E_lo,
                                         const double* __restrict__ E_hi, uint32_t n_curves,
-                                        uint32_t nE, Job* __restrict__ jobs) {
+                                        uint32_t nE, int grid, uint32_t j0, Job* __restrict__ jobs) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_curves) return;
     Job jb;
-    jb.E0    = E_lo[c];
-    jb.dE    = nE > 1 ? __ddiv_rn(__dsub_rn(E_hi[c], E_lo[c]), static_cast<double>(nE - 1)) : 0.0;
+    jb.E0 = E_lo[c];
+    if (grid) jb.dE = E_hi[c];
+    else jb.dE = nE > 1 ? __ddiv_rn(__dsub_rn(E_hi[c], E_lo[c]), static_cast<double>(nE - 1)) : 0.0;
     jb.e_off = static_cast<uint64_t>(c) * nE;
     jb.curve = c;
-    jb.j0    = 0;
+    jb.j0    = grid ? j0 : 0u;
     jb.nE    = nE;
     jb.level = 0;
     jb.slot  = c;
@@ -509,6 +533,7 @@ __global__ void crossing_kernel(const uint32_t* __restrict__ nodes, uint64_t str
                                 uint32_t* __restrict__ jstar) {
     const uint32_t  row  = blockIdx.x / blocks_per_row;
     const uint32_t  j    = (blockIdx.x - row * blocks_per_row) * blockDim.x + threadIdx.x;
+    if (jobs[row].nE == 0) return;  // idle refinement row (uniform per block)
     const uint32_t* r    = nodes + static_cast<uint64_t>(row) * stride;
     const uint32_t  lane = threadIdx.x & 31;
     const uint32_t  b    = (j < nE) ? r[j] : 0u;
@@ -531,14 +556,18 @@ __global__ void bracket_init_kernel(const uint32_t* __restrict__ nodes, uint64_t
                                     const Job* __restrict__ jobs, const uint32_t* __restrict__ jstar,
                                     uint32_t n_curves, uint32_t v_min, uint32_t n_lev,
                                     double* __restrict__ lo, double* __restrict__ hi,
-                                    uint32_t* __restrict__ state, uint32_t* __restrict__ n_below) {
+                                    uint32_t* __restrict__ state, uint32_t* __restrict__ n_below,
+                                    uint32_t* __restrict__ n_first) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_curves * n_lev) return;
     const uint32_t c = idx / n_lev, l = idx - c * n_lev, v = v_min + l;
     const Job      jb    = jobs[c];
     const uint32_t first = nodes[static_cast<uint64_t>(c) * stride];
     const uint32_t last  = nodes[static_cast<uint64_t>(c) * stride + jb.nE - 1];
-    if (l == 0) n_below[c] = last;
+    if (l == 0) {
+        n_below[c] = last;
+        n_first[c] = first;
+    }
     const uint32_t j = jstar[idx];
     if (last <= v || first > v || j == kNone || j == 0) {
         lo[idx]    = __longlong_as_double(0x7ff8000000000000LL);
@@ -546,62 +575,49 @@ __global__ void bracket_init_kernel(const uint32_t* __restrict__ nodes, uint64_t
         state[idx] = 0;
         return;
     }
-    lo[idx]    = __dadd_rn(jb.E0, __dmul_rn(static_cast<double>(j - 1), jb.dE));
-    hi[idx]    = __dadd_rn(jb.E0, __dmul_rn(static_cast<double>(j), jb.dE));
+    const unsigned long long jg = static_cast<unsigned long long>(jb.j0) + j;  // index on the global grid
+    lo[idx]    = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(jg - 1), jb.dE));
+    hi[idx]    = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(jg), jb.dE));
     state[idx] = 1;
 }
 
-// Convergence test + ordered compaction of the still-active brackets into the
-// refinement job list (single CTA; a few thousand entries at most).
-__global__ void check_compact_kernel(const double* __restrict__ lo, const double* __restrict__ hi,
-                                     uint32_t* __restrict__ state, uint32_t total, uint32_t n_lev,
-                                     uint32_t v_min, double rel_tol, uint32_t M,
-                                     Job* __restrict__ jobs_out, uint32_t* __restrict__ n_active) {
-    __shared__ uint32_t warp_cnt[32];
-    __shared__ uint32_t running;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < total; base += blockDim.x) {
-        const uint32_t idx  = base + threadIdx.x;
-        bool           flag = false;
-        double         l = 0, h = 0;
-        if (idx < total && state[idx] == 1) {
-            l = lo[idx];
-            h = hi[idx];
-            const double w   = __dsub_rn(h, l);
-            const double mag = fmax(fabs(l), fabs(h));
-            if (w <= __dmul_rn(rel_tol, mag)) state[idx] = 2;
-            else flag = true;
+// Convergence test + refinement rows.  Rows are DENSE: row = curve * n_lev_pad + l (n_lev_pad a
+// multiple of the sweep's rows-per-CTA so that packed rows of a CTA share a curve); a row that is
+// absent, converged or padding gets nE = 0 and costs nothing downstream.
+__global__ void make_refine_jobs_kernel(const double* __restrict__ lo, const double* __restrict__ hi,
+                                        uint32_t* __restrict__ state, uint32_t n_curves, uint32_t n_lev,
+                                        uint32_t n_lev_pad, uint32_t v_min, double rel_tol, uint32_t M,
+                                        Job* __restrict__ jobs_out, uint32_t* __restrict__ n_active) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_curves * n_lev_pad) return;
+    const uint32_t c = row / n_lev_pad, l = row - c * n_lev_pad;
+    Job            jb;
+    jb.E0    = 0.0;
+    jb.dE    = 0.0;
+    jb.e_off = 0;
+    jb.curve = c;
+    jb.j0    = 1;
+    jb.nE    = 0;
+    jb.level = v_min + l;
+    jb.slot  = c * n_lev + l;
+    jb.pad   = 0;
+    if (l < n_lev) {
+        const uint32_t idx = jb.slot;
+        if (state[idx] == 1) {
+            const double a = lo[idx], b = hi[idx];
+            const double w   = __dsub_rn(b, a);
+            const double mag = fmax(fabs(a), fabs(b));
+            if (w <= __dmul_rn(rel_tol, mag)) {
+                state[idx] = 2;
+            } else {
+                jb.E0 = a;
+                jb.dE = __ddiv_rn(__dsub_rn(b, a), static_cast<double>(M + 1));
+                jb.nE = M;
+                atomicAdd(n_active, 1u);
+            }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t off = running;
-        for (uint32_t w = 0; w < warp; w++) off += warp_cnt[w];
-        if (flag) {
-            const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
-            Job            jb;
-            jb.E0    = l;
-            jb.dE    = __ddiv_rn(__dsub_rn(h, l), static_cast<double>(M + 1));
-            jb.e_off = 0;
-            jb.curve = idx / n_lev;
-            jb.j0    = 1;
-            jb.nE    = M;
-            jb.level = v_min + (idx - (idx / n_lev) * n_lev);
-            jb.slot  = idx;
-            jb.pad   = 0;
-            jobs_out[pos] = jb;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) tot += warp_cnt[w];
-            running += tot;
-        }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *n_active = running;
+    jobs_out[row] = jb;
 }
 
 __global__ void bracket_update_kernel(const Job* __restrict__ jobs,
@@ -611,6 +627,7 @@ __global__ void bracket_update_kernel(const Job* __restrict__ jobs,
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_jobs) return;
     const Job      jb  = jobs[r];
+    if (jb.nE == 0) return;  // idle row
     const uint32_t js  = jstar[r];
     const uint32_t m   = (js == kNone) ? M + 1 : js + 1;
     const double   lo0 = jb.E0, hi0 = hi[jb.slot];

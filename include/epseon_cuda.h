@@ -133,6 +133,12 @@ int eps_sweep(eps_ctx* ctx, const double* E, uint64_t n_energies, uint32_t* node
 int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint64_t n_energies,
                       uint32_t* nodes, double* tail_mant, int32_t* tail_exp);
 
+/* Affine grid: E_j = E0[c] + (j0 + j) * dE[c], j = 0..n-1 -- a slice of a larger ("global")
+ * uniform grid with the global grid's energies reproduced bit for bit.  This is what a rank of an
+ * energy-range-sharded job calls. */
+int eps_sweep_grid(eps_ctx* ctx, const double* E0, const double* dE, uint32_t j0, uint64_t n_energies,
+                   uint32_t* nodes, double* tail_mant, int32_t* tail_exp);
+
 /* ---- bracketing + k-section refinement of levels v_min..v_max of every
  * resident curve inside [E_lo[c], E_hi[c]].  Outputs (host):
  *   levels[n_curves][level_count]  (NaN where the level is not in range) --
@@ -141,6 +147,16 @@ int eps_sweep_uniform(eps_ctx* ctx, const double* E_lo, const double* E_hi, uint
  *   n_below[n_curves]              levels below E_hi[c]   (may be NULL). */
 int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo,
                      const double* E_hi, double* levels, double* widths, uint32_t* n_below);
+
+/* Same search with the coarse sweep on the affine grid E_j = E0[c] + (j0 + j) * dE[c],
+ * j = 0..p->n_coarse-1.  n_last / n_first (may be NULL) receive the node counts at the last /
+ * first grid point of every curve.  Energy-range sharding: rank r passes j0 = r * per and
+ * n_coarse = per + 1 (one shared point with its neighbour); every bracket of the global grid then
+ * falls into exactly one rank's slice and the union of the ranks' levels is bit-identical to a
+ * single-device eps_solve_levels over the whole range. */
+int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double* E0, const double* dE,
+                          uint32_t j0, double* levels, double* widths, uint32_t* n_last,
+                          uint32_t* n_first);
 
 /* ---- options / counters.
  * EPS_OPT_SCAN_SEGMENTS: transfer-matrix (scan) path of the sweep for the few-energy, long-grid

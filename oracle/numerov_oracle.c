@@ -68,6 +68,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU baseline (rank 0 only) asks
+ * for the host's cores explicitly. */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* N1. V_i = De * (1 - exp(-a (r_i - re)))^2 on r_i = rmin + i*h,
  * h = (rmax - rmin)/(N-1).  Fills the slot left empty at
  * potential_source.hpp:223-225. */
@@ -226,7 +236,8 @@ void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, d
 }
 
 /* N5 + N6.  Locate levels vmin..vmax of one curve in [E_lo, E_hi]:
- *   coarse:  n_coarse uniform energies, E_j = E_lo + j*dE, dE=(E_hi-E_lo)/(n_coarse-1);
+ *   coarse:  n_coarse energies on the affine grid E_j = E0 + (j0 + j)*dE (a slice of a global
+ *            uniform grid; orc_solve_levels below passes E0 = E_lo, dE=(E_hi-E_lo)/(n_coarse-1), j0 = 0);
  *   bracket: j* = first j with nodes_j > v  ->  [E_{j*-1}, E_{j*}]
  *            (level absent if nodes_last <= v or nodes_0 > v -> NaN);
  *   refine:  rounds of M interior points E_m = lo + m*step, step=(hi-lo)/(M+1),
@@ -237,21 +248,21 @@ void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, d
  *   result:  0.5*(lo+hi).
  * All decisions are integer comparisons of node counts.  Returns the number of
  * refinement rounds used; *steps_done gets grid-steps x energies executed. */
-int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, double E_hi,
-                     uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
+int orc_solve_levels_grid(const double* F, uint32_t n_steps, double s, double E0, double dE, uint64_t j0,
+                          uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
                      uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
-                     uint64_t* steps_done) {
+                          uint32_t* n_first, uint64_t* steps_done) {
     const uint32_t nlev  = vmax - vmin + 1;
     uint64_t       steps = 0;
     uint32_t*      nodes = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_coarse > M ? n_coarse : M));
     double*        lo    = (double*)malloc(sizeof(double) * nlev);
     double*        hi    = (double*)malloc(sizeof(double) * nlev);
     uint8_t*       act   = (uint8_t*)malloc(nlev);
-    const double   dE    = (E_hi - E_lo) / (double)(n_coarse - 1);
 
-    orc_sweep_uniform(F, n_steps, s, E_lo, dE, 0, n_coarse, nodes, 0, 0);
+    orc_sweep_uniform(F, n_steps, s, E0, dE, j0, n_coarse, nodes, 0, 0);
     steps += (uint64_t)n_steps * n_coarse;
     if (n_below_hi) *n_below_hi = nodes[n_coarse - 1];
+    if (n_first) *n_first = nodes[0];
     for (uint32_t l = 0; l < nlev; l++) {
         const uint32_t v = vmin + l;
         act[l]           = 0;
@@ -259,8 +270,8 @@ int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, d
         if (nodes[n_coarse - 1] <= v || nodes[0] > v) continue;
         uint32_t j = 1;
         while (nodes[j] <= v) j++;
-        lo[l]  = E_lo + (double)(j - 1) * dE;
-        hi[l]  = E_lo + (double)j * dE;
+        lo[l]  = E0 + (double)(j0 + j - 1) * dE;
+        hi[l]  = E0 + (double)(j0 + j) * dE;
         act[l] = 1;
     }
     uint32_t round = 0;
@@ -300,6 +311,16 @@ int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, d
     free(hi);
     free(act);
     return (int)round;
+}
+
+/* Uniform coarse grid over [E_lo, E_hi]: dE = (E_hi - E_lo)/(n_coarse - 1), j0 = 0. */
+int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, double E_hi,
+                     uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
+                     uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
+                     uint64_t* steps_done) {
+    const double dE = (E_hi - E_lo) / (double)(n_coarse - 1);
+    return orc_solve_levels_grid(F, n_steps, s, E_lo, dE, 0, n_coarse, vmin, vmax, M, rel_tol, max_rounds,
+                                 levels, widths, n_below_hi, 0, steps_done);
 }
 
 /* N7.  Normalised wavefunction of one level at energy E on the integration

@@ -54,10 +54,12 @@ class Oracle:
     host threads); used for the timed CPU baseline.
     """
 
-    def __init__(self, omp: bool = False):
+    def __init__(self, omp: bool = False, threads: int | None = None):
         build_oracle()
         self.lib = C.CDLL(str(_BUILD / ("liboracle_omp.so" if omp else "liboracle.so")))
         L = self.lib
+        if omp and threads:
+            L.orc_set_threads(C.c_int(int(threads)))
         L.orc_num_threads.restype = C.c_int
         L.orc_scale.restype = C.c_double
         L.orc_scale.argtypes = [C.c_double] * 3
@@ -75,6 +77,11 @@ class Oracle:
                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                        C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64)]
+        L.orc_solve_levels_grid.restype = C.c_int
+        L.orc_solve_levels_grid.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint64,
+                                            C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                            C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_wavefunction.restype = C.c_int64
         L.orc_wavefunction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, _f64p]
 
@@ -136,6 +143,16 @@ class Oracle:
                                            rel_tol, max_rounds, levels, widths, C.byref(nb),
                                            C.byref(st))
         return levels, widths, nb.value, rounds, st.value
+
+    def solve_levels_grid(self, AB, s, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol=1e-12, max_rounds=8):
+        """Coarse grid E_j = E0 + (j0 + j) dE -> (levels, widths, n_last, n_first, rounds, steps)"""
+        nlev = vmax - vmin + 1
+        levels = np.empty(nlev, dtype=np.float64)
+        widths = np.empty(nlev, dtype=np.float64)
+        nb, nf, st = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        rounds = self.lib.orc_solve_levels_grid(AB, AB.size, s, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol,
+                                                max_rounds, levels, widths, C.byref(nb), C.byref(nf), C.byref(st))
+        return levels, widths, nb.value, nf.value, rounds, st.value
 
     def wavefunction(self, AB, s, E, h):
         """-> (psi[n_steps] on the integration window, match index m or -1)"""
