@@ -224,8 +224,8 @@ class Context:
                                             _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
         return psi, mi
 
-    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT = 1, 2
-    CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED = 1, 2
+    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE = 1, 2, 3, 4
+    CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED, CNT_CBANK_LAUNCHES = 1, 2, 3
 
     def set_option(self, option: int, value: int) -> None:
         self._ck(self.lib.eps_set_option(self.h, C.c_int(option), C.c_int64(value)))

@@ -9,6 +9,7 @@
 // CUDA runtime cannot provide the device.
 #include "../../include/epseon_cuda.h"
 #include "numerov_kernels.cuh"
+#include "numerov_cbank.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -86,6 +87,15 @@ struct eps_ctx {
     int64_t          opt_scan_segments = 0;  // 0 auto, 1 never, >= 2 forced segment count
     int64_t          opt_scan_exact    = 1;  // 1: eps_solve_levels also recomputes flagged energies sequentially
     uint64_t         scan_launches = 0, scan_flagged = 0;
+
+    // constant-bank sweep: host copy of the (single) curve's table + per-energy carry
+    std::vector<double> h_F;
+    DevBuf<double>      d_cbX, d_cbS;
+    DevBuf<int32_t>     d_cbexp;
+    DevBuf<uint32_t>    d_cbnodes, d_cbprev;
+    int64_t             opt_cbank = 0;  // 0 auto (large single-curve sweeps), 1 always when the launch qualifies, 2 never
+    int                 cb_ept = 4, cb_threads = 128;
+    uint64_t            cbank_launches = 0;
 
     // wavefunction scratch
     DevBuf<double>   d_wfE, d_wfraw, d_wfin, d_wfpsi, d_wfh;
@@ -225,6 +235,65 @@ cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, 
     return launch_sweep_s<1, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
 }
 
+// Constant-bank sweep (numerov_cbank.cuh): one launch per chunk of kCbChunk steps, the chunk passed
+// by value through the kernel-parameter constant bank.
+template <int kEpt, int kThreads, int kStride, bool kTails>
+cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
+                                 const SweepOut& out) {
+    constexpr uint32_t per_cta = kThreads * kEpt;
+    const uint64_t chunks = (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
+    const uint64_t grid   = chunks * n_jobs;
+    if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
+    const uint32_t n_steps = ctx->curves[0].n_steps;
+    const CbState  st{ctx->d_cbX.p, ctx->d_cbS.p, ctx->d_cbexp.p, ctx->d_cbnodes.p, ctx->d_cbprev.p};
+    static thread_local FChunk chunk;  // 31 KiB staging of the by-value parameter
+    for (uint32_t k0 = 0; k0 < n_steps; k0 += kCbChunk) {
+        const uint32_t len = std::min<uint32_t>(kCbChunk, n_steps - k0);
+        std::memcpy(&chunk, ctx->h_F.data() + k0, len * sizeof(double));
+        if (len < kCbChunk) std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk - len) * sizeof(double));
+        numerov_cbank_kernel<kEpt, kThreads, kStride, kTails><<<static_cast<unsigned>(grid), kThreads, 0, ctx->stream>>>(
+            chunk, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->curves[0].scale, len, k0 == 0 ? 1 : 0,
+            k0 + len >= n_steps ? 1 : 0, st, out.nodes, kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        ctx->cbank_launches++;
+    }
+    return cudaSuccess;
+}
+
+template <int kEpt, int kThreads>
+cudaError_t launch_cbank_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
+    if (stride == 32) return tails ? launch_cbank_variant<kEpt, kThreads, 32, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 32, false>(ctx, j, n, nE, E, out);
+    if (stride == 8) return tails ? launch_cbank_variant<kEpt, kThreads, 8, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 8, false>(ctx, j, n, nE, E, out);
+    return tails ? launch_cbank_variant<kEpt, kThreads, 1, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 1, false>(ctx, j, n, nE, E, out);
+}
+
+int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp, bool tails, int stride,
+                 const SweepOut& out) {
+    const size_t n_out = static_cast<size_t>(n_jobs) * nE;
+    EPS_CUDA(ctx, ctx->d_cbX.reserve(n_out));
+    EPS_CUDA(ctx, ctx->d_cbS.reserve(n_out));
+    EPS_CUDA(ctx, ctx->d_cbexp.reserve(n_out));
+    EPS_CUDA(ctx, ctx->d_cbnodes.reserve(n_out));
+    EPS_CUDA(ctx, ctx->d_cbprev.reserve(n_out));
+    cudaError_t e;
+    if (ctx->cb_ept == 4 && ctx->cb_threads == 128) e = launch_cbank_s<4, 128>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    else if (ctx->cb_ept == 4) e = launch_cbank_s<4, 256>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    else if (ctx->cb_threads == 128) e = launch_cbank_s<2, 128>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    else e = launch_cbank_s<2, 256>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    EPS_CUDA(ctx, e);
+    return EPS_OK;
+}
+
+// Constant-bank kernel policy: measured on the C2 table (profiles/r1_cbank.log) it overtakes the TMA
+// kernel once a launch carries >= ~2 CTAs of 512 energies per SM (+1 % at 151 552 energies, +5 % at
+// 303 104, +9 % at 2^20); below that the per-chunk launch overhead (26 launches per 100k steps) loses.
+bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_rows) {
+    if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->h_F.empty() || ctx->force_ept || pack_log2_for(nE, pack_rows) != 0) return false;
+    if (ctx->opt_cbank == 1) return true;
+    return static_cast<uint64_t>(n_jobs) * nE >= 2ull * 512 * ctx->sm_count;
+}
+
 // Transfer-matrix (scan) policy.  A sweep of E_tot = n_jobs * nE energies occupies
 // ceil(E_tot / 512) SMs with the sequential kernel; when that leaves most of the GPU idle on a
 // long grid, the grid is cut into n_seg segments of whole tiles so that about two 256-energy CTAs
@@ -336,6 +405,8 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     const SweepOut out{ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p};
     if (n_seg >= 2) {
         if (int rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out)) return rc;
+    } else if (use_cbank(ctx, n_jobs, nE, pack_rows)) {
+        if (int rc = launch_cbank(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out)) return rc;
     } else {
         EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out,
                                         ctx->force_ept ? 0 : pack_log2_for(nE, pack_rows)));
@@ -496,6 +567,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_fixm.release(); ctx->d_fixE.release(); ctx->d_segeA.release(); ctx->d_segeB.release(); ctx->d_fixe.release();
         ctx->d_segnA.release(); ctx->d_fixn.release(); ctx->d_nflag.release(); ctx->d_flagged.release();
         ctx->d_jobs_fix.release();
+        ctx->d_cbX.release(); ctx->d_cbS.release(); ctx->d_cbexp.release(); ctx->d_cbnodes.release(); ctx->d_cbprev.release();
         ctx->d_wfE.release();
         ctx->d_wfraw.release();
         ctx->d_wfin.release();
@@ -576,6 +648,8 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     ctx->N      = N;
     ctx->slot   = slot;
     ctx->curves = std::move(infos);
+    if (n_curves == 1) ctx->h_F.assign(ab.begin(), ab.begin() + cds[0].n_steps);
+    else ctx->h_F.clear();
     ctx->n_tiles_max = 0;
     for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
     return EPS_OK;
@@ -858,6 +932,16 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
         case EPS_OPT_SCAN_EXACT:
             ctx->opt_scan_exact = value != 0;
             return EPS_OK;
+        case EPS_OPT_CBANK:
+            EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "cbank: 0 auto, 1 always, 2 never");
+            ctx->opt_cbank = value;
+            return EPS_OK;
+        case EPS_OPT_CBANK_SHAPE:  // tuning: energies per thread * 1000 + threads per CTA
+            EPS_REQUIRE(ctx, (value / 1000 == 2 || value / 1000 == 4) && (value % 1000 == 128 || value % 1000 == 256), EPS_ERR_INVALID,
+                        "cbank shape: (2|4)*1000 + (128|256)");
+            ctx->cb_ept     = static_cast<int>(value / 1000);
+            ctx->cb_threads = static_cast<int>(value % 1000);
+            return EPS_OK;
         default: return fail(ctx, EPS_ERR_INVALID, "unknown option");
     }
 }
@@ -867,6 +951,7 @@ int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value) {
     switch (counter) {
         case EPS_CNT_SCAN_LAUNCHES: *value = ctx->scan_launches; return EPS_OK;
         case EPS_CNT_SCAN_FLAGGED: *value = ctx->scan_flagged; return EPS_OK;
+        case EPS_CNT_CBANK_LAUNCHES: *value = ctx->cbank_launches; return EPS_OK;
         default: return fail(ctx, EPS_ERR_INVALID, "unknown counter");
     }
 }
