@@ -250,7 +250,7 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     for (uint32_t k0 = 0; k0 < n_steps; k0 += kCbChunk) {
         const uint32_t len = std::min<uint32_t>(kCbChunk, n_steps - k0);
         std::memcpy(&chunk, ctx->h_F.data() + k0, len * sizeof(double));
-        if (len < kCbChunk) std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk - len) * sizeof(double));
+        std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk + 2 - len) * sizeof(double));
         numerov_cbank_kernel<kEpt, kThreads, kStride, kTails><<<static_cast<unsigned>(grid), kThreads, 0, ctx->stream>>>(
             chunk, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->curves[0].scale, len, k0 == 0 ? 1 : 0,
             k0 + len >= n_steps ? 1 : 0, st, out.nodes, kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps);

@@ -24,7 +24,7 @@ namespace eps {
 constexpr int kCbChunk = 3968;  // steps per launch: 31 renormalisation blocks, 31 744 B of parameters
 
 struct alignas(16) FChunk {
-    double2 f2[kCbChunk / 2];
+    double2 f2[kCbChunk / 2 + 1];  // + one pad pair: the march loads one pair ahead
 };
 
 struct CbState {  // per-energy carry between chunk launches, [row * out_stride + j]
@@ -84,6 +84,8 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
 
     const uint32_t n_full = len / kRenorm;
     uint32_t       k      = 0;
+    double2        nxt    = P.f2[0];  // software pipeline: the pair of steps (k, k+1) is loaded one pair ahead,
+                                      // across the loop back-edges ptxas will not hoist an LDCU over
 #pragma unroll 1
     for (uint32_t r = 0; r < n_full; r++) {
 #pragma unroll 1
@@ -93,7 +95,8 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
             for (int i = 0; i < kEpt; i++) mask[i] = 0;
 #pragma unroll
             for (int p = 0; p < 16; p++) {
-                const double2 ff = P.f2[(k >> 1) + p];  // uniform index: LDCU.128 into uniform registers
+                const double2 ff = nxt;
+                nxt              = P.f2[(k >> 1) + p + 1];  // uniform index: LDCU into uniform registers
 #pragma unroll
                 for (int i = 0; i < kEpt; i++) {
                     numerov_step(c[i], ff.x, ep[i]);

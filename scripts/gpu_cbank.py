@@ -14,7 +14,7 @@ ctx = cabi.Context(0)
 ctx.set_potentials(w["V"], w["s"])
 n_steps = ctx.curve_info(0).n_steps
 ref = {}
-for shape in (0, 2256, 4128):
+for shape in (0, 4128, 4256):
     ctx.set_option(ctx.OPT_CBANK, 1 if shape else 2)
     if shape:
         ctx.set_option(ctx.OPT_CBANK_SHAPE, shape)
