@@ -102,6 +102,15 @@ namespace epseon::gpu::cpp {
         for (uint32_t k = 0; k < nC; k++)
             for (uint32_t l = 0; l < nlev; l++) out[k][l] = static_cast<FP>(lev[static_cast<size_t>(k) * nlev + l]);
         handle->setResults(std::move(out), std::move(below), ms);
+
+        // ---- N7 (on request): normalised wavefunctions of the located levels ----
+        if (configurator.getWavefunctionOutput() && !stop_token.stop_requested()) {
+            handle->setStatus("computing wavefunctions");
+            std::vector<double> psi(static_cast<size_t>(nC) * nlev * N);
+            detail::check(eps_wavefunctions(ctx, lev.data(), nlev, steps.data(), psi.data(), nullptr), ctx,
+                          "eps_wavefunctions");
+            handle->setWavefunctions(std::move(psi), nC, nlev, N);
+        }
         handle->setStatus("done");
     }
 } // namespace epseon::gpu::cpp

@@ -41,6 +41,7 @@ namespace epseon::gpu::python {
         // additive
         std::vector<std::vector<FP>> get_levels() { return handle->getLevels(); }
         std::vector<uint32_t>        get_level_counts() { return handle->getLevelCounts(); }
+        std::shared_ptr<cpp::TaskHandle<FP>> getHandle() const { return handle; }
         bool                         has_failed() { return handle->hasFailed(); }
         double                       get_device_milliseconds() { return handle->getDeviceMilliseconds(); }
     };
@@ -101,6 +102,12 @@ namespace epseon::gpu::python {
                                        static_cast<FP>(c.getMaxR()), n);
             }
             configurator->setPotentialSource(std::make_shared<cpp::MorsePotentialGenerator<FP>>(std::move(converted)));
+            return *this;
+        }
+
+        // Additive: ask the task to also return normalised wavefunctions.
+        TaskConfigurator& set_wavefunction_output(bool enabled) {
+            configurator->setWavefunctionOutput(enabled);
             return *this;
         }
 

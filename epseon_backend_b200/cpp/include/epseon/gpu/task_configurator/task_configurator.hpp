@@ -22,6 +22,8 @@ namespace epseon::gpu::cpp {
         std::shared_ptr<HardwareConfig<FP>>  hardware_config  = {};
         std::shared_ptr<PotentialSource<FP>> potential_source = {};
         std::shared_ptr<AlgorithmConfig<FP>> algorithm_config = {};
+        // additive: also return the normalised wavefunctions of the located levels
+        bool wavefunction_output = false;
 
         template <typename T>
         static std::shared_ptr<T> clone_or_null(const std::shared_ptr<T>& p) {
@@ -40,12 +42,14 @@ namespace epseon::gpu::cpp {
             std::enable_shared_from_this<TaskConfigurator<FP>>(),
             hardware_config(std::move(o.hardware_config)),
             potential_source(std::move(o.potential_source)),
-            algorithm_config(std::move(o.algorithm_config)) {}
+            algorithm_config(std::move(o.algorithm_config)),
+            wavefunction_output(o.wavefunction_output) {}
         TaskConfigurator& operator=(TaskConfigurator&& o) noexcept {
             if (this != &o) {
-                hardware_config  = std::move(o.hardware_config);
-                potential_source = std::move(o.potential_source);
-                algorithm_config = std::move(o.algorithm_config);
+                hardware_config     = std::move(o.hardware_config);
+                potential_source    = std::move(o.potential_source);
+                algorithm_config    = std::move(o.algorithm_config);
+                wavefunction_output = o.wavefunction_output;
             }
             return *this;
         }
@@ -53,12 +57,14 @@ namespace epseon::gpu::cpp {
             std::enable_shared_from_this<TaskConfigurator<FP>>(),
             hardware_config(clone_or_null(o.hardware_config)),
             potential_source(clone_or_null(o.potential_source)),
-            algorithm_config(clone_or_null(o.algorithm_config)) {}
+            algorithm_config(clone_or_null(o.algorithm_config)),
+            wavefunction_output(o.wavefunction_output) {}
         TaskConfigurator& operator=(const TaskConfigurator& o) {
             if (this != &o) {
-                hardware_config  = clone_or_null(o.hardware_config);
-                potential_source = clone_or_null(o.potential_source);
-                algorithm_config = clone_or_null(o.algorithm_config);
+                hardware_config     = clone_or_null(o.hardware_config);
+                potential_source    = clone_or_null(o.potential_source);
+                algorithm_config    = clone_or_null(o.algorithm_config);
+                wavefunction_output = o.wavefunction_output;
             }
             return *this;
         }
@@ -81,6 +87,12 @@ namespace epseon::gpu::cpp {
             return *this;
         }
         [[nodiscard]] std::shared_ptr<AlgorithmConfig<FP>> getAlgorithmConfig() const { return algorithm_config; }
+
+        TaskConfigurator& setWavefunctionOutput(bool enabled) {
+            wavefunction_output = enabled;
+            return *this;
+        }
+        [[nodiscard]] bool getWavefunctionOutput() const { return wavefunction_output; }
 
         [[nodiscard]] bool isConfigured() const {
             return static_cast<bool>(hardware_config) && static_cast<bool>(potential_source) &&

@@ -38,6 +38,8 @@ namespace epseon::gpu::cpp {
         std::vector<std::vector<FP>> levels;       // [curve][level - min_level], NaN = not found
         std::vector<uint32_t>        level_counts; // [curve] levels below the search ceiling
         double                       device_ms = 0.0;
+        std::vector<double>          wavefunctions;           // [curve][level][point], flat; empty unless requested
+        uint32_t                     wf_curves = 0, wf_levels = 0, wf_points = 0;
 
         std::jthread worker = {}; // last member: joins before the rest is destroyed
 
@@ -108,6 +110,22 @@ namespace epseon::gpu::cpp {
             levels       = std::move(levels_);
             level_counts = std::move(counts_);
             device_ms    = ms;
+        }
+        void setWavefunctions(std::vector<double> psi, uint32_t n_curves, uint32_t n_levels, uint32_t n_points) {
+            std::lock_guard<std::mutex> g(result_mutex);
+            wavefunctions = std::move(psi);
+            wf_curves     = n_curves;
+            wf_levels     = n_levels;
+            wf_points     = n_points;
+        }
+        // Normalised wavefunctions psi[curve][level - min_level][grid point] (h * sum psi^2 = 1, first
+        // lobe positive, zero rows for levels that were not found); dims = {curves, levels, points}.
+        [[nodiscard]] std::vector<double> getWavefunctions(uint32_t dims[3]) const {
+            std::lock_guard<std::mutex> g(result_mutex);
+            dims[0] = wf_curves;
+            dims[1] = wf_levels;
+            dims[2] = wf_points;
+            return wavefunctions;
         }
         [[nodiscard]] std::string getStatusMessage() const {
             std::lock_guard<std::mutex> g(result_mutex);

@@ -5,9 +5,11 @@
 
 #include "epseon/gpu/common.hpp"
 
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstring>
 #include <tuple>
 
 namespace py = pybind11;
@@ -55,6 +57,17 @@ namespace epseon::gpu::python {
                 .def("get_levels", &H::get_levels,
                      "Vibrational level energies [curve][level - min_level] (NaN where a level was not found).")
                 .def("get_level_counts", &H::get_level_counts, "Number of levels below the search ceiling, per curve.")
+                .def("get_wavefunctions",
+                     [](H& h) {
+                         uint32_t   d[3] = {0, 0, 0};
+                         const auto psi  = h.getHandle()->getWavefunctions(d);
+                         py::array_t<double> out({static_cast<py::ssize_t>(d[0]), static_cast<py::ssize_t>(d[1]),
+                                                  static_cast<py::ssize_t>(d[2])});
+                         if (!psi.empty()) std::memcpy(out.mutable_data(), psi.data(), psi.size() * sizeof(double));
+                         return out;
+                     },
+                     "Normalised wavefunctions as a numpy array [curve][level - min_level][grid point] "
+                     "(empty unless set_wavefunction_output(True) was configured).")
                 .def("has_failed", &H::has_failed, "True when the worker stopped with an error (see status message).")
                 .def("get_device_milliseconds", &H::get_device_milliseconds, "CUDA-event time of the level solve.")
                 .doc() = "Handle object for referencing GPU compute task.";
@@ -69,6 +82,9 @@ namespace epseon::gpu::python {
                 .def("set_morse_potential", &C::set_morse_potential, py::arg("configurations"),
                      py::return_value_policy::reference,
                      "Set potential data source configuration for GPU compute task.")
+                .def("set_wavefunction_output", &C::set_wavefunction_output, py::arg("enabled"),
+                     py::return_value_policy::reference,
+                     "Also compute the normalised wavefunctions of the located levels (TaskHandle.get_wavefunctions).")
                 .def("set_potential_files", &C::set_potential_files, py::arg("file_names"),
                      py::return_value_policy::reference, "Use tabulated 'r V' text files as potential source.")
                 .def("set_vibwa_algorithm", &C::set_vibwa_algorithm, py::arg("mass_atom_0"), py::arg("mass_atom_1"),

@@ -247,3 +247,33 @@ def test_failure_is_reported_not_fatal(gpu_mod):
     handle.wait()
     assert handle.is_done() and handle.has_failed()
     assert handle.get_status_message().startswith("failed:")
+
+
+@pytest.mark.gpu
+def test_wavefunctions_through_python_api(gpu_mod, oracle):
+    """Additive surface: set_wavefunction_output(True) -> TaskHandle.get_wavefunctions() returns the
+    normalised wavefunctions [curve][level][point] of the levels the task located."""
+    interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
+    cfg = _configure_task(gpu_mod, interface.get_task_configurator("float64"), max_level=5)
+    assert cfg.set_wavefunction_output(True) is cfg
+    handle = interface.submit_task(cfg)
+    handle.wait()
+    assert not handle.has_failed(), handle.get_status_message()
+    psi = handle.get_wavefunctions()
+    levels = np.array(handle.get_levels())
+    assert psi.shape == (2, 6, 16500) and psi.dtype == np.float64
+    h = W.grid_h(0.0, 10.0, 16500)
+    for v in range(6):
+        p = psi[0, v]
+        assert abs(h * np.sum(p * p) - 1.0) < 1e-12
+        nz = p[np.abs(p) > 1e-9 * np.abs(p).max()]
+        assert int(np.sum(np.signbit(nz[1:]) != np.signbit(nz[:-1]))) == v
+    V = oracle.morse(5500.0, 0.6, 10.0, 0.0, 10.0, 16500)
+    s = oracle.scale(87.62, 87.62, h)
+    F, i0, n, _ = oracle.prep(V, s)
+    ref, m = oracle.wavefunction(F, s, levels[0, 3], h)
+    assert np.abs(psi[0, 3, i0:i0 + n] - ref).max() <= 1e-12 * np.abs(ref).max()
+    # not requested -> empty array
+    handle2 = interface.submit_task(_configure_task(gpu_mod, interface.get_task_configurator("float64")))
+    handle2.wait()
+    assert handle2.get_wavefunctions().size == 0
