@@ -49,7 +49,7 @@ METRIC = "numerov_grid_steps_x_trial_energies_per_s"
 FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 
-C2 = dict(N=100_000, n_coarse=65_536, refine_points=4096, rel_tol=1e-10, max_rounds=8, v_max=16)
+C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
 C3 = dict(N=1_000_000, nE=4096)
 C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=64, rel_tol=1e-10, max_rounds=8, v_max=7)
 C5 = dict(N=200_000, nE=1 << 24)

@@ -164,8 +164,11 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
                                  const SweepOut& out, uint32_t n_seg, uint32_t tiles_per_seg, const SegOut& so,
                                  uint32_t pack_log2 = 0) {
     constexpr uint32_t per_cta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
-    const uint64_t chunks = pack_log2 ? 1 : (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
-    const uint64_t grid   = pack_log2 ? ((n_jobs + (1u << pack_log2) - 1) >> pack_log2) : chunks * n_jobs * (kScan ? n_seg : 1u);
+    const bool     flat   = pack_log2 == kFlatRows;
+    const uint64_t chunks = flat ? n_jobs : pack_log2 ? 1 : (static_cast<uint64_t>(nE) + per_cta - 1) / per_cta;
+    const uint64_t grid   = flat        ? (static_cast<uint64_t>(n_jobs) * nE + per_cta - 1) / per_cta
+                            : pack_log2 ? ((n_jobs + (1u << pack_log2) - 1) >> pack_log2)
+                                        : chunks * n_jobs * (kScan ? n_seg : 1u);
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
     auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan>;
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
@@ -289,7 +292,8 @@ int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
 // kernel once a launch carries >= ~2 CTAs of 512 energies per SM (+1 % at 151 552 energies, +5 % at
 // 303 104, +9 % at 2^20); below that the per-chunk launch overhead (26 launches per 100k steps) loses.
 bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_rows) {
-    if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->h_F.empty() || ctx->force_ept || pack_log2_for(nE, pack_rows) != 0) return false;
+    if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->h_F.empty() || ctx->force_ept) return false;
+    if (pack_rows != kFlatRows && pack_log2_for(nE, pack_rows) != 0) return false;  // (flat rows: cbank uses per-row CTAs instead)
     if (ctx->opt_cbank == 1) return true;
     return static_cast<uint64_t>(n_jobs) * nE >= 2ull * 512 * ctx->sm_count;
 }
@@ -408,8 +412,8 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     } else if (use_cbank(ctx, n_jobs, nE, pack_rows)) {
         if (int rc = launch_cbank(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out)) return rc;
     } else {
-        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out,
-                                        ctx->force_ept ? 0 : pack_log2_for(nE, pack_rows)));
+        const uint32_t pk = ctx->force_ept ? 0 : pack_rows == kFlatRows ? kFlatRows : pack_log2_for(nE, pack_rows);
+        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out, pk));
     }
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
@@ -795,16 +799,25 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches += 2;
     }
-    // ---- k-section refinement rounds (dense rows [curve][level padded to the CTA packing]) ----
-    const uint32_t pack_rows = 1u << pack_log2_for(M, 512);
-    const uint32_t nlev_pad  = (nlev + pack_rows - 1) / pack_rows * pack_rows;
-    const uint32_t n_rows    = nC * nlev_pad;
-    EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_rows));
-    EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_rows, total)));
+    // ---- k-section refinement rounds ----
+    // One curve resident: the active brackets are compacted into rows that are swept with the
+    // flat-row mapping (full CTAs).  Several curves: dense rows [curve][level padded to the CTA
+    // packing] so that the 2^g short rows packed into a CTA share a curve.
+    const bool     flat      = nC == 1 && !ctx->force_ept;
+    const uint32_t pack_rows = flat ? kFlatRows : 1u << pack_log2_for(M, 512);
+    const uint32_t nlev_pad  = flat ? nlev : (nlev + pack_rows - 1) / pack_rows * pack_rows;
+    const uint32_t n_dense   = nC * nlev_pad;
+    EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_dense));
+    EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_dense, total)));
     for (uint32_t round = 0; round < p->max_rounds; round++) {
-        EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nactive.p, 0, sizeof(uint32_t), ctx->stream));
-        make_refine_jobs_kernel<<<(n_rows + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, nC, nlev, nlev_pad, p->v_min,
-                                                                              p->rel_tol, M, ctx->d_jobs_ref.p, ctx->d_nactive.p);
+        if (flat) {
+            compact_refine_jobs_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
+                                                                  ctx->d_jobs_ref.p, ctx->d_nactive.p);
+        } else {
+            EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nactive.p, 0, sizeof(uint32_t), ctx->stream));
+            make_refine_jobs_kernel<<<(n_dense + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, nC, nlev, nlev_pad, p->v_min,
+                                                                                   p->rel_tol, M, ctx->d_jobs_ref.p, ctx->d_nactive.p);
+        }
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches++;
         EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -812,6 +825,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         ctx->stats.d2h_bytes += sizeof(uint32_t);
         const uint32_t n_active = ctx->h_pinned[0];
         if (n_active == 0) break;
+        const uint32_t n_rows = flat ? n_active : n_dense;
         if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows)) return rc;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_rows * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;

@@ -25,6 +25,7 @@ constexpr int      kStages        = 4;     // TMA ring depth
 // 32 * kWarps * kEpt trial energies per CTA.
 constexpr int      kRenorm        = 128;   // exponent renormalisation period (steps)
 constexpr uint32_t kNone          = 0xffffffffu;
+constexpr uint32_t kFlatRows      = 31;    // pack_log2 value selecting the flat-row mapping
 
 // One potential curve resident in HBM: its coefficient table F_k = (1 - q_k)/12
 // lives at F[f_off .. f_off + slot), slot a multiple of kTile, padded with 1/12.
@@ -166,6 +167,9 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // energies; the caller lays the rows out so that the 2^g rows of a CTA share one curve
 // (jobs[] dense by [curve][level], level count padded to a multiple of 2^g, nE = 0 for idle
 // rows), so the CTA still streams ONE table.  chunks_per_job is 1 in that mode.
+// Flat rows (pack_log2 == kFlatRows, launches whose rows all sit on ONE curve and all have nE
+// energies): the CTA takes kPerCta consecutive energies of the flattened (row, j) index space, so
+// rows may straddle CTAs and every CTA but the last is full -- 17 rows x 4457 points fill 148 CTAs.
 //
 // kScan (transfer-matrix mode, N4): the grid is cut into n_seg segments of whole tiles and a
 // CTA marches ONE segment for kWarps*32 energies; each thread carries two basis solutions of
@@ -206,11 +210,14 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 
     const uint32_t seg     = kScan ? blockIdx.x % n_seg : 0u;
     const uint32_t cta     = kScan ? blockIdx.x / n_seg : blockIdx.x;
-    const uint32_t job_idx = (cta / chunks_per_job) << pack_log2;  // first row of this CTA
-    const uint32_t chunk   = cta - (cta / chunks_per_job) * chunks_per_job;
+    const bool     flat    = !kScan && pack_log2 == kFlatRows;
+    const uint32_t job_idx = flat ? 0u : (cta / chunks_per_job) << pack_log2;  // first row of this CTA
+    const uint32_t chunk   = flat ? 0u : cta - (cta / chunks_per_job) * chunks_per_job;
     const Job      job     = jobs[job_idx];
     const CurveDev cv      = curves[job.curve];
-    const uint32_t slot_sz = kPerCta >> pack_log2;                 // energies per packed row slot
+    const uint32_t slot_sz = flat ? job.nE : kPerCta >> pack_log2;  // energies per row (flat) / packed row slot
+    const uint64_t flat0   = static_cast<uint64_t>(cta) * kPerCta;  // flat mode: first (row * nE + j) of this CTA
+    const uint64_t flat_n  = static_cast<uint64_t>(chunks_per_job) * job.nE;  // flat mode: chunks_per_job carries n_rows
     const uint32_t n_steps = cv.n_steps;
     const uint32_t n_tiles_all = (n_steps + kTile - 1) / kTile;
     const uint32_t t_begin = kScan ? min(seg * tiles_per_seg, n_tiles_all) : 0u;
@@ -221,7 +228,10 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 
     const uint32_t e_base = chunk * kPerCta;
     uint32_t       cta_energies;  // valid trial energies of this CTA
-    if (pack_log2 == 0) {
+    if (flat) {
+        if (flat0 >= flat_n) return;
+        cta_energies = static_cast<uint32_t>(min(static_cast<uint64_t>(kPerCta), flat_n - flat0));
+    } else if (pack_log2 == 0) {
         if (e_base >= job.nE) return;  // whole CTA past the end of the row (uniform)
         cta_energies = min(job.nE - e_base, kPerCta);
     } else {
@@ -265,8 +275,16 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
     for (int i = 0; i < kEpt; i++) {
         const uint32_t t  = (kScan ? 0 : i) * (kWarps * 32) + warp * 32 + lane;  // energy slot in the CTA
-        const Job      jb = pack_log2 ? jobs[job_idx + t / slot_sz] : job;
-        uint32_t       j  = pack_log2 ? t % slot_sz : e_base + t;
+        uint32_t row_i = job_idx, j = e_base + t;
+        if (flat) {
+            const uint64_t f = min(flat0 + t, flat_n - 1);  // clamp: keeps the warp converged; result discarded
+            row_i            = static_cast<uint32_t>(f / slot_sz);
+            j                = static_cast<uint32_t>(f - static_cast<uint64_t>(row_i) * slot_sz);
+        } else if (pack_log2) {
+            row_i = job_idx + t / slot_sz;
+            j     = t % slot_sz;
+        }
+        const Job jb = (flat || pack_log2) ? jobs[row_i] : job;
         if (j >= jb.nE) j = jb.nE ? jb.nE - 1 : 0;  // keep the warp converged; result discarded
         double E;
         if (Eexp != nullptr) E = Eexp[jb.e_off + j];
@@ -367,9 +385,17 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     for (int i = 0; i < kEpt; i++) {
         renorm(c[i], expo[i]);
         const uint32_t t   = i * (kWarps * 32) + warp * 32 + lane;
-        const uint32_t row = pack_log2 ? job_idx + t / slot_sz : job_idx;
-        const uint32_t j   = pack_log2 ? t % slot_sz : e_base + t;
-        const uint32_t lim = pack_log2 ? min(jobs[row].nE, slot_sz) : job.nE;
+        uint32_t row = job_idx, j = e_base + t, lim = job.nE;
+        if (flat) {
+            const uint64_t f = flat0 + t;
+            row              = static_cast<uint32_t>(f / slot_sz);
+            j                = static_cast<uint32_t>(f - static_cast<uint64_t>(row) * slot_sz);
+            lim              = f < flat_n ? slot_sz : 0u;
+        } else if (pack_log2) {
+            row = job_idx + t / slot_sz;
+            j   = t % slot_sz;
+            lim = min(jobs[row].nE, slot_sz);
+        }
         if (j < lim) {
             const uint64_t o = static_cast<uint64_t>(row) * out_stride + j;
             nodes_out[o] = n_nodes[i];
@@ -579,6 +605,60 @@ __global__ void bracket_init_kernel(const uint32_t* __restrict__ nodes, uint64_t
     lo[idx]    = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(jg - 1), jb.dE));
     hi[idx]    = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(jg), jb.dE));
     state[idx] = 1;
+}
+
+// Convergence test + ORDERED COMPACTION of the still-active brackets into refinement rows (used when
+// one curve is resident: the compact rows are then swept with the flat-row mapping).  Single CTA;
+// a few thousand (curve, level) entries at most.
+__global__ void compact_refine_jobs_kernel(const double* __restrict__ lo, const double* __restrict__ hi,
+                                           uint32_t* __restrict__ state, uint32_t total, uint32_t n_lev,
+                                           uint32_t v_min, double rel_tol, uint32_t M,
+                                           Job* __restrict__ jobs_out, uint32_t* __restrict__ n_active) {
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ uint32_t running;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < total; base += blockDim.x) {
+        const uint32_t idx  = base + threadIdx.x;
+        bool           flag = false;
+        double         l = 0, h = 0;
+        if (idx < total && state[idx] == 1) {
+            l = lo[idx];
+            h = hi[idx];
+            const double w   = __dsub_rn(h, l);
+            const double mag = fmax(fabs(l), fabs(h));
+            if (w <= __dmul_rn(rel_tol, mag)) state[idx] = 2;
+            else flag = true;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = running;
+        for (uint32_t w = 0; w < warp; w++) off += warp_cnt[w];
+        if (flag) {
+            const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
+            Job            jb;
+            jb.E0    = l;
+            jb.dE    = __ddiv_rn(__dsub_rn(h, l), static_cast<double>(M + 1));
+            jb.e_off = 0;
+            jb.curve = idx / n_lev;
+            jb.j0    = 1;
+            jb.nE    = M;
+            jb.level = v_min + (idx - (idx / n_lev) * n_lev);
+            jb.slot  = idx;
+            jb.pad   = 0;
+            jobs_out[pos] = jb;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) tot += warp_cnt[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_active = running;
 }
 
 // Convergence test + refinement rows.  Rows are DENSE: row = curve * n_lev_pad + l (n_lev_pad a
