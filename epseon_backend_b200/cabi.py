@@ -224,7 +224,7 @@ class Context:
                                             _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
         return psi, mi
 
-    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE = 1, 2, 3, 4
+    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE, OPT_CBANK_PDL = 1, 2, 3, 4, 5
     CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED, CNT_CBANK_LAUNCHES = 1, 2, 3
 
     def set_option(self, option: int, value: int) -> None:

@@ -61,7 +61,8 @@ struct eps_ctx {
     // resident potentials
     uint32_t                    nC = 0, N = 0;
     uint64_t                    slot = 0;  // doubles per curve
-    DevBuf<double>              d_F;
+    DevBuf<double>              d_F, d_V, d_scale;
+    DevBuf<PrepOut>             d_prep;
     DevBuf<CurveDev>            d_curves;
     std::vector<eps_curve_info> curves;
 
@@ -94,7 +95,7 @@ struct eps_ctx {
     DevBuf<int32_t>     d_cbexp;
     DevBuf<uint32_t>    d_cbnodes, d_cbprev;
     int64_t             opt_cbank = 0;  // 0 auto (large single-curve sweeps), 1 always when the launch qualifies, 2 never
-    int                 cb_ept = 4, cb_threads = 128;
+    int                 cb_ept = 4, cb_threads = 128, cb_pdl = 1;
     uint64_t            cbank_launches = 0;
 
     // wavefunction scratch
@@ -254,10 +255,19 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
         const uint32_t len = std::min<uint32_t>(kCbChunk, n_steps - k0);
         std::memcpy(&chunk, ctx->h_F.data() + k0, len * sizeof(double));
         std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk + 2 - len) * sizeof(double));
-        numerov_cbank_kernel<kEpt, kThreads, kStride, kTails><<<static_cast<unsigned>(grid), kThreads, 0, ctx->stream>>>(
-            chunk, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, ctx->curves[0].scale, len, k0 == 0 ? 1 : 0,
-            k0 + len >= n_steps ? 1 : 0, st, out.nodes, kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps);
-        cudaError_t e = cudaGetLastError();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim  = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream   = ctx->stream;
+        cudaLaunchAttribute attr{};
+        attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs    = &attr;
+        cfg.numAttrs = (ctx->cb_pdl && grid >= 2ull * ctx->sm_count) ? 1 : 0;  // single-wave grids: early-resident CTAs land unevenly (-12 %)
+        cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails>, chunk, d_jobs,
+                                           static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
+                                           k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, st, out.nodes, kTails ? out.mant : nullptr,
+                                           kTails ? out.expo : nullptr, ctx->d_steps);
         if (e != cudaSuccess) return e;
         ctx->cbank_launches++;
     }
@@ -550,6 +560,9 @@ int eps_ctx_destroy(eps_ctx* ctx) {
     if (ctx->dev >= 0 && cudaSetDevice(ctx->dev) == cudaSuccess) {
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         ctx->d_F.release();
+        ctx->d_V.release();
+        ctx->d_scale.release();
+        ctx->d_prep.release();
         ctx->d_curves.release();
         ctx->d_jobs.release();
         ctx->d_jobs_ref.release();
@@ -602,6 +615,8 @@ int eps_sync(eps_ctx* ctx) {
 
 // Preparation (spec DESIGN.md section 3.2): q = s V, window [i0, iend] around the
 // minimum with q - q_min <= T_MAX, coefficient table F_k = (1 - q_{i0+k}) / 12.
+// Preparation (spec DESIGN.md section 3.2) runs on the device: the raw table goes up once,
+// prep_curves_kernel derives window + coefficient table per curve, 32 B per curve come back.
 int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
                        const double* scale) {
     if (int rc = bind(ctx)) return rc;
@@ -609,51 +624,44 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     EPS_REQUIRE(ctx, n_curves >= 1 && n_points >= 3, EPS_ERR_INVALID, "need >=1 curve of >=3 points");
     const uint32_t N    = n_points;
     const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
-    std::vector<double>         ab(static_cast<size_t>(slot) * n_curves, 1.0 / 12.0);
-    std::vector<CurveDev>       cds(n_curves);
-    std::vector<eps_curve_info> infos(n_curves);
-    for (uint32_t c = 0; c < n_curves; c++) {
-        const double* v = V + static_cast<size_t>(c) * N;
-        const double  s = scale[c];
-        EPS_REQUIRE(ctx, std::isfinite(s) && s > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
-        uint32_t m = 0;
-        for (uint32_t i = 0; i < N; i++) {
-            EPS_REQUIRE(ctx, std::isfinite(v[i]), EPS_ERR_RANGE, "potential table holds a non-finite value");
-            if (s * v[i] < s * v[m]) m = i;
-        }
-        const double qmin = s * v[m];
-        const double thr  = qmin + kTMax;
-        uint32_t     ilo  = 0;
-        for (uint32_t j = 0; j < m; j++)
-            if (s * v[j] > thr) ilo = j + 1;
-        uint32_t ihi = N - 1;
-        for (uint32_t j = N - 1; j > m; j--)
-            if (s * v[j] > thr) ihi = j - 1;
-        const uint32_t i0   = ilo < 1 ? 1 : ilo;
-        const uint32_t iend = (ihi + 1 < N - 1) ? ihi + 1 : N - 1;
-        EPS_REQUIRE(ctx, iend >= i0 + 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
-        const uint32_t n   = iend - i0;
-        double*        dst = ab.data() + static_cast<size_t>(c) * slot;
-        for (uint32_t k = 0; k < n; k++) {
-            const double q = s * v[i0 + k];
-            dst[k]         = (1.0 - q) / 12.0;
-        }
-        cds[c]   = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, v[m]};
-        infos[c] = eps_curve_info{i0, n, s, v[m], v[N - 1]};
-    }
+    for (uint32_t c = 0; c < n_curves; c++)
+        EPS_REQUIRE(ctx, std::isfinite(scale[c]) && scale[c] > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
+    const size_t n_v = static_cast<size_t>(N) * n_curves, n_f = static_cast<size_t>(slot) * n_curves;
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    EPS_CUDA(ctx, ctx->d_F.reserve(ab.size()));
+    EPS_CUDA(ctx, ctx->d_V.reserve(n_v));
+    EPS_CUDA(ctx, ctx->d_scale.reserve(n_curves));
+    EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
+    EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
     EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_F.p, ab.data(), ab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_curves.p, cds.data(), cds.size() * sizeof(CurveDev), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_V.p, V, n_v * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scale.p, scale, n_curves * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (n_v + n_curves) * sizeof(double);
+    prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    std::vector<PrepOut> po(n_curves);
+    EPS_CUDA(ctx, cudaMemcpyAsync(po.data(), ctx->d_prep.p, n_curves * sizeof(PrepOut), cudaMemcpyDeviceToHost, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.h2d_bytes += ab.size() * sizeof(double) + cds.size() * sizeof(CurveDev);
+    ctx->stats.d2h_bytes += n_curves * sizeof(PrepOut);
+    ctx->nC = 0;  // invalid until every curve checked out
+    for (uint32_t c = 0; c < n_curves; c++) {
+        EPS_REQUIRE(ctx, po[c].status != 1, EPS_ERR_RANGE, "potential table holds a non-finite value");
+        EPS_REQUIRE(ctx, po[c].status != 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
+    }
+    std::vector<eps_curve_info> infos(n_curves);
+    for (uint32_t c = 0; c < n_curves; c++) infos[c] = eps_curve_info{po[c].i0, po[c].n_steps, scale[c], po[c].v_min, po[c].v_last};
     ctx->nC     = n_curves;
     ctx->N      = N;
     ctx->slot   = slot;
     ctx->curves = std::move(infos);
-    if (n_curves == 1) ctx->h_F.assign(ab.begin(), ab.begin() + cds[0].n_steps);
-    else ctx->h_F.clear();
+    if (n_curves == 1) {  // host copy of the table for the constant-bank kernel's by-value chunks
+        ctx->h_F.resize(po[0].n_steps);
+        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_F.data(), ctx->d_F.p, po[0].n_steps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += po[0].n_steps * sizeof(double);
+    } else {
+        ctx->h_F.clear();
+    }
     ctx->n_tiles_max = 0;
     for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
     return EPS_OK;
@@ -949,6 +957,9 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
         case EPS_OPT_CBANK:
             EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "cbank: 0 auto, 1 always, 2 never");
             ctx->opt_cbank = value;
+            return EPS_OK;
+        case EPS_OPT_CBANK_PDL:
+            ctx->cb_pdl = value != 0;
             return EPS_OK;
         case EPS_OPT_CBANK_SHAPE:  // tuning: energies per thread * 1000 + threads per CTA
             EPS_REQUIRE(ctx, (value / 1000 == 2 || value / 1000 == 4) && (value % 1000 == 128 || value % 1000 == 256), EPS_ERR_INVALID,

@@ -728,6 +728,120 @@ __global__ void finalize_levels_kernel(const double* __restrict__ lo, const doub
 }
 
 // ---------------------------------------------------------------------------
+// Preparation on the device (spec DESIGN.md section 3.2; oracle: orc_prep).  One CTA per curve:
+// first argmin of q = s V, the window around it with q - q_min <= T_MAX, the coefficient table
+// F_k = (1 - q_{i0+k}) / 12 written into the curve's slot (padded with 1/12).  Every value is
+// produced by the same single IEEE operations as on the host, so the table is bit-identical to
+// the oracle's.  status[c]: 0 ok, 1 non-finite table value, 2 window shorter than 2 steps.
+// ---------------------------------------------------------------------------
+struct PrepOut {  // one per curve, read back by the host
+    uint32_t i0, n_steps, status, pad;
+    double   v_min, v_last;
+};
+
+constexpr int kPrepThreads = 512;
+
+__global__ void __launch_bounds__(kPrepThreads)
+prep_curves_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint64_t slot,
+                   double t_max, double* __restrict__ F, CurveDev* __restrict__ curves,
+                   PrepOut* __restrict__ out) {
+    __shared__ double   red_q[kPrepThreads / 32];
+    __shared__ uint32_t red_i[kPrepThreads / 32];
+    __shared__ uint32_t red_a[kPrepThreads / 32], red_b[kPrepThreads / 32], red_bad[kPrepThreads / 32];
+    __shared__ double   qmin_sh;
+    __shared__ uint32_t m_sh, ilo_sh, ihi_sh, bad_sh;
+    const uint32_t c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double*  v = V + static_cast<uint64_t>(c) * N;
+    const double   s = scale[c];
+
+    // ---- first argmin of q (ties -> smallest index), non-finite check ----
+    double   bq  = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+    uint32_t bi  = kNone, bad = 0;
+    for (uint32_t i = tid; i < N; i += kPrepThreads) {
+        const double vi = v[i];
+        if (!isfinite(vi)) bad = 1;
+        const double q = __dmul_rn(s, vi);
+        if (q < bq) {  // strided ascending i per thread: strict < keeps the first index
+            bq = q;
+            bi = i;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double   oq = __shfl_xor_sync(0xffffffffu, bq, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        if (oq < bq || (oq == bq && oi < bi)) {
+            bq = oq;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        red_q[warp]   = bq;
+        red_i[warp]   = bi;
+        red_bad[warp] = bad;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double   q = red_q[0];
+        uint32_t i = red_i[0], b = red_bad[0];
+        for (int w = 1; w < kPrepThreads / 32; w++) {
+            b |= red_bad[w];
+            if (red_q[w] < q || (red_q[w] == q && red_i[w] < i)) {
+                q = red_q[w];
+                i = red_i[w];
+            }
+        }
+        qmin_sh = q;
+        m_sh    = i;
+        bad_sh  = b;
+    }
+    __syncthreads();
+    const uint32_t m   = m_sh;
+    const double   thr = __dadd_rn(qmin_sh, t_max);
+
+    // ---- window: ilo = 1 + last j < m with q_j > thr (else 0); ihi = first j > m with q_j > thr, minus 1 (else N-1) ----
+    uint32_t a = 0, b = N;  // a: (last j<m above thr) + 1;  b: first j>m above thr (N = none)
+    for (uint32_t i = tid; i < N; i += kPrepThreads) {
+        const double q = __dmul_rn(s, v[i]);
+        if (q > thr) {
+            if (i < m) a = max(a, i + 1);
+            else if (i > m) b = min(b, i);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) {
+        red_a[warp] = a;
+        red_b[warp] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t aa = 0, bb = N;
+        for (int w = 0; w < kPrepThreads / 32; w++) {
+            aa = max(aa, red_a[w]);
+            bb = min(bb, red_b[w]);
+        }
+        ilo_sh = aa;
+        ihi_sh = bb == N ? N - 1 : bb - 1;
+    }
+    __syncthreads();
+    const uint32_t i0   = ilo_sh < 1 ? 1 : ilo_sh;
+    const uint32_t iend = (ihi_sh + 1 < N - 1) ? ihi_sh + 1 : N - 1;
+    uint32_t       status = bad_sh ? 1u : (iend >= i0 + 2 ? 0u : 2u);
+    const uint32_t n      = status ? 0u : iend - i0;
+
+    double* dst = F + static_cast<uint64_t>(c) * slot;
+    for (uint64_t k = tid; k < slot; k += kPrepThreads)
+        dst[k] = (k < n) ? __ddiv_rn(__dsub_rn(1.0, __dmul_rn(s, v[i0 + k])), 12.0) : 1.0 / 12.0;
+    if (tid == 0) {
+        curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, v[m]};
+        out[c]    = PrepOut{i0, n, status, 0u, v[m], v[N - 1]};
+    }
+}
+
+// ---------------------------------------------------------------------------
 // N7: wavefunctions of located levels (spec DESIGN.md section 3.6; oracle:
 // orc_wavefunction).  Few (curve, level) items, each a strictly serial three-term
 // recurrence u_{k+1} = fma(c_k, u_k, -u_{k-1}), c_k = 1/fp_k - 10, so the design

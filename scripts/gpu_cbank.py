@@ -14,8 +14,9 @@ ctx = cabi.Context(0)
 ctx.set_potentials(w["V"], w["s"])
 n_steps = ctx.curve_info(0).n_steps
 ref = {}
-for shape in (0, 4128, 4256):
+for shape, pdl in ((0, 0), (4128, 0), (4128, 1), (2256, 1), (2128, 1)):
     ctx.set_option(ctx.OPT_CBANK, 1 if shape else 2)
+    ctx.set_option(ctx.OPT_CBANK_PDL, pdl)
     if shape:
         ctx.set_option(ctx.OPT_CBANK_SHAPE, shape)
     for nE in (65536, 69632, 148 * 512, 148 * 1024, 148 * 2048, 1 << 20):
@@ -38,7 +39,7 @@ for shape in (0, 4128, 4256):
                 r = ref[key]
                 same = "bits==tma" if (np.array_equal(n, r[0]) and np.array_equal(m.view(np.uint64), r[1].view(np.uint64))
                                        and np.array_equal(x, r[2])) else "MISMATCH"
-        print(f"shape {shape:5d} nE {nE:8d}  ms {st.sweep_ms / reps:8.3f}  steps/s {rate:.4g}  pipe {rate * 4 / (148 * 64 * 1.965e9):.3f} {same}",
+        print(f"shape {shape:5d} pdl {pdl} nE {nE:8d}  ms {st.sweep_ms / reps:8.3f}  steps/s {rate:.4g}  pipe {rate * 4 / (148 * 64 * 1.965e9):.3f} {same}",
               flush=True)
 print("cbank launches", ctx.counter(ctx.CNT_CBANK_LAUNCHES))
 ctx.close()

@@ -165,3 +165,35 @@ def test_sign_stride_threshold(oracle, gpu_ctx, N, expect):
     rng = np.random.default_rng(N)
     E = np.sort(rng.uniform(0.0, W.H2["De"] - 1.0, 4096))
     _check_sweep(oracle, gpu_ctx, V, s, E)
+
+
+def test_device_prep_rejects_bad_tables(gpu_ctx):
+    """eps_set_potentials prepares on the device: non-finite values and degenerate windows still fail
+    with EPS_ERR_RANGE, and a failed call leaves the context without resident curves."""
+    from epseon_backend_b200.cabi import EpsError
+
+    V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, 3000)
+    s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, 3000))
+    bad = V.copy()
+    bad[1234] = np.nan
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.set_potentials(np.stack([V, bad]), s)
+    assert ei.value.code == 3
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.sweep_uniform(0.0, 100.0, 8)
+    assert ei.value.code == 4  # EPS_ERR_STATE: nothing resident
+    spike = np.full(50, 1e12)
+    spike[25] = 0.0  # a one-point well: the window has fewer than 2 steps
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.set_potentials(spike, 1.0)
+    assert ei.value.code == 3
+
+
+def test_device_prep_ties_and_plateaus(oracle, gpu_ctx):
+    """Flat-bottomed and double-minimum tables: the first minimum wins, as in the oracle."""
+    x = np.linspace(-2.0, 2.0, 5001)
+    V = 4000.0 * (x * x - 1.0) ** 2  # symmetric double well: two equal minima
+    V[2400:2600] = np.minimum(V[2400:2600], 3000.0)  # plateau on the barrier
+    s = W.scale(15.0, 15.0, 4.0 / 5000)
+    E = np.linspace(10.0, 3900.0, 300)
+    _check_sweep(oracle, gpu_ctx, V, s, E)
