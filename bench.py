@@ -49,6 +49,16 @@ METRIC = "numerov_grid_steps_x_trial_energies_per_s"
 FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 
+# dominant kernel per workload + its DRAM traffic per launch from the committed `ncu --set full`
+# captures (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1c_ncu.md, r1c_scan_ncu.md,
+# r1b_cbank_ncu.md).  Algorithmic bytes = the coefficient table once per launch (8 B x grid steps).
+KERNEL_META = {
+    "c2": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=32> (TMA ring, flat refinement rows)", 826_112, "profiles/r1c_ncu.md"),
+    "c3": ("eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)", 8_028_416, "profiles/r1c_scan_ncu.md"),
+    "c4": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=8> (TMA ring, packed refinement rows)", None, None),
+    "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", None, None),
+}
+
 C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
 C3 = dict(N=1_000_000, nE=4096)
 C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=64, rel_tol=1e-10, max_rounds=8, v_max=7)
@@ -424,7 +434,7 @@ def main() -> None:
                     "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps)},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "fp64", "kernel": "eps::numerov_sweep_kernel<2,32,false>",
+                "bound": "fp64", "kernel": KERNEL_META[args.workload][0],
                 "achieved": FLOP_PER_STEP * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": FLOP_PER_STEP * sweep_rate / 1e12 / fp64_peak,
                 "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
@@ -433,7 +443,8 @@ def main() -> None:
                 "flop_per_step": FLOP_PER_STEP, "steps_per_s_kernel": sweep_rate,
                 "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
                 "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
-                "traffic": None,
+                "traffic": KERNEL_META[args.workload][1], "traffic_source": KERNEL_META[args.workload][2],
+                "algorithmic_bytes_per_launch": 8 * int(n_steps),
             },
             "clocks": clocks,
         }
