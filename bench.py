@@ -77,19 +77,49 @@ def rank_curve(rank: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (recipe's clocks line)."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 20 ms from a
+    thread (nvidia_ml_py), falling back to `nvidia-smi -lms` when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.nvml, self._stop = device, [], None, None, False
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop:
+            try:
+                clk = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((time.time(), float(clk), pw, [k for k, b in bits.items() if mask & b]))
+            except Exception:  # noqa: BLE001 - sampling must never break the benchmark
+                pass
+            time.sleep(0.02)
 
     def start(self):
         try:
+            import pynvml as n
+
+            n.nvmlInit()
+            idx = self.device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[self.device])
+            h = n.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            threading.Thread(target=self._nvml_loop, daemon=True).start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.device), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -100,8 +130,16 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float) -> dict:
+        if self.nvml is not None:
+            self._stop = True
+            time.sleep(0.02)
+            sel = [r for r in self.rows if t0 <= r[0] <= t1]
+            reasons = sorted({x for r in sel for x in r[3]})
+            return {"sm_mhz": float(np.median([r[1] for r in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(sel), "power_w_max": max((r[2] for r in sel), default=None), "reasons": reasons,
+                    "source": "nvml, 20 ms period, inside the timed region"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         mhz, mx, reasons, power = [], None, set(), []
@@ -123,7 +161,7 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "samples": len(mhz),
-                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 def host_threads() -> int:

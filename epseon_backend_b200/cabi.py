@@ -21,7 +21,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
-    "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
+    "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
 ]
 
@@ -223,6 +223,17 @@ class Context:
         self._ck(self.lib.eps_wavefunctions(self.h, _ptr(E, np.float64), C.c_uint32(E.shape[1]),
                                             _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
         return psi, mi
+
+    def spline_resample(self, r, V, r_min: float, r_max: float, n_points: int) -> np.ndarray:
+        """Natural cubic spline through (r, V), evaluated on the device on n_points uniform points."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        assert r.shape == V.shape and r.ndim == 1
+        out = np.empty(n_points, dtype=np.float64)
+        self._ck(self.lib.eps_spline_resample(self.h, _ptr(r, np.float64), _ptr(V, np.float64), C.c_uint32(r.size),
+                                              C.c_double(r_min), C.c_double(r_max), C.c_uint32(n_points),
+                                              _ptr(out, np.float64)))
+        return out
 
     OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE, OPT_CBANK_PDL = 1, 2, 3, 4, 5
     CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED, CNT_CBANK_LAUNCHES = 1, 2, 3

@@ -112,8 +112,8 @@ namespace epseon::gpu::python {
         }
 
         // Additive: tabulated curves from "r V" text files.
-        TaskConfigurator& set_potential_files(const std::vector<std::string>& file_names) {
-            configurator->setPotentialSource(std::make_shared<cpp::PotentialFileLoader<FP>>(file_names));
+        TaskConfigurator& set_potential_files(const std::vector<std::string>& file_names, uint32_t point_count) {
+            configurator->setPotentialSource(std::make_shared<cpp::PotentialFileLoader<FP>>(file_names, point_count));
             return *this;
         }
 

@@ -7,6 +7,8 @@
 #pragma once
 #include "epseon/gpu/predecl.hpp"
 
+#include "epseon_cuda.h"
+
 #include <cmath>
 #include <cstdint>
 #include <fstream>
@@ -39,13 +41,23 @@ namespace epseon::gpu::cpp {
         [[nodiscard]] virtual std::unique_ptr<PotentialSource<FP>> unique_clone() const     = 0;
     };
 
-    // Tabulated curves from text files: one "r V" pair per line ('#' comments allowed), r uniformly
-    // spaced.  The reference stores the names and loads nothing.
+    // Tabulated curves from text files: one "r V" pair per line ('#' comments allowed).  A table on
+    // a uniform r grid is used as it is; a table on a non-uniform grid (ab initio points), or any
+    // table when `point_count` > 0, is resampled onto `point_count` uniform points of
+    // [r_first, r_last] with a natural cubic spline (coefficients: eps_spline_coefficients of the
+    // C ABI; evaluation fma(fma(fma(d,dx,c),dx,b),dx,a) -- DESIGN.md section 3.1).  The reference
+    // stores the names and loads nothing.
     template <typename FP>
     class PotentialFileLoader : public PotentialSource<FP> {
-        std::vector<std::string> file_names = {};
+        std::vector<std::string> file_names  = {};
+        uint32_t                 point_count = 0; // 0: keep the file's own point count
 
-        static void read_table(const std::string& path, std::vector<double>& r, std::vector<FP>& v) {
+        struct Table {
+            std::vector<double> v;
+            double              h = 0.0;
+        };
+
+        static void read_table(const std::string& path, std::vector<double>& r, std::vector<double>& v) {
             std::ifstream in(path);
             if (!in) throw std::runtime_error("PotentialFileLoader: cannot open '" + path + "'");
             std::string line;
@@ -56,44 +68,76 @@ namespace epseon::gpu::cpp {
                 double             ri = 0, vi = 0;
                 if (ls >> ri >> vi) {
                     r.push_back(ri);
-                    v.push_back(static_cast<FP>(vi));
+                    v.push_back(vi);
                 }
             }
             if (r.size() < 3) throw std::runtime_error("PotentialFileLoader: '" + path + "' holds fewer than 3 points");
         }
 
+        static bool is_uniform(const std::vector<double>& r) {
+            const double h = (r.back() - r.front()) / static_cast<double>(r.size() - 1);
+            for (size_t i = 0; i < r.size(); i++)
+                if (std::fabs(r[i] - (r.front() + static_cast<double>(i) * h)) > 1e-9 * std::fabs(h)) return false;
+            return true;
+        }
+
+        [[nodiscard]] Table load(const std::string& path) const {
+            std::vector<double> r, v;
+            read_table(path, r, v);
+            Table          t;
+            const uint32_t n = point_count > 0 ? point_count : static_cast<uint32_t>(r.size());
+            t.h              = (r.back() - r.front()) / static_cast<double>(n - 1);
+            if (point_count == 0 && is_uniform(r)) {
+                t.v = std::move(v);
+                return t;
+            }
+            const uint32_t      K = static_cast<uint32_t>(r.size());
+            std::vector<double> coef(4 * static_cast<size_t>(K - 1));
+            if (eps_spline_coefficients(r.data(), v.data(), K, coef.data()) != EPS_OK)
+                throw std::runtime_error("PotentialFileLoader: '" + path + "': " + eps_last_error(nullptr));
+            t.v.resize(n);
+            for (uint32_t i = 0; i < n; i++) {
+                const double x  = r.front() + static_cast<double>(i) * t.h;
+                uint32_t     lo = 0, hi = K - 1;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) / 2;
+                    if (r[mid] <= x) lo = mid;
+                    else hi = mid;
+                }
+                const double  dx = x - r[lo];
+                const double* c  = coef.data() + 4 * static_cast<size_t>(lo);
+                t.v[i]           = std::fma(std::fma(std::fma(c[3], dx, c[2]), dx, c[1]), dx, c[0]);
+            }
+            return t;
+        }
+
       public:
         PotentialFileLoader() noexcept = default;
-        PotentialFileLoader(const std::span<const std::string> names) : // NOLINT(hicpp-explicit-conversions)
-            file_names(names.begin(), names.end()) {}
+        PotentialFileLoader(const std::span<const std::string> names, uint32_t point_count_ = 0) : // NOLINT(hicpp-explicit-conversions)
+            file_names(names.begin(), names.end()), point_count(point_count_) {
+            if (point_count_ == 1 || point_count_ == 2) throw std::runtime_error("PotentialFileLoader: point_count must be 0 or >= 3");
+        }
         ~PotentialFileLoader() override = default;
 
         bool equals(const PotentialSource<FP>& other) const override {
             const auto* o = dynamic_cast<const PotentialFileLoader<FP>*>(&other);
-            return o != nullptr && file_names == o->file_names;
+            return o != nullptr && file_names == o->file_names && point_count == o->point_count;
         }
 
         std::vector<std::vector<FP>> get_potential_data() override {
             std::vector<std::vector<FP>> out;
             for (const auto& name : file_names) {
-                std::vector<double> r;
-                std::vector<FP>     v;
-                read_table(name, r, v);
-                if (!out.empty() && out.front().size() != v.size())
+                const Table t = load(name);
+                if (!out.empty() && out.front().size() != t.v.size())
                     throw std::runtime_error("PotentialFileLoader: all curves must have the same point count");
-                out.push_back(std::move(v));
+                out.emplace_back(t.v.begin(), t.v.end());
             }
             return out;
         }
 
         std::vector<double> get_grid_steps() const override {
             std::vector<double> out;
-            for (const auto& name : file_names) {
-                std::vector<double> r;
-                std::vector<FP>     v;
-                read_table(name, r, v);
-                out.push_back((r.back() - r.front()) / static_cast<double>(r.size() - 1));
-            }
+            for (const auto& name : file_names) out.push_back(load(name).h);
             return out;
         }
 

@@ -61,7 +61,7 @@ struct eps_ctx {
     // resident potentials
     uint32_t                    nC = 0, N = 0;
     uint64_t                    slot = 0;  // doubles per curve
-    DevBuf<double>              d_F, d_V, d_scale;
+    DevBuf<double>              d_F, d_V, d_scale, d_spl;
     DevBuf<PrepOut>             d_prep;
     DevBuf<CurveDev>            d_curves;
     std::vector<eps_curve_info> curves;
@@ -562,6 +562,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_F.release();
         ctx->d_V.release();
         ctx->d_scale.release();
+        ctx->d_spl.release();
         ctx->d_prep.release();
         ctx->d_curves.release();
         ctx->d_jobs.release();
@@ -941,6 +942,62 @@ int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const do
     if (match_index)  // report the matching point as an index of the full r grid
         for (uint32_t it = 0; it < items; it++)
             if (match_index[it] != kNone) match_index[it] += ctx->curves[it / n_levels].i0;
+    return EPS_OK;
+}
+
+// Natural cubic spline coefficients (a, b, c, d per knot interval); host arithmetic, same operation
+// order as the oracle counterpart; this file is compiled with -ffp-contract=off.
+int eps_spline_coefficients(const double* r, const double* V, uint32_t K, double* coef) {
+    if (!r || !V || !coef) return fail(nullptr, EPS_ERR_INVALID, "null argument");
+    if (K < 3) return fail(nullptr, EPS_ERR_INVALID, "a cubic spline needs at least 3 knots");
+    for (uint32_t k = 0; k < K; k++)
+        if (!std::isfinite(r[k]) || !std::isfinite(V[k])) return fail(nullptr, EPS_ERR_RANGE, "non-finite knot");
+    for (uint32_t k = 0; k + 1 < K; k++)
+        if (!(r[k + 1] > r[k])) return fail(nullptr, EPS_ERR_INVALID, "knot abscissae must be strictly increasing");
+    std::vector<double> m(K, 0.0), cp(K, 0.0), dp(K, 0.0);
+    for (uint32_t k = 1; k + 1 < K; k++) {
+        const double hl = r[k] - r[k - 1], hr = r[k + 1] - r[k];
+        const double diag = 2.0 * (hl + hr);
+        const double rhs  = 6.0 * ((V[k + 1] - V[k]) / hr - (V[k] - V[k - 1]) / hl);
+        const double sub  = (k == 1) ? 0.0 : hl;
+        const double den  = diag - sub * cp[k - 1];
+        cp[k]             = (k + 2 < K) ? hr / den : 0.0;
+        dp[k]             = (rhs - sub * dp[k - 1]) / den;
+    }
+    for (uint32_t k = K - 2; k >= 1; k--) m[k] = dp[k] - cp[k] * m[k + 1];
+    for (uint32_t k = 0; k + 1 < K; k++) {
+        const double h = r[k + 1] - r[k];
+        coef[4 * k + 0] = V[k];
+        coef[4 * k + 1] = (V[k + 1] - V[k]) / h - (h * (2.0 * m[k] + m[k + 1])) / 6.0;
+        coef[4 * k + 2] = m[k] / 2.0;
+        coef[4 * k + 3] = (m[k + 1] - m[k]) / (6.0 * h);
+    }
+    return EPS_OK;
+}
+
+int eps_spline_resample(eps_ctx* ctx, const double* r, const double* V, uint32_t n_knots, double r_min,
+                        double r_max, uint32_t n_points, double* V_out) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, V_out && n_points >= 2 && std::isfinite(r_min) && std::isfinite(r_max) && r_max > r_min, EPS_ERR_INVALID,
+                "bad output grid");
+    std::vector<double> coef(4 * static_cast<size_t>(n_knots > 1 ? n_knots - 1 : 1));
+    if (int rc = eps_spline_coefficients(r, V, n_knots, coef.data())) {
+        ctx->err = g_last_error;
+        return rc;
+    }
+    EPS_CUDA(ctx, ctx->d_V.reserve(n_points));
+    EPS_CUDA(ctx, ctx->d_spl.reserve(coef.size() + n_knots));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spl.p, r, n_knots * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_spl.p + n_knots, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (n_knots + coef.size()) * sizeof(double);
+    const double h = (r_max - r_min) / static_cast<double>(n_points - 1);
+    spline_eval_kernel<<<(n_points + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_spl.p, ctx->d_spl.p + n_knots, n_knots, r_min, h, n_points, ctx->d_V.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    EPS_CUDA(ctx, cudaMemcpyAsync(V_out, ctx->d_V.p, n_points * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n_points * sizeof(double);
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EPS_OK;
 }
 

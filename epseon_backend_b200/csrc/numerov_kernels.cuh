@@ -728,6 +728,28 @@ __global__ void finalize_levels_kernel(const double* __restrict__ lo, const doub
 }
 
 // ---------------------------------------------------------------------------
+// N1 for tabulated sources: evaluate the natural cubic spline (coefficients a,b,c,d per knot
+// interval, computed on the host by eps_spline_coefficients) on the uniform grid
+// r_i = rmin + i*h.  Same operations as the oracle's orc_spline_resample: binary search for the
+// interval, dx = r - r_k, fma(fma(fma(d,dx,c),dx,b),dx,a).
+// ---------------------------------------------------------------------------
+__global__ void spline_eval_kernel(const double* __restrict__ knots, const double* __restrict__ coef,
+                                   uint32_t K, double rmin, double h, uint32_t N, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x  = __dadd_rn(rmin, __dmul_rn(static_cast<double>(i), h));
+    uint32_t     lo = 0, hi = K - 1;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (knots[mid] <= x) lo = mid;
+        else hi = mid;
+    }
+    const double  dx = __dsub_rn(x, knots[lo]);
+    const double* c  = coef + 4 * lo;
+    out[i]           = __fma_rn(__fma_rn(__fma_rn(c[3], dx, c[2]), dx, c[1]), dx, c[0]);
+}
+
+// ---------------------------------------------------------------------------
 // Preparation on the device (spec DESIGN.md section 3.2; oracle: orc_prep).  One CTA per curve:
 // first argmin of q = s V, the window around it with q - q_min <= T_MAX, the coefficient table
 // F_k = (1 - q_{i0+k}) / 12 written into the curve's slot (padded with 1/12).  Every value is

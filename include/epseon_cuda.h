@@ -121,6 +121,17 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
                        const double* scale);
 int eps_get_curve_info(eps_ctx* ctx, uint32_t curve, eps_curve_info* out);
 
+/* ---- tabulated sources (N1): natural cubic spline through n_knots points (r strictly increasing),
+ * resampled on the uniform grid r_i = r_min + i*(r_max-r_min)/(n_points-1).  Makes real the
+ * tabulated-file source the reference declares and leaves empty
+ * (PotentialFileLoader<FP>::get_potential_data, potential_source.hpp:89-91) for ab initio tables
+ * on non-uniform grids.  eps_spline_coefficients is host-only (no context): coef receives
+ * a,b,c,d of S = a + dx(b + dx(c + dx d)) per interval, 4*(n_knots-1) doubles.
+ * eps_spline_resample evaluates on the device and returns V_out (host, n_points doubles). */
+int eps_spline_coefficients(const double* r, const double* V, uint32_t n_knots, double* coef);
+int eps_spline_resample(eps_ctx* ctx, const double* r, const double* V, uint32_t n_knots, double r_min,
+                        double r_max, uint32_t n_points, double* V_out);
+
 /* ---- Numerov sweep + node count (the missing compute dispatch of
  * vibwa.hpp:605-637).  Per curve, n_energies trial energies; outputs are host
  * buffers [n_curves][n_energies] and any of them may be NULL (results then

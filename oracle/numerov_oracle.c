@@ -401,3 +401,71 @@ int64_t orc_wavefunction(const double* F, uint32_t n_steps, double s, double E, 
     free(cexp);
     return m;
 }
+
+/* N1 (tabulated sources).  Natural cubic spline through the knots (r_k, V_k), k = 0..K-1 (r strictly
+ * increasing), resampled on r_i = rmin + i*h, h = (rmax - rmin)/(N - 1).  Fills the slot of
+ * PotentialFileLoader::get_potential_data (potential_source.hpp:89-91) for ab initio tables on
+ * non-uniform grids.  Second derivatives m_k from the tridiagonal system
+ *     h_{k-1} m_{k-1} + 2 (h_{k-1} + h_k) m_k + h_k m_{k+1} = 6 ((V_{k+1}-V_k)/h_k - (V_k-V_{k-1})/h_{k-1}),
+ * m_0 = m_{K-1} = 0 (Thomas algorithm, forward sweep then back substitution); on [r_k, r_{k+1}]
+ *     S = a + dx (b + dx (c + dx d)),  dx = r - r_k,
+ *     a = V_k, b = (V_{k+1}-V_k)/h_k - h_k (2 m_k + m_{k+1})/6, c = m_k/2, d = (m_{k+1}-m_k)/(6 h_k),
+ * evaluated as fma(fma(fma(d,dx,c),dx,b),dx,a).  Points left of r_0 / right of r_{K-1} use the first /
+ * last interval (extrapolation).  coef (4*(K-1) doubles, may be NULL) receives a,b,c,d per interval.
+ * Returns 0, or -1 on bad input. */
+int orc_spline_coefficients(const double* r, const double* V, uint32_t K, double* coef) {
+    if (K < 3) return -1;
+    for (uint32_t k = 0; k + 1 < K; k++)
+        if (!(r[k + 1] > r[k])) return -1;
+    double* m  = (double*)calloc(K, sizeof(double));
+    double* cp = (double*)calloc(K, sizeof(double));
+    double* dp = (double*)calloc(K, sizeof(double));
+    /* interior rows k = 1..K-2; unknowns m_1..m_{K-2} */
+    for (uint32_t k = 1; k + 1 < K; k++) {
+        const double hl = r[k] - r[k - 1], hr = r[k + 1] - r[k];
+        const double diag = 2.0 * (hl + hr);
+        const double rhs  = 6.0 * ((V[k + 1] - V[k]) / hr - (V[k] - V[k - 1]) / hl);
+        const double sub  = (k == 1) ? 0.0 : hl;
+        const double den  = diag - sub * cp[k - 1];
+        cp[k]             = (k + 2 < K) ? hr / den : 0.0;
+        dp[k]             = (rhs - sub * dp[k - 1]) / den;
+    }
+    for (uint32_t k = K - 2; k >= 1; k--) m[k] = dp[k] - cp[k] * m[k + 1];
+    for (uint32_t k = 0; k + 1 < K; k++) {
+        const double h = r[k + 1] - r[k];
+        coef[4 * k + 0] = V[k];
+        coef[4 * k + 1] = (V[k + 1] - V[k]) / h - (h * (2.0 * m[k] + m[k + 1])) / 6.0;
+        coef[4 * k + 2] = m[k] / 2.0;
+        coef[4 * k + 3] = (m[k + 1] - m[k]) / (6.0 * h);
+    }
+    free(m);
+    free(cp);
+    free(dp);
+    return 0;
+}
+
+int orc_spline_resample(const double* r, const double* V, uint32_t K, double rmin, double rmax,
+                        uint32_t N, double* out) {
+    if (N < 2) return -1;
+    double* coef = (double*)malloc(sizeof(double) * 4 * (K > 1 ? K - 1 : 1));
+    if (orc_spline_coefficients(r, V, K, coef) != 0) {
+        free(coef);
+        return -1;
+    }
+    const double h = (rmax - rmin) / (double)(N - 1);
+    for (uint32_t i = 0; i < N; i++) {
+        const double x = rmin + (double)i * h;
+        /* interval: largest k <= K-2 with r_k <= x (k = 0 when x < r_0) */
+        uint32_t lo = 0, hi = K - 1;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (r[mid] <= x) lo = mid;
+            else hi = mid;
+        }
+        const double  dx = x - r[lo];
+        const double* c  = coef + 4 * lo;
+        out[i]           = fma(fma(fma(c[3], dx, c[2]), dx, c[1]), dx, c[0]);
+    }
+    free(coef);
+    return 0;
+}

@@ -82,6 +82,8 @@ class Oracle:
                                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                             C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_spline_resample.restype = C.c_int
+        L.orc_spline_resample.argtypes = [_f64p, _f64p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, _f64p]
         L.orc_wavefunction.restype = C.c_int64
         L.orc_wavefunction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, _f64p]
 
@@ -159,3 +161,12 @@ class Oracle:
         psi = np.empty(AB.size, dtype=np.float64)
         m = self.lib.orc_wavefunction(AB, AB.size, s, float(E), float(h), psi)
         return psi, int(m)
+
+    def spline_resample(self, r, V, rmin, rmax, N):
+        """Natural cubic spline through (r, V) resampled on N uniform points of [rmin, rmax]."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        out = np.empty(N, dtype=np.float64)
+        if self.lib.orc_spline_resample(r, V, r.size, float(rmin), float(rmax), N, out) != 0:
+            raise ValueError("orc_spline_resample: bad knots")
+        return out
