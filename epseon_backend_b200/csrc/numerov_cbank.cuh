@@ -49,11 +49,13 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
     constexpr uint32_t kPerCta = kThreads * kEpt;
     // Programmatic dependent launch: the chunk launches of one sweep are chained with
-    // cudaLaunchAttributeProgrammaticStreamSerialization.  Letting the next chunk's CTAs become
-    // resident right away and park on griddepcontrol.wait (which returns once the previous chunk has
-    // completed and its state stores are visible) hides the launch latency between chunks.
-    asm volatile("griddepcontrol.launch_dependents;");
+    // cudaLaunchAttributeProgrammaticStreamSerialization.  griddepcontrol.wait returns once the
+    // previous chunk has completed and its state stores are visible; only THEN does this chunk let
+    // its own dependent become resident, so exactly one chunk is ever parked behind the running one
+    // (triggering before the wait lets every queued chunk of the sweep pile up on the SMs:
+    // measured 2.21 ms instead of 1.97 ms on a one-wave sweep).
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t job_idx = blockIdx.x / chunks_per_job;
     const uint32_t chunk   = blockIdx.x - job_idx * chunks_per_job;
     const Job      job     = jobs[job_idx];

@@ -21,6 +21,7 @@ namespace eps {
 
 constexpr int      kTile          = 2048;  // grid steps per shared-memory stage (16 KiB of F_k)
 constexpr int      kStages        = 4;     // TMA ring depth
+constexpr uint32_t kProducerSuspendNs = 1000000;  // try_wait suspend-time hint of the TMA producer
 // CTA shape of the sweep: kWarps consumer warps (template parameter) + 1 TMA producer warp,
 // 32 * kWarps * kEpt trial energies per CTA.
 constexpr int      kRenorm        = 128;   // exponent renormalisation period (steps)
@@ -86,23 +87,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// Producer-side wait: poll with a back-off so the (otherwise idle) producer warp does not
-// steal issue slots from the consumer warps sharing its scheduler (profiles/: a bare
-// try_wait spin was 10 % of all executed instructions).
+// Producer-side wait.  The (otherwise idle) producer warp shares a scheduler with two consumer
+// warps, so it must not spin: try_wait carries a suspend-time hint, i.e. the hardware parks the
+// thread until the phase completes or the hint (ns) expires -- no issue slots are taken meanwhile.
+// (profiles/r1c_ncu.md: a NANOSLEEP/try_wait/BRA poll loop still executed 26 M times per launch,
+// 7.5 % of all warp instructions, all on the producer's scheduler.)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     while (true) {
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, P1;\n"
             "}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(kProducerSuspendNs)
             : "memory");
         if (done) break;
-        __nanosleep(2000);
     }
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA

@@ -14,7 +14,7 @@ ctx = cabi.Context(0)
 ctx.set_potentials(w["V"], w["s"])
 n_steps = ctx.curve_info(0).n_steps
 ref = {}
-for shape, pdl in ((0, 0), (4128, 0), (4128, 1), (2256, 1), (2128, 1)):
+for shape, pdl in ((0, 0), (4128, 0), (4128, 2), (2256, 0), (2256, 2), (2128, 2), (4256, 2)):
     ctx.set_option(ctx.OPT_CBANK, 1 if shape else 2)
     ctx.set_option(ctx.OPT_CBANK_PDL, pdl)
     if shape:
