@@ -22,7 +22,7 @@ SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
     "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
-    "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe",
+    "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe", "eps_host_alloc", "eps_host_free",
 ]
 
 
@@ -144,6 +144,20 @@ class Context:
                                              C.c_uint32(V.shape[1]), _ptr(scale, np.float64)))
         self.n_curves = V.shape[0]
         self.n_points = V.shape[1]
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """Uninitialised numpy array in page-locked host memory (eps_host_alloc); freed with the array."""
+        import weakref
+
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._ck(self.lib.eps_host_alloc(self.h, C.c_size_t(max(n, 1)), C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        lib, addr = self.lib, p.value
+        weakref.finalize(buf, lambda: lib.eps_host_free(None, C.c_void_p(addr)))
+        return arr
 
     def curve_info(self, curve: int = 0) -> CurveInfo:
         ci = CurveInfo()

@@ -281,8 +281,21 @@ cudaError_t launch_cbank_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, u
     return tails ? launch_cbank_variant<kEpt, kThreads, 1, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 1, false>(ctx, j, n, nE, E, out);
 }
 
+// Host copy of the (single) curve's coefficient table: the constant-bank kernel takes its chunks by
+// value.  Fetched once per eps_set_potentials, on the first launch that needs it.
+int fetch_host_table(eps_ctx* ctx) {
+    if (!ctx->h_F.empty()) return EPS_OK;
+    const uint32_t n = ctx->curves[0].n_steps;
+    ctx->h_F.resize(n);
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_F.data(), ctx->d_F.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += n * sizeof(double);
+    return EPS_OK;
+}
+
 int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp, bool tails, int stride,
                  const SweepOut& out) {
+    if (int rc = fetch_host_table(ctx)) return rc;
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_cbX.reserve(n_out));
     EPS_CUDA(ctx, ctx->d_cbS.reserve(n_out));
@@ -302,7 +315,7 @@ int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
 // kernel once a launch carries >= ~2 CTAs of 512 energies per SM (+1 % at 151 552 energies, +5 % at
 // 303 104, +9 % at 2^20); below that the per-chunk launch overhead (26 launches per 100k steps) loses.
 bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_rows) {
-    if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->h_F.empty() || ctx->force_ept) return false;
+    if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->force_ept) return false;
     if (pack_rows != kFlatRows && pack_log2_for(nE, pack_rows) != 0) return false;  // (flat rows: cbank uses per-row CTAs instead)
     if (ctx->opt_cbank == 1) return true;
     return static_cast<uint64_t>(n_jobs) * nE >= 2ull * 512 * ctx->sm_count;
@@ -655,14 +668,7 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     ctx->N      = N;
     ctx->slot   = slot;
     ctx->curves = std::move(infos);
-    if (n_curves == 1) {  // host copy of the table for the constant-bank kernel's by-value chunks
-        ctx->h_F.resize(po[0].n_steps);
-        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_F.data(), ctx->d_F.p, po[0].n_steps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += po[0].n_steps * sizeof(double);
-    } else {
-        ctx->h_F.clear();
-    }
+    ctx->h_F.clear();  // host copy for the constant-bank kernel: fetched on first use (fetch_host_table)
     ctx->n_tiles_max = 0;
     for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
     return EPS_OK;
@@ -1071,6 +1077,21 @@ int eps_stats_reset(eps_ctx* ctx) {
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats = eps_stats{};
+    return EPS_OK;
+}
+
+int eps_host_alloc(eps_ctx* ctx, size_t bytes, void** out) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, out && bytes > 0, EPS_ERR_INVALID, "out is null or bytes == 0");
+    *out = nullptr;
+    EPS_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return EPS_OK;
+}
+
+int eps_host_free(eps_ctx* ctx, void* p) {
+    if (!p) return EPS_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail(ctx, EPS_ERR_CUDA, cudaGetErrorString(e));
     return EPS_OK;
 }
 
