@@ -20,7 +20,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 # every symbol include/epseon_cuda.h declares
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
-    "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_get_curve_info",
+    "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_set_potentials_rot", "eps_get_curve_info",
     "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe", "eps_host_alloc", "eps_host_free",
 ]
@@ -143,6 +143,18 @@ class Context:
         self._ck(self.lib.eps_set_potentials(self.h, _ptr(V, np.float64), C.c_uint32(V.shape[0]),
                                              C.c_uint32(V.shape[1]), _ptr(scale, np.float64)))
         self.n_curves = V.shape[0]
+        self.n_points = V.shape[1]
+
+    def set_potentials_rot(self, V: np.ndarray, scale, r_min, grid_step, J) -> None:
+        """Resident curves c*len(J) + j: V_J = V + J(J+1) (h^2 / 12 s) / r^2, expanded on the device."""
+        V = np.ascontiguousarray(np.atleast_2d(V), dtype=np.float64)
+        nC = V.shape[0]
+        scale, r_min, grid_step = _vec(scale, nC), _vec(r_min, nC), _vec(grid_step, nC)
+        J = np.ascontiguousarray(np.atleast_1d(J), dtype=np.uint32)
+        self._ck(self.lib.eps_set_potentials_rot(self.h, _ptr(V, np.float64), C.c_uint32(nC), C.c_uint32(V.shape[1]),
+                                                 _ptr(scale, np.float64), _ptr(r_min, np.float64),
+                                                 _ptr(grid_step, np.float64), _ptr(J, np.uint32), C.c_uint32(J.size)))
+        self.n_curves = nC * J.size
         self.n_points = V.shape[1]
 
     def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:

@@ -46,16 +46,21 @@ namespace epseon::gpu::cpp {
         handle->setStatus("tabulating potentials");
         const auto                table = source->get_potential_data();
         const std::vector<double> steps = source->get_grid_steps();
-        const uint32_t            nC    = static_cast<uint32_t>(table.size());
-        if (nC == 0) throw std::runtime_error("potential source holds no curves");
+        const uint32_t            nT    = static_cast<uint32_t>(table.size()); // tables (one per configured curve)
+        if (nT == 0) throw std::runtime_error("potential source holds no curves");
+        // additive: every table is solved once per rotational state J; row = table*nJ + j
+        const std::vector<uint32_t>& J  = configurator.getRotationalStates();
+        const uint32_t               nJ = static_cast<uint32_t>(J.size());
+        const bool     rotating = std::any_of(J.begin(), J.end(), [](uint32_t j) { return j != 0; }) || nJ > 1;
+        const uint32_t nC       = nT * nJ;
         const uint32_t N = static_cast<uint32_t>(table.front().size());
         if (hardware->getPotentialBufferSize() < N)
             throw std::runtime_error("potential_buffer_size is smaller than the potential's point count");
-        std::vector<double> V(static_cast<size_t>(nC) * N), scale(nC);
+        std::vector<double> V(static_cast<size_t>(nT) * N), scale(nT);
         const double m0 = algorithm->getMassAtom0(), m1 = algorithm->getMassAtom1();
         const double mu = (m0 * m1) / (m0 + m1);
         const double c  = mu / detail::kHbar2Over2;
-        for (uint32_t k = 0; k < nC; k++) {
+        for (uint32_t k = 0; k < nT; k++) {
             if (table[k].size() != N) throw std::runtime_error("all curves must have the same point count");
             for (uint32_t i = 0; i < N; i++) V[static_cast<size_t>(k) * N + i] = static_cast<double>(table[k][i]);
             scale[k] = ((steps[k] * steps[k]) * c) / 12.0;
@@ -67,7 +72,14 @@ namespace epseon::gpu::cpp {
         detail::CtxGuard guard;
         detail::check(eps_ctx_create(handle->getDeviceInterface().getCudaOrdinal(), &guard.ctx), nullptr, "eps_ctx_create");
         eps_ctx* ctx = guard.ctx;
-        detail::check(eps_set_potentials(ctx, V.data(), nC, N, scale.data()), ctx, "eps_set_potentials");
+        if (rotating) {
+            const std::vector<double> origins = source->get_grid_origins();
+            detail::check(eps_set_potentials_rot(ctx, V.data(), nT, N, scale.data(), origins.data(), steps.data(),
+                                                 J.data(), nJ),
+                          ctx, "eps_set_potentials_rot");
+        } else {
+            detail::check(eps_set_potentials(ctx, V.data(), nT, N, scale.data()), ctx, "eps_set_potentials");
+        }
 
         // ---- search window per curve: [V_min, V_last - min_distance_to_asymptote] ----
         std::vector<double> E_lo(nC), E_hi(nC);
@@ -106,8 +118,9 @@ namespace epseon::gpu::cpp {
         // ---- N7 (on request): normalised wavefunctions of the located levels ----
         if (configurator.getWavefunctionOutput() && !stop_token.stop_requested()) {
             handle->setStatus("computing wavefunctions");
-            std::vector<double> psi(static_cast<size_t>(nC) * nlev * N);
-            detail::check(eps_wavefunctions(ctx, lev.data(), nlev, steps.data(), psi.data(), nullptr), ctx,
+            std::vector<double> psi(static_cast<size_t>(nC) * nlev * N), steps_eff(nC);
+            for (uint32_t k = 0; k < nC; k++) steps_eff[k] = steps[k / nJ];
+            detail::check(eps_wavefunctions(ctx, lev.data(), nlev, steps_eff.data(), psi.data(), nullptr), ctx,
                           "eps_wavefunctions");
             handle->setWavefunctions(std::move(psi), nC, nlev, N);
         }

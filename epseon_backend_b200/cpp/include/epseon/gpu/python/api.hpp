@@ -111,6 +111,13 @@ namespace epseon::gpu::python {
             return *this;
         }
 
+        // Additive: solve every curve once per rotational quantum number J
+        // (centrifugal term J(J+1) hbar^2 / 2 mu r^2); result rows are ordered [curve][J].
+        TaskConfigurator& set_rotational_states(const std::vector<uint32_t>& j_values) {
+            configurator->setRotationalStates(j_values);
+            return *this;
+        }
+
         // Additive: tabulated curves from "r V" text files.
         TaskConfigurator& set_potential_files(const std::vector<std::string>& file_names, uint32_t point_count) {
             configurator->setPotentialSource(std::make_shared<cpp::PotentialFileLoader<FP>>(file_names, point_count));

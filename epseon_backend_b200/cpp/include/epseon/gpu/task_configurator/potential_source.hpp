@@ -37,6 +37,8 @@ namespace epseon::gpu::cpp {
         virtual std::vector<std::vector<FP>> get_potential_data()                           = 0;
         // Grid spacing h of every curve (additive; needed to scale energies).
         virtual std::vector<double>          get_grid_steps() const                         = 0;
+        // First grid point r_0 of every curve (additive; the centrifugal term needs r).
+        virtual std::vector<double>          get_grid_origins() const                       = 0;
         [[nodiscard]] virtual std::shared_ptr<PotentialSource<FP>> shared_clone() const     = 0;
         [[nodiscard]] virtual std::unique_ptr<PotentialSource<FP>> unique_clone() const     = 0;
     };
@@ -54,7 +56,8 @@ namespace epseon::gpu::cpp {
 
         struct Table {
             std::vector<double> v;
-            double              h = 0.0;
+            double              h  = 0.0;
+            double              r0 = 0.0;
         };
 
         static void read_table(const std::string& path, std::vector<double>& r, std::vector<double>& v) {
@@ -87,6 +90,7 @@ namespace epseon::gpu::cpp {
             Table          t;
             const uint32_t n = point_count > 0 ? point_count : static_cast<uint32_t>(r.size());
             t.h              = (r.back() - r.front()) / static_cast<double>(n - 1);
+            t.r0             = r.front();
             if (point_count == 0 && is_uniform(r)) {
                 t.v = std::move(v);
                 return t;
@@ -138,6 +142,12 @@ namespace epseon::gpu::cpp {
         std::vector<double> get_grid_steps() const override {
             std::vector<double> out;
             for (const auto& name : file_names) out.push_back(load(name).h);
+            return out;
+        }
+
+        std::vector<double> get_grid_origins() const override {
+            std::vector<double> out;
+            for (const auto& name : file_names) out.push_back(load(name).r0);
             return out;
         }
 
@@ -233,6 +243,12 @@ namespace epseon::gpu::cpp {
         std::vector<double> get_grid_steps() const override {
             std::vector<double> out;
             for (const auto& cfg : configurations) out.push_back(cfg.getGridStep());
+            return out;
+        }
+
+        std::vector<double> get_grid_origins() const override {
+            std::vector<double> out;
+            for (const auto& cfg : configurations) out.push_back(static_cast<double>(cfg.getMinR()));
             return out;
         }
 

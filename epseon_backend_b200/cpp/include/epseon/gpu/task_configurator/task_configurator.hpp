@@ -10,6 +10,7 @@
 #include "epseon/gpu/task_configurator/potential_source.hpp"
 
 #include <memory>
+#include <stdexcept>
 #include <type_traits>
 #include <vector>
 
@@ -24,6 +25,9 @@ namespace epseon::gpu::cpp {
         std::shared_ptr<AlgorithmConfig<FP>> algorithm_config = {};
         // additive: also return the normalised wavefunctions of the located levels
         bool wavefunction_output = false;
+        // additive: rotational quantum numbers J; every curve is solved once per J with
+        // V_J = V + J(J+1) hbar^2/(2 mu r^2).  Default {0}: the reference's J-less problem.
+        std::vector<uint32_t> rotational_states = {0};
 
         template <typename T>
         static std::shared_ptr<T> clone_or_null(const std::shared_ptr<T>& p) {
@@ -43,13 +47,15 @@ namespace epseon::gpu::cpp {
             hardware_config(std::move(o.hardware_config)),
             potential_source(std::move(o.potential_source)),
             algorithm_config(std::move(o.algorithm_config)),
-            wavefunction_output(o.wavefunction_output) {}
+            wavefunction_output(o.wavefunction_output),
+            rotational_states(std::move(o.rotational_states)) {}
         TaskConfigurator& operator=(TaskConfigurator&& o) noexcept {
             if (this != &o) {
                 hardware_config     = std::move(o.hardware_config);
                 potential_source    = std::move(o.potential_source);
                 algorithm_config    = std::move(o.algorithm_config);
                 wavefunction_output = o.wavefunction_output;
+                rotational_states   = std::move(o.rotational_states);
             }
             return *this;
         }
@@ -58,13 +64,15 @@ namespace epseon::gpu::cpp {
             hardware_config(clone_or_null(o.hardware_config)),
             potential_source(clone_or_null(o.potential_source)),
             algorithm_config(clone_or_null(o.algorithm_config)),
-            wavefunction_output(o.wavefunction_output) {}
+            wavefunction_output(o.wavefunction_output),
+            rotational_states(o.rotational_states) {}
         TaskConfigurator& operator=(const TaskConfigurator& o) {
             if (this != &o) {
                 hardware_config     = clone_or_null(o.hardware_config);
                 potential_source    = clone_or_null(o.potential_source);
                 algorithm_config    = clone_or_null(o.algorithm_config);
                 wavefunction_output = o.wavefunction_output;
+                rotational_states   = o.rotational_states;
             }
             return *this;
         }
@@ -93,6 +101,15 @@ namespace epseon::gpu::cpp {
             return *this;
         }
         [[nodiscard]] bool getWavefunctionOutput() const { return wavefunction_output; }
+
+        TaskConfigurator& setRotationalStates(std::vector<uint32_t> j_values) {
+            if (j_values.empty()) throw std::runtime_error("rotational_states must hold at least one J");
+            for (const uint32_t j : j_values)
+                if (j >= (1u << 26)) throw std::runtime_error("rotational quantum numbers must be below 2^26");
+            rotational_states = std::move(j_values);
+            return *this;
+        }
+        [[nodiscard]] const std::vector<uint32_t>& getRotationalStates() const { return rotational_states; }
 
         [[nodiscard]] bool isConfigured() const {
             return static_cast<bool>(hardware_config) && static_cast<bool>(potential_source) &&

@@ -85,6 +85,11 @@ namespace epseon::gpu::python {
                 .def("set_wavefunction_output", &C::set_wavefunction_output, py::arg("enabled"),
                      py::return_value_policy::reference,
                      "Also compute the normalised wavefunctions of the located levels (TaskHandle.get_wavefunctions).")
+                .def("set_rotational_states", &C::set_rotational_states, py::arg("j_values"),
+                     py::return_value_policy::reference,
+                     "Solve every curve once per rotational quantum number J (effective potential "
+                     "V + J(J+1) hbar^2 / (2 mu r^2)); get_levels() rows are then ordered curve-major, "
+                     "row = curve * len(j_values) + j.  Default [0].")
                 .def("set_potential_files", &C::set_potential_files, py::arg("file_names"), py::arg("point_count") = 0,
                      py::return_value_policy::reference,
                      "Use tabulated 'r V' text files as potential source; tables on a non-uniform grid (or any "

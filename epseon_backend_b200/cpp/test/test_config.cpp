@@ -123,6 +123,21 @@ void task_configurator() {
     CHECK(req[0].outputBuffersElementCount == 3 && req[0].stagingBuffersElementCount == 500);
     CHECK(req[0].getStagingBuffersSizeBytes() == 500 * sizeof(FP));
     CHECK(req[0].getGpuOnlyStorageBufferSizeBytes() == 5 * 500 * sizeof(FP));
+    // additive: rotational states (default {0}; copied and moved with the configurator; validated)
+    CHECK(cfg.getRotationalStates() == std::vector<uint32_t>{0});
+    cfg.setRotationalStates({0, 1, 7});
+    TaskConfigurator<FP> rot(cfg);
+    CHECK((rot.getRotationalStates() == std::vector<uint32_t>{0, 1, 7}));
+    TaskConfigurator<FP> rot_moved(std::move(rot));
+    CHECK(rot_moved.getRotationalStates().size() == 3);
+    bool refused = false;
+    try {
+        cfg.setRotationalStates({});
+    } catch (const std::runtime_error&) {
+        refused = true;
+    }
+    CHECK(refused && cfg.getRotationalStates().size() == 3);
+    CHECK(cfg.getPotentialSource()->get_grid_origins() == std::vector<double>{0.0});
 }
 
 int main() {

@@ -61,7 +61,8 @@ struct eps_ctx {
     // resident potentials
     uint32_t                    nC = 0, N = 0;
     uint64_t                    slot = 0;  // doubles per curve
-    DevBuf<double>              d_F, d_V, d_scale, d_spl;
+    DevBuf<double>              d_F, d_V, d_scale, d_spl, d_Vraw, d_rot;
+    DevBuf<uint32_t>            d_J;
     DevBuf<PrepOut>             d_prep;
     DevBuf<CurveDev>            d_curves;
     std::vector<eps_curve_info> curves;
@@ -470,6 +471,41 @@ int fetch_sweep(eps_ctx* ctx, size_t n, uint32_t* nodes, double* mant, int32_t* 
     return EPS_OK;
 }
 
+// Second half of eps_set_potentials*: the tables are in d_V, the scales in d_scale (both on the
+// device already); prep_curves_kernel derives window + coefficient table per curve (spec
+// DESIGN.md section 3.2) and 32 B per curve come back.
+template <typename ScaleOf>
+int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf scale_of) {
+    const uint32_t N    = n_points;
+    const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
+    const size_t   n_f  = static_cast<size_t>(slot) * n_curves;
+    EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
+    EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
+    EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
+    prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    std::vector<PrepOut> po(n_curves);
+    EPS_CUDA(ctx, cudaMemcpyAsync(po.data(), ctx->d_prep.p, n_curves * sizeof(PrepOut), cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += n_curves * sizeof(PrepOut);
+    ctx->nC = 0;  // invalid until every curve checked out
+    for (uint32_t c = 0; c < n_curves; c++) {
+        EPS_REQUIRE(ctx, po[c].status != 1, EPS_ERR_RANGE, "potential table holds a non-finite value");
+        EPS_REQUIRE(ctx, po[c].status != 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
+    }
+    std::vector<eps_curve_info> infos(n_curves);
+    for (uint32_t c = 0; c < n_curves; c++) infos[c] = eps_curve_info{po[c].i0, po[c].n_steps, scale_of(c), po[c].v_min, po[c].v_last};
+    ctx->nC     = n_curves;
+    ctx->N      = N;
+    ctx->slot   = slot;
+    ctx->curves = std::move(infos);
+    ctx->h_F.clear();  // host copy for the constant-bank kernel: fetched on first use (fetch_host_table)
+    ctx->n_tiles_max = 0;
+    for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
+    return EPS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -576,6 +612,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_V.release();
         ctx->d_scale.release();
         ctx->d_spl.release();
+        ctx->d_Vraw.release(); ctx->d_rot.release(); ctx->d_J.release();
         ctx->d_prep.release();
         ctx->d_curves.release();
         ctx->d_jobs.release();
@@ -628,50 +665,58 @@ int eps_sync(eps_ctx* ctx) {
 }
 
 // Preparation (spec DESIGN.md section 3.2): q = s V, window [i0, iend] around the
-// minimum with q - q_min <= T_MAX, coefficient table F_k = (1 - q_{i0+k}) / 12.
-// Preparation (spec DESIGN.md section 3.2) runs on the device: the raw table goes up once,
-// prep_curves_kernel derives window + coefficient table per curve, 32 B per curve come back.
+// minimum with q - q_min <= T_MAX, coefficient table F_k = (1 - q_{i0+k}) / 12 -- on the device:
+// the raw table goes up once, prep_resident() does the rest.
 int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
                        const double* scale) {
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, V && scale, EPS_ERR_INVALID, "V/scale is null");
     EPS_REQUIRE(ctx, n_curves >= 1 && n_points >= 3, EPS_ERR_INVALID, "need >=1 curve of >=3 points");
-    const uint32_t N    = n_points;
-    const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
     for (uint32_t c = 0; c < n_curves; c++)
         EPS_REQUIRE(ctx, std::isfinite(scale[c]) && scale[c] > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
-    const size_t n_v = static_cast<size_t>(N) * n_curves, n_f = static_cast<size_t>(slot) * n_curves;
+    const size_t n_v = static_cast<size_t>(n_points) * n_curves;
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     EPS_CUDA(ctx, ctx->d_V.reserve(n_v));
     EPS_CUDA(ctx, ctx->d_scale.reserve(n_curves));
-    EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
-    EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
-    EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
     EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_V.p, V, n_v * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_scale.p, scale, n_curves * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (n_v + n_curves) * sizeof(double);
-    prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+    return prep_resident(ctx, n_curves, n_points, [&](uint32_t c) { return scale[c]; });
+}
+
+int eps_set_potentials_rot(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points, const double* scale,
+                           const double* r_min, const double* grid_step, const uint32_t* J, uint32_t n_J) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, V && scale && r_min && grid_step && J, EPS_ERR_INVALID, "null argument");
+    EPS_REQUIRE(ctx, n_curves >= 1 && n_points >= 3 && n_J >= 1, EPS_ERR_INVALID, "need >=1 curve of >=3 points and >=1 rotational state");
+    EPS_REQUIRE(ctx, static_cast<uint64_t>(n_curves) * n_J <= 65535u * 64u, EPS_ERR_INVALID, "too many (curve, J) pairs");
+    for (uint32_t c = 0; c < n_curves; c++) {
+        EPS_REQUIRE(ctx, std::isfinite(scale[c]) && scale[c] > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
+        EPS_REQUIRE(ctx, std::isfinite(r_min[c]) && std::isfinite(grid_step[c]) && grid_step[c] > 0.0, EPS_ERR_INVALID,
+                    "r_min must be finite and grid_step finite and positive");
+    }
+    for (uint32_t j = 0; j < n_J; j++) EPS_REQUIRE(ctx, J[j] < (1u << 26), EPS_ERR_INVALID, "J must be below 2^26");
+    const uint32_t n_eff = n_curves * n_J;
+    const size_t   n_raw = static_cast<size_t>(n_points) * n_curves, n_v = static_cast<size_t>(n_points) * n_eff;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EPS_CUDA(ctx, ctx->d_Vraw.reserve(n_raw));
+    EPS_CUDA(ctx, ctx->d_rot.reserve(3 * static_cast<size_t>(n_curves)));
+    EPS_CUDA(ctx, ctx->d_J.reserve(n_J));
+    EPS_CUDA(ctx, ctx->d_V.reserve(n_v));
+    EPS_CUDA(ctx, ctx->d_scale.reserve(n_eff));
+    double* d_s = ctx->d_rot.p, *d_r0 = d_s + n_curves, *d_h = d_r0 + n_curves;
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_Vraw.p, V, n_raw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(d_s, scale, n_curves * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(d_r0, r_min, n_curves * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(d_h, grid_step, n_curves * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_J.p, J, n_J * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (n_raw + 3 * static_cast<size_t>(n_curves)) * sizeof(double) + n_J * sizeof(uint32_t);
+    const uint32_t bx = std::min<uint32_t>((n_points + 255) / 256, 64u);
+    centrifugal_kernel<<<dim3(bx, n_eff), 256, 0, ctx->stream>>>(ctx->d_Vraw.p, d_s, d_r0, d_h, ctx->d_J.p, n_J, n_points,
+                                                                 ctx->d_V.p, ctx->d_scale.p);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
-    std::vector<PrepOut> po(n_curves);
-    EPS_CUDA(ctx, cudaMemcpyAsync(po.data(), ctx->d_prep.p, n_curves * sizeof(PrepOut), cudaMemcpyDeviceToHost, ctx->stream));
-    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += n_curves * sizeof(PrepOut);
-    ctx->nC = 0;  // invalid until every curve checked out
-    for (uint32_t c = 0; c < n_curves; c++) {
-        EPS_REQUIRE(ctx, po[c].status != 1, EPS_ERR_RANGE, "potential table holds a non-finite value");
-        EPS_REQUIRE(ctx, po[c].status != 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
-    }
-    std::vector<eps_curve_info> infos(n_curves);
-    for (uint32_t c = 0; c < n_curves; c++) infos[c] = eps_curve_info{po[c].i0, po[c].n_steps, scale[c], po[c].v_min, po[c].v_last};
-    ctx->nC     = n_curves;
-    ctx->N      = N;
-    ctx->slot   = slot;
-    ctx->curves = std::move(infos);
-    ctx->h_F.clear();  // host copy for the constant-bank kernel: fetched on first use (fetch_host_table)
-    ctx->n_tiles_max = 0;
-    for (const auto& ci : ctx->curves) ctx->n_tiles_max = std::max(ctx->n_tiles_max, (ci.n_steps + kTile - 1) / kTile);
-    return EPS_OK;
+    return prep_resident(ctx, n_eff, n_points, [&](uint32_t c) { return scale[c / n_J]; });
 }
 
 int eps_get_curve_info(eps_ctx* ctx, uint32_t curve, eps_curve_info* out) {

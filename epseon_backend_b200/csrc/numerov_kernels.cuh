@@ -752,6 +752,34 @@ __global__ void spline_eval_kernel(const double* __restrict__ knots, const doubl
 }
 
 // ---------------------------------------------------------------------------
+// Rotational states (spec DESIGN.md section 3.7; oracle: orc_centrifugal).  Expands n_curves raw
+// tables into n_curves * n_J effective ones, V_J = V + J(J+1) (h^2 / 12 s) / r^2, row c*n_J + j.
+// Pure streaming: 8 B read (L2 hit for all but the first J of a curve) + 8 B written per point.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+centrifugal_kernel(const double* __restrict__ Vraw, const double* __restrict__ scale, const double* __restrict__ rmin,
+                   const double* __restrict__ hstep, const uint32_t* __restrict__ J, uint32_t n_J, uint32_t N,
+                   double* __restrict__ Vout, double* __restrict__ scale_out) {
+    const uint32_t row = blockIdx.y, c = row / n_J, j = row - c * n_J;
+    const uint32_t Jv  = J[j];
+    const double   s = scale[c], h = hstep[c], r0 = rmin[c];
+    const double   jj = static_cast<double>(static_cast<unsigned long long>(Jv) * (static_cast<unsigned long long>(Jv) + 1ull));
+    const double   cj = __ddiv_rn(__dmul_rn(jj, __dmul_rn(h, h)), __dmul_rn(12.0, s));
+    const double*  src = Vraw + static_cast<uint64_t>(c) * N;
+    double*        dst = Vout + static_cast<uint64_t>(row) * N;
+    if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[row] = s;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        double v = src[i];
+        if (Jv != 0) {
+            const double r = __dadd_rn(r0, __dmul_rn(static_cast<double>(i), h));
+            v              = __dadd_rn(v, __ddiv_rn(cj, __dmul_rn(r, r)));
+            if (v > 1e300) v = 1e300;
+        }
+        dst[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Preparation on the device (spec DESIGN.md section 3.2; oracle: orc_prep).  One CTA per curve:
 // first argmin of q = s V, the window around it with q - q_min <= T_MAX, the coefficient table
 // F_k = (1 - q_{i0+k}) / 12 written into the curve's slot (padded with 1/12).  Every value is

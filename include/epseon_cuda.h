@@ -122,6 +122,19 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
                        const double* scale);
 int eps_get_curve_info(eps_ctx* ctx, uint32_t curve, eps_curve_info* out);
 
+/* ---- rotational states (the reference's parameter set has no J,
+ * algorithm_config.hpp:78-83 -- additive).  Every table row is expanded ON THE DEVICE into n_J
+ * effective curves
+ *     V_J(r_i) = V(r_i) + J(J+1) * (hbar^2/2mu) / r_i^2,   r_i = r_min[c] + i*grid_step[c],
+ * hbar^2/2mu = grid_step[c]^2 / (12*scale[c]).  Resident curve index = c*n_J + j, so every later
+ * call (eps_sweep*, eps_solve_levels*, eps_wavefunctions, eps_get_curve_info) sees
+ * n_curves*n_J curves and takes / returns arrays of that many rows.  J[j] = 0 keeps the row bit
+ * for bit; a grid point at r = 0 becomes a 1e300 wall.  V: host [n_curves][n_points];
+ * scale, r_min, grid_step: host [n_curves]; J: host [n_J]. */
+int eps_set_potentials_rot(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_t n_points,
+                           const double* scale, const double* r_min, const double* grid_step,
+                           const uint32_t* J, uint32_t n_J);
+
 /* ---- tabulated sources (N1): natural cubic spline through n_knots points (r strictly increasing),
  * resampled on the uniform grid r_i = r_min + i*(r_max-r_min)/(n_points-1).  Makes real the
  * tabulated-file source the reference declares and leaves empty

@@ -103,6 +103,28 @@ void orc_lj_tabulate(double De, double re, double rmin, double rmax, uint32_t N,
     }
 }
 
+/* Rotational states (spec DESIGN.md section 3.7): effective potential
+ *   V_J(r_i) = V(r_i) + J(J+1) * (hbar^2 / 2 mu) / r_i^2,   r_i = rmin + i*h,
+ * with hbar^2/2mu = h^2/(12 s) taken from the curve's own scale s, so no mass enters twice.
+ * J = 0 copies the table bit for bit.  A point at r = 0 (the reference fixture's min_r,
+ * python/test/test_libepseon_gpu.py:183-190) gives an infinite barrier: values above 1e300 are
+ * clamped to 1e300 (a wall; the window rule of orc_prep excludes it).  NaN stays NaN. */
+void orc_centrifugal(const double* V, uint32_t N, double s, double rmin, double h, uint32_t J,
+                     double* out) {
+    if (J == 0) {
+        memcpy(out, V, sizeof(double) * N);
+        return;
+    }
+    const double jj = (double)((uint64_t)J * ((uint64_t)J + 1u));
+    const double cj = (jj * (h * h)) / (12.0 * s);
+    for (uint32_t i = 0; i < N; i++) {
+        const double r = rmin + (double)i * h;
+        double       v = V[i] + cj / (r * r);
+        if (v > 1e300) v = 1e300;
+        out[i] = v;
+    }
+}
+
 /* s = h^2 * (2 mu / hbar^2) / 12 with mu = m0 m1/(m0+m1): maps an energy in
  * cm^-1 to the dimensionless Numerov variable.  Masses are
  * VibwaAlgorithmConfig::mass_atom_{0,1} (algorithm_config.hpp:78-79). */

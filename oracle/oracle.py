@@ -84,6 +84,7 @@ class Oracle:
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_spline_resample.restype = C.c_int
         L.orc_spline_resample.argtypes = [_f64p, _f64p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, _f64p]
+        L.orc_centrifugal.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32, _f64p]
         L.orc_wavefunction.restype = C.c_int64
         L.orc_wavefunction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, _f64p]
 
@@ -103,6 +104,13 @@ class Oracle:
         V = np.empty(N, dtype=np.float64)
         self.lib.orc_lj_tabulate(De, re, rmin, rmax, N, V)
         return V
+
+    def centrifugal(self, V, s, rmin, h, J) -> np.ndarray:
+        """V_J = V + J(J+1) (h^2 / 12 s) / r^2 on r_i = rmin + i h (J = 0: copy)."""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        out = np.empty_like(V)
+        self.lib.orc_centrifugal(V, V.size, float(s), float(rmin), float(h), int(J), out)
+        return out
 
     def prep(self, V: np.ndarray, s: float):
         """-> (F[n_steps], i0, n_steps, vmin)"""

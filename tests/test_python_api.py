@@ -277,3 +277,32 @@ def test_wavefunctions_through_python_api(gpu_mod, oracle):
     handle2 = interface.submit_task(_configure_task(gpu_mod, interface.get_task_configurator("float64")))
     handle2.wait()
     assert handle2.get_wavefunctions().size == 0
+
+
+@pytest.mark.gpu
+def test_rotational_states_through_python_api(gpu_mod, oracle):
+    """Additive surface: set_rotational_states([J...]) -> rows [curve][J]; levels carry
+    the bits of the oracle run on orc_centrifugal's table."""
+    interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
+    cfg = _configure_task(gpu_mod, interface.get_task_configurator("float64"), max_level=3)
+    with pytest.raises(RuntimeError):
+        cfg.set_rotational_states([])
+    with pytest.raises(RuntimeError):
+        cfg.set_rotational_states([1 << 26])
+    assert cfg.set_rotational_states([0, 2, 10]) is cfg
+    handle = interface.submit_task(cfg)
+    handle.wait()
+    assert not handle.has_failed(), handle.get_status_message()
+    levels = np.array(handle.get_levels())
+    assert levels.shape == (6, 4)  # 2 curves x 3 J
+    assert np.array_equal(levels[:3], levels[3:])
+    assert np.all(np.diff(levels[:3], axis=0) > 0)
+    N = 16500
+    h = W.grid_h(0.0, 10.0, N)
+    V = oracle.morse(5500.0, 0.6, 10.0, 0.0, 10.0, N)
+    s = oracle.scale(87.62, 87.62, h)
+    for k, J in enumerate((0, 2, 10)):
+        VJ = oracle.centrifugal(V, s, 0.0, h, J)
+        F, _, _, vmin = oracle.prep(VJ, s)
+        lev_o, *_ = oracle.solve_levels(F, s, vmin, VJ[-1] - 0.1, 1024, 0, 3, 256, 1e-12, 16)
+        assert np.array_equal(levels[k].view(np.uint64), lev_o.view(np.uint64)), J
