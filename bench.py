@@ -46,6 +46,7 @@ sys.path.insert(0, str(ROOT))
 from tests import workloads as W  # noqa: E402
 
 METRIC = "numerov_grid_steps_x_trial_energies_per_s"
+_REAL_STDOUT = 1  # fd of the run's own stdout (main() moves fd 1 to stderr)
 FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
 CPU_SAMPLE_SECONDS = 10.0  # bounded CPU sample of the same workload (cpu_baseline)
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
@@ -64,6 +65,27 @@ C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rou
 C3 = dict(N=1_000_000, nE=4096)
 C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=64, rel_tol=1e-10, max_rounds=8, v_max=7)
 C5 = dict(N=200_000, nE=1 << 24)
+
+
+def workload_config(name: str) -> dict:
+    """`config` of the JSON line: the same dict for the CUDA arm and for `--impl reference`."""
+    l2 = "flushed between timed steps (256 MiB memset)"
+    if name == "c2":
+        return {"workload": "c2: Morse (H2-like) 100k-point grid, 65536 trial energies coarse sweep + k-section "
+                            "refinement of all 17 bound levels to 1e-10 rel.; one curve per GPU (curve-sharded)",
+                "grid_points": C2["N"], "trial_energies_coarse": C2["n_coarse"],
+                "refine_points_per_level": C2["refine_points"], "levels": C2["v_max"] + 1, "l2": l2}
+    if name == "c3":
+        return {"workload": "c3: tabulated curve (64 knots, natural cubic spline) resampled to a 1M-point grid, sweep of "
+                            "4096 trial energies through the transfer-matrix scan path; replicas at N > 1",
+                "grid_points": C3["N"], "trial_energies": C3["nE"], "l2": l2}
+    if name == "c4":
+        return {"workload": "c4: 4096 perturbed Morse/LJ curves x 1024 coarse energies, levels 0..7 refined to 1e-10 "
+                            "rel.; curves sharded over the ranks",
+                "curves": C4["nC"], "grid_points": C4["N"], "trial_energies_coarse": C4["n_coarse"],
+                "refine_points_per_level": C4["refine_points"], "levels": C4["v_max"] + 1, "l2": l2}
+    return {"workload": "c5: dense sweep of 2^24 trial energies on a 200k-point grid, energy-range sharded",
+            "grid_points": C5["N"], "trial_energies": C5["nE"], "l2": l2}
 
 
 def rank_curve(rank: int):
@@ -218,7 +240,7 @@ def run_reference(args) -> None:
             return time.perf_counter() - t, n_steps * nE
 
         sample = f"2^16 of the 2^24 energies (every 256th) on the 200k grid, {orc.threads} threads"
-        cfg = {"workload": "c5: dense sweep 2^24 energies x 200k-point grid (energy-range sharded)"}
+        cfg = workload_config("c5")
     elif args.workload == "c3":
         w = W.c3(C3["N"], C3["nE"])
         F, *_ = orc.prep(w["V"], w["s"])
@@ -230,7 +252,7 @@ def run_reference(args) -> None:
             return time.perf_counter() - t, F.size * C3["nE"]
 
         sample = f"the full C3 sweep (4096 energies x 1M-point grid), {orc.threads} threads"
-        cfg = {"workload": "c3: tabulated curve, 1M-point grid, sweep of 4096 trial energies"}
+        cfg = workload_config("c3")
     elif args.workload == "c4":
         w = W.c4(64, C4["N"], C4["n_coarse"])
 
@@ -243,7 +265,7 @@ def run_reference(args) -> None:
             return time.perf_counter() - t, steps
 
         sample = f"64 of the 4096 curves (full level solve each), {orc.threads} threads"
-        cfg = {"workload": "c4: 4096 perturbed Morse/LJ curves x 1024 energies, levels 0..7 to 1e-10"}
+        cfg = workload_config("c4")
     else:
         V, s, E_lo, E_hi, _ = rank_curve(0)
 
@@ -252,7 +274,7 @@ def run_reference(args) -> None:
             return dt, steps
 
         sample = f"full C2 solve (coarse 65536 + refinement of 17 levels), {orc.threads} threads"
-        cfg = {"workload": "c2: Morse 100k-point grid, 65536 trial energies, all 17 bound levels to 1e-10"}
+        cfg = workload_config("c2")
     for _ in range(args.warmup):
         one()
     tot_t = tot_s = 0.0
@@ -261,7 +283,7 @@ def run_reference(args) -> None:
         tot_t += dt
         tot_s += st
     val = tot_s / tot_t
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "strong" if args.workload in ("c4", "c5") else "weak",
@@ -269,10 +291,21 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": orc.threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference repo has no implementation of this path; this is the build's CPU oracle (port)",
-    }))
+    })
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the run, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def main() -> None:
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,
+    # compiler chatter of build()) goes to stderr instead.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -325,11 +358,7 @@ def main() -> None:
             ctx.set_potentials(V, s)  # host table -> prep -> H2D
             return step_resident()  # ... -> levels, widths, counts D2H
 
-        cfg = {"workload": "c2: Morse (H2-like) 100k-point grid, 65536 trial energies coarse sweep + k-section "
-                           "refinement of all 17 bound levels to 1e-10 rel.; one curve per GPU (curve-sharded)",
-               "grid_points": C2["N"], "trial_energies_coarse": C2["n_coarse"],
-               "refine_points_per_level": C2["refine_points"], "levels": C2["v_max"] + 1,
-               "l2": "flushed between timed steps (256 MiB memset)"}
+        cfg = workload_config("c2")
         scaling = "weak"
     elif args.workload == "c3":
         w = W.c3(C3["N"], C3["nE"])
@@ -346,9 +375,7 @@ def main() -> None:
             n, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
             return n
 
-        cfg = {"workload": "c3: tabulated curve (64 knots, natural cubic spline) resampled to a 1M-point grid, sweep of "
-                           "4096 trial energies through the transfer-matrix scan path; replicas at N > 1",
-               "grid_points": C3["N"], "trial_energies": C3["nE"], "l2": "flushed between timed steps (256 MiB memset)"}
+        cfg = workload_config("c3")
         scaling = "weak"
     elif args.workload == "c4":
         w = W.c4(C4["nC"], C4["N"], C4["n_coarse"])
@@ -367,11 +394,7 @@ def main() -> None:
             ctx.set_potentials(V, s)
             return step_resident()
 
-        cfg = {"workload": "c4: 4096 perturbed Morse/LJ curves x 1024 coarse energies, levels 0..7 refined to 1e-10 "
-                           "rel.; curves sharded over the ranks",
-               "curves": C4["nC"], "grid_points": C4["N"], "trial_energies_coarse": C4["n_coarse"],
-               "refine_points_per_level": C4["refine_points"], "levels": C4["v_max"] + 1,
-               "l2": "flushed between timed steps (256 MiB memset)"}
+        cfg = workload_config("c4")
         scaling = "strong"
     else:
         w = W.c5(C5["N"], C5["nE"])
@@ -392,8 +415,7 @@ def main() -> None:
             n, _, _ = ctx.sweep_grid(w["E_lo"], dE, j0, per, nodes=True, tails=False)  # 4 B/energy D2H
             return n
 
-        cfg = {"workload": "c5: dense sweep of 2^24 trial energies on a 200k-point grid, energy-range sharded",
-               "grid_points": C5["N"], "trial_energies": C5["nE"], "l2": "flushed between timed steps (256 MiB memset)"}
+        cfg = workload_config("c5")
         scaling = "strong"
 
     def gather_small(arr: np.ndarray):
@@ -573,7 +595,7 @@ def main() -> None:
                 line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": orc.threads,
                                         "kind": "port", "sample": f"2^18 of the 2^24 energies (every 64th), repeated {reps}x",
                                         "seconds": secs}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
