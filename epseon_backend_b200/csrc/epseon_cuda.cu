@@ -264,10 +264,11 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
         attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs    = &attr;
-        cfg.numAttrs = (ctx->cb_pdl == 2 || (ctx->cb_pdl == 1 && grid >= 2ull * ctx->sm_count)) ? 1 : 0;
+        cfg.numAttrs = (ctx->cb_pdl >= 2 || (ctx->cb_pdl == 1 && grid >= 2ull * ctx->sm_count)) ? 1 : 0;
+        const int pdl_late = ctx->cb_pdl > 2 ? ctx->cb_pdl - 2 : 0;  // trigger that many 128-step blocks before the chunk's end
         cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails>, chunk, d_jobs,
                                            static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
-                                           k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, st, out.nodes, kTails ? out.mant : nullptr,
+                                           k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, pdl_late, st, out.nodes, kTails ? out.mant : nullptr,
                                            kTails ? out.expo : nullptr, ctx->d_steps);
         if (e != cudaSuccess) return e;
         ctx->cbank_launches++;
@@ -1067,7 +1068,7 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
             ctx->opt_cbank = value;
             return EPS_OK;
         case EPS_OPT_CBANK_PDL:
-            ctx->cb_pdl = value < 0 ? 0 : value > 2 ? 2 : static_cast<int>(value);
+            ctx->cb_pdl = value < 0 ? 0 : value > 18 ? 18 : static_cast<int>(value);
             return EPS_OK;
         case EPS_OPT_CBANK_SHAPE:  // tuning: energies per thread * 1000 + threads per CTA
             EPS_REQUIRE(ctx, (value / 1000 == 2 || value / 1000 == 4) && (value % 1000 == 128 || value % 1000 == 256), EPS_ERR_INVALID,

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreads)
 numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ jobs,
                      const uint32_t chunks_per_job, const double* __restrict__ Eexp,
                      const uint64_t out_stride, const double scale, const uint32_t len, const int first,
-                     const int last, const CbState st, uint32_t* __restrict__ nodes_out,
+                     const int last, const int pdl_late, const CbState st, uint32_t* __restrict__ nodes_out,
                      double* __restrict__ mant_out, int32_t* __restrict__ exp_out,
                      unsigned long long* __restrict__ steps_done) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
@@ -53,9 +53,11 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
     // previous chunk has completed and its state stores are visible; only THEN does this chunk let
     // its own dependent become resident, so exactly one chunk is ever parked behind the running one
     // (triggering before the wait lets every queued chunk of the sweep pile up on the SMs:
-    // measured 2.21 ms instead of 1.97 ms on a one-wave sweep).
+    // measured 2.21 ms instead of 1.97 ms on a one-wave sweep).  pdl_late > 0 moves the trigger to
+    // pdl_late renormalisation blocks (128 steps, ~2 us) before the end of the chunk: the dependent
+    // is then resident only while this chunk drains, which is all a one-wave sweep can overlap.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (pdl_late == 0) asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t job_idx = blockIdx.x / chunks_per_job;
     const uint32_t chunk   = blockIdx.x - job_idx * chunks_per_job;
     const Job      job     = jobs[job_idx];
@@ -96,6 +98,7 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
                                       // across the loop back-edges ptxas will not hoist an LDCU over
 #pragma unroll 1
     for (uint32_t r = 0; r < n_full; r++) {
+        if (pdl_late != 0 && r + pdl_late == n_full) asm volatile("griddepcontrol.launch_dependents;");
 #pragma unroll 1
         for (int q = 0; q < kRenorm / 32; q++) {
             uint32_t mask[kEpt];
