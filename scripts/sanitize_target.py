@@ -1,0 +1,39 @@
+"""Small pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+TMA sweep (tails, packed + flat refinement rows), scan path + fix-up, constant-bank chunks,
+device prep, centrifugal expansion, spline evaluation, wavefunctions.  Sizes are tiny: the
+sanitizer slows kernels 10-100x."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from epseon_backend_b200 import cabi  # noqa: E402
+from tests import workloads as W  # noqa: E402
+
+N = 6000
+h = W.grid_h(0.4, 9.0, N)
+V = np.stack([W.morse(5500.0, 2.2, 1.6, 0.4, 9.0, N), W.lj(4800.0, 2.4, 0.4, 9.0, N)])
+s = W.scale(20.0, 20.0, h)
+with cabi.Context(0) as ctx:
+    ctx.set_potentials(V, s)
+    lo, hi = V.min(axis=1), V[:, -1] - 1.0
+    ctx.sweep_uniform(lo, hi, 700)                                     # TMA kernel, tails
+    lev, wid, nb = ctx.solve_levels(lo, hi, 512, 0, 5, 64, 1e-10, 6)   # packed refinement rows
+    ctx.wavefunctions(lev, np.full(2, h))
+    ctx.set_potentials_rot(V, s, 0.4, h, [0, 3])                      # centrifugal expansion + prep
+    ctx.sweep_uniform(np.repeat(lo, 2), np.repeat(hi, 2), 64, tails=False)
+    ctx.set_potentials(V[0], s)
+    ctx.solve_levels(lo[0], hi[0], 1024, 0, 5, 300, 1e-10, 6)          # flat refinement rows (one curve)
+    ctx.set_option(ctx.OPT_CBANK, 1)                                   # constant-bank chunks (2 launches)
+    ctx.sweep_uniform(lo[0], hi[0], 1500)
+    ctx.set_option(ctx.OPT_CBANK, 2)
+    ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 3)                           # transfer-matrix scan + combine (+ fix-up)
+    ctx.sweep_uniform(lo[0], hi[0], 300, tails=False)
+    ctx.solve_levels(lo[0], hi[0], 256, 0, 3, 32, 1e-10, 6)
+    ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 0)
+    rk = np.concatenate([np.linspace(0.4, 4.0, 40), np.linspace(4.5, 9.0, 8)])
+    ctx.spline_resample(rk, W.morse(5500.0, 2.2, 1.6, 0.4, 9.0, 2)[0] + 5500.0 * (1 - np.exp(-1.6 * (rk - 2.2))) ** 2, 0.4, 9.0, 3000)
+    ctx.sync()
+print("sanitize_target done")
