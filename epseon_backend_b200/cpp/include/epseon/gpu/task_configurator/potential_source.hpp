@@ -10,6 +10,7 @@
 #include "epseon_cuda.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <fstream>
 #include <memory>
@@ -43,7 +44,8 @@ namespace epseon::gpu::cpp {
         [[nodiscard]] virtual std::unique_ptr<PotentialSource<FP>> unique_clone() const     = 0;
     };
 
-    // Tabulated curves from text files: one "r V" pair per line ('#' comments allowed).  A table on
+    // Tabulated curves from files: text with one "r V" pair per line ('#' comments allowed), or a
+    // NumPy .npy array of shape (n, 2) (float64, C order) when the name ends in ".npy".  A table on
     // a uniform r grid is used as it is; a table on a non-uniform grid (ab initio points), or any
     // table when `point_count` > 0, is resampled onto `point_count` uniform points of
     // [r_first, r_last] with a natural cubic spline (coefficients: eps_spline_coefficients of the
@@ -60,7 +62,46 @@ namespace epseon::gpu::cpp {
             double              r0 = 0.0;
         };
 
+        // NumPy .npy (format 1.0 / 2.0 / 3.0): a C-ordered little-endian float64 array of shape (n, 2),
+        // column 0 = r, column 1 = V.
+        static void read_npy(const std::string& path, std::vector<double>& r, std::vector<double>& v) {
+            std::ifstream in(path, std::ios::binary);
+            if (!in) throw std::runtime_error("PotentialFileLoader: cannot open '" + path + "'");
+            unsigned char head[10] = {};
+            in.read(reinterpret_cast<char*>(head), 10);
+            if (!in || std::string(reinterpret_cast<char*>(head), 6) != "\x93NUMPY")
+                throw std::runtime_error("PotentialFileLoader: '" + path + "' is not a .npy file");
+            size_t hlen = head[8] | (static_cast<size_t>(head[9]) << 8);
+            if (head[6] >= 2) { // 4-byte header length
+                unsigned char more[2] = {};
+                in.read(reinterpret_cast<char*>(more), 2);
+                hlen |= (static_cast<size_t>(more[0]) << 16) | (static_cast<size_t>(more[1]) << 24);
+            }
+            std::string header(hlen, '\0');
+            in.read(header.data(), static_cast<std::streamsize>(hlen));
+            if (!in) throw std::runtime_error("PotentialFileLoader: '" + path + "': truncated .npy header");
+            const auto has = [&](const char* needle) { return header.find(needle) != std::string::npos; };
+            if (!(has("'<f8'") || has("'=f8'") || has("'|f8'")) || !has("'fortran_order': False"))
+                throw std::runtime_error("PotentialFileLoader: '" + path + "' must hold C-ordered little-endian float64");
+            const auto lp = header.find('(', header.find("'shape'")), rp = header.find(')', lp);
+            unsigned long long n = 0, cols = 0;
+            if (lp == std::string::npos || rp == std::string::npos ||
+                std::sscanf(header.substr(lp, rp - lp + 1).c_str(), "(%llu, %llu)", &n, &cols) != 2 || cols != 2)
+                throw std::runtime_error("PotentialFileLoader: '" + path + "' must have shape (n, 2)");
+            if (n < 3) throw std::runtime_error("PotentialFileLoader: '" + path + "' holds fewer than 3 points");
+            std::vector<double> rv(2 * static_cast<size_t>(n));
+            in.read(reinterpret_cast<char*>(rv.data()), static_cast<std::streamsize>(rv.size() * sizeof(double)));
+            if (!in) throw std::runtime_error("PotentialFileLoader: '" + path + "': truncated .npy data");
+            r.resize(n);
+            v.resize(n);
+            for (size_t i = 0; i < n; i++) {
+                r[i] = rv[2 * i];
+                v[i] = rv[2 * i + 1];
+            }
+        }
+
         static void read_table(const std::string& path, std::vector<double>& r, std::vector<double>& v) {
+            if (path.size() >= 4 && path.compare(path.size() - 4, 4, ".npy") == 0) return read_npy(path, r, v);
             std::ifstream in(path);
             if (!in) throw std::runtime_error("PotentialFileLoader: cannot open '" + path + "'");
             std::string line;

@@ -92,7 +92,8 @@ namespace epseon::gpu::python {
                      "row = curve * len(j_values) + j.  Default [0].")
                 .def("set_potential_files", &C::set_potential_files, py::arg("file_names"), py::arg("point_count") = 0,
                      py::return_value_policy::reference,
-                     "Use tabulated 'r V' text files as potential source; tables on a non-uniform grid (or any "
+                     "Use tabulated 'r V' text files (or NumPy .npy arrays of shape (n, 2)) as potential source; "
+                     "tables on a non-uniform grid (or any "
                      "table when point_count > 0) are resampled with a natural cubic spline.")
                 .def("set_vibwa_algorithm", &C::set_vibwa_algorithm, py::arg("mass_atom_0"), py::arg("mass_atom_1"),
                      py::arg("integration_step"), py::arg("min_distance_to_asymptote"), py::arg("min_level"),

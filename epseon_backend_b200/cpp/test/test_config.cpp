@@ -83,6 +83,37 @@ void potential_source() {
         auto                           t = fl.get_potential_data();
         CHECK(t.size() == 1 && t[0].size() == 11 && t[0][5] == FP(0) && t[0][0] == FP(50));
         CHECK(std::fabs(fl.get_grid_steps()[0] - 0.5) < 1e-15);
+        CHECK(fl.get_grid_origins()[0] == 1.0);
+    }
+    {   // the same table as a NumPy .npy array of shape (11, 2) (format 1.0, what numpy.save writes)
+        const char* path = "/tmp/epseon_b200_test_curve.npy";
+        {
+            std::string dict = "{'descr': '<f8', 'fortran_order': False, 'shape': (11, 2), }";
+            while ((10 + dict.size() + 1) % 64 != 0) dict.push_back(' ');
+            dict.push_back('\n');
+            std::ofstream out(path, std::ios::binary);
+            const unsigned char head[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, static_cast<unsigned char>(dict.size() & 0xff),
+                                            static_cast<unsigned char>(dict.size() >> 8)};
+            out.write(reinterpret_cast<const char*>(head), 10);
+            out.write(dict.data(), static_cast<std::streamsize>(dict.size()));
+            for (int i = 0; i < 11; i++) {
+                const double rv[2] = {1.0 + 0.5 * i, (i - 5) * (i - 5) * 2.0};
+                out.write(reinterpret_cast<const char*>(rv), sizeof(rv));
+            }
+        }
+        const std::vector<std::string> one{path};
+        PotentialFileLoader<FP>        fl(one);
+        auto                           t = fl.get_potential_data();
+        CHECK(t.size() == 1 && t[0].size() == 11 && t[0][5] == FP(0) && t[0][0] == FP(50) && t[0][10] == FP(50));
+        CHECK(std::fabs(fl.get_grid_steps()[0] - 0.5) < 1e-15);
+        bool refused = false;
+        try {
+            const std::vector<std::string> bad{"/tmp/epseon_b200_test_curve.txt.npy"};
+            PotentialFileLoader<FP>(bad).get_potential_data();
+        } catch (const std::runtime_error&) {
+            refused = true;
+        }
+        CHECK(refused);
     }
 }
 

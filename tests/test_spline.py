@@ -62,18 +62,22 @@ def test_gpu_spline_rejects_bad_knots(gpu_ctx):
 
 
 @pytest.mark.gpu
-def test_file_loader_resamples_non_uniform_table(tmp_path, oracle):
-    """PotentialFileLoader made real for ab initio tables: a 64-knot non-uniform 'r V' file, resampled
-    by the C++ loader to 20 001 points, solved through the Python API == the oracle on the oracle's
-    own resampling of the same knots."""
+@pytest.mark.parametrize("fmt", ["dat", "npy"])
+def test_file_loader_resamples_non_uniform_table(tmp_path, oracle, fmt):
+    """PotentialFileLoader made real for ab initio tables: a 64-knot non-uniform 'r V' file (text, or
+    a NumPy .npy array of shape (n, 2)), resampled by the C++ loader to 20 001 points, solved through
+    the Python API == the oracle on the oracle's own resampling of the same knots."""
     from epseon_backend.device.gpu import _libepseon_gpu as gpu_mod
 
     rk, Vk = _knots(seed=11)
-    path = tmp_path / "curve.dat"
-    with open(path, "w") as f:
-        f.write("# r [Angstrom]   V [cm^-1]\n")
-        for a, b in zip(rk, Vk):
-            f.write(f"{float(a)!r} {float(b)!r}\n")
+    path = tmp_path / f"curve.{fmt}"
+    if fmt == "npy":
+        np.save(path, np.column_stack([rk, Vk]))
+    else:
+        with open(path, "w") as f:
+            f.write("# r [Angstrom]   V [cm^-1]\n")
+            for a, b in zip(rk, Vk):
+                f.write(f"{float(a)!r} {float(b)!r}\n")
     N = 20_001
     interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
     cfg = interface.get_task_configurator("float64")
