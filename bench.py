@@ -53,12 +53,19 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1
 
 # dominant kernel per workload + its DRAM traffic per launch from the committed `ncu --set full`
 # captures (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1c_ncu.md, r1c_scan_ncu.md,
-# r1b_cbank_ncu.md).  Algorithmic bytes = the coefficient table once per launch (8 B x grid steps).
+# r1e_c4_ncu.md, r1e_c5_cbank_ncu.md).  Algorithmic bytes = every resident curve's coefficient table
+# once per launch (8 B x grid steps x curves).
+#   c4: one launch streams the tables of all 4096 curves (measured on the 1-GPU shape).
+#   c5: a "launch" of the bench is one sweep = 51 chunk launches of the constant-bank kernel; each
+#       carries the per-energy state (28 B read + 28 B written per energy) through HBM by design:
+#       881 MB per chunk launch at 2^24 energies = 58 GB/s, under 1 % of the HBM peak.
 KERNEL_META = {
     "c2": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=32> (TMA ring, flat refinement rows)", 826_112, "profiles/r1c_ncu.md"),
     "c3": ("eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)", 8_028_416, "profiles/r1c_scan_ncu.md"),
-    "c4": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=8> (TMA ring, packed refinement rows)", None, None),
-    "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", None, None),
+    "c4": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=8> (TMA ring, packed refinement rows)", 346_653_184,
+           "profiles/r1e_c4_ncu.md (1-GPU shape: 4096 curves per launch)"),
+    "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", 51 * 881_415_680,
+           "profiles/r1e_c5_cbank_ncu.md (1-GPU shape: 51 chunk launches x 881 MB of per-energy state carry)"),
 }
 
 C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
@@ -527,7 +534,7 @@ def main() -> None:
                 "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
                 "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
                 "traffic": KERNEL_META[args.workload][1], "traffic_source": KERNEL_META[args.workload][2],
-                "algorithmic_bytes_per_launch": 8 * int(n_steps),
+                "algorithmic_bytes_per_launch": 8 * int(n_steps) * int(ctx.n_curves),
             },
             "clocks": clocks,
         }
