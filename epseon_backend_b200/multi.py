@@ -100,3 +100,39 @@ def solve_levels_energy_sharded(solver, dist, E_lo, E_hi, n_coarse: int, v_min: 
     lasts = all_gather_array(dist, np.asarray(n_last, dtype=np.uint32))
     owners = [r for r in range(world) if energy_shard(n_coarse, world, r)[1] >= 2]
     return merge_levels(levs), merge_levels(wids), lasts[owners[-1]]
+
+
+def solve_morse_batch_all_devices(gpu_mod, configurations, hardware: dict, algorithm: dict, precision: str = "float64",
+                                  device_ids=None, rotational_states=None):
+    """In-process fan-out over the reference's own API ("one
+    ComputeDeviceInterface per GPU"): the list of ``MorsePotentialConfig`` is cut into contiguous
+    blocks (``curve_shard``), one task per device is configured and submitted -- every
+    ``TaskHandle`` owns a worker thread and its own CUDA context, so the devices run concurrently
+    -- and the per-curve results are concatenated in the original order.
+
+    ``hardware`` / ``algorithm`` are the keyword arguments of ``set_hardware_config`` /
+    ``set_vibwa_algorithm``.  Returns (levels [curve][level], level_counts [curve], handles).
+    """
+    ctx = gpu_mod.EpseonComputeContext.create()
+    if device_ids is None:
+        device_ids = [d.device_properties.device_id for d in ctx.get_physical_device_info()]
+    device_ids = list(device_ids)[: max(1, len(configurations))]
+    handles = []
+    for r, dev in enumerate(device_ids):
+        sl = curve_shard(len(configurations), len(device_ids), r)
+        if sl.stop == sl.start:
+            continue
+        interface = ctx.get_device_interface(dev)
+        cfg = (interface.get_task_configurator(precision).set_hardware_config(**hardware)
+               .set_morse_potential(list(configurations[sl])).set_vibwa_algorithm(**algorithm))
+        if rotational_states is not None:
+            cfg.set_rotational_states(list(rotational_states))
+        handles.append(interface.submit_task(cfg))
+    levels, counts = [], []
+    for h in handles:
+        h.wait()
+        if h.has_failed():
+            raise RuntimeError(h.get_status_message())
+        levels.extend(h.get_levels())
+        counts.extend(h.get_level_counts())
+    return levels, counts, handles

@@ -92,3 +92,27 @@ def test_gpu_energy_sliced_solve_equals_whole(gpu_ctx):
     j0, n = multi.energy_shard(2049, 4, 2)
     n_part, _, _ = gpu_ctx.sweep_grid(w["E_lo"], dE, j0, n, tails=False)
     assert np.array_equal(n_part[0], n_all[0][j0:j0 + n])
+
+
+@pytest.mark.gpu
+def test_in_process_fanout_over_reference_api():
+    """One task per visible device through the reference's own classes (threads, no torchrun):
+    the concatenated levels equal a single-device task over the whole batch, bit for bit."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    import epseon_backend.device.gpu._libepseon_gpu as m
+
+    rng = np.random.default_rng(7)
+    cfgs = [m.MorsePotentialConfig(dissociation_energy=5500.0 * (1 + 0.05 * rng.random()), equilibrium_bond_distance=2.2,
+                                   well_width=1.6, min_r=0.4, max_r=10.0, point_count=8000) for _ in range(11)]
+    hw = dict(potential_buffer_size=8000, group_size=1024, allocation_block_size=1 << 20)
+    alg = dict(mass_atom_0=20.0, mass_atom_1=20.0, integration_step=0.1, min_distance_to_asymptote=1.0,
+               min_level=0, max_level=4)
+    ids = [d.device_properties.device_id for d in m.EpseonComputeContext.create().get_physical_device_info()]
+    lev_all, cnt_all, handles = multi.solve_morse_batch_all_devices(m, cfgs, hw, alg)
+    assert len(handles) == min(len(ids), len(cfgs)) and len(lev_all) == len(cfgs) == len(cnt_all)
+    lev_one, cnt_one, _ = multi.solve_morse_batch_all_devices(m, cfgs, hw, alg, device_ids=ids[:1])
+    assert np.array_equal(np.array(lev_all).view(np.uint64), np.array(lev_one).view(np.uint64))
+    assert cnt_all == cnt_one
+    assert np.all(np.diff(np.array(lev_all), axis=1) > 0)
