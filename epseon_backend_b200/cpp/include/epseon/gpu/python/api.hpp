@@ -118,6 +118,13 @@ namespace epseon::gpu::python {
             return *this;
         }
 
+        // Additive: curves already in memory, rows of a [n_curves][point_count] table on a uniform grid.
+        TaskConfigurator& set_potential_tables(std::vector<std::vector<double>> tables, double min_r, double max_r) {
+            configurator->setPotentialSource(
+                std::make_shared<cpp::TabulatedPotentialSource<FP>>(std::move(tables), min_r, max_r));
+            return *this;
+        }
+
         // Additive: tabulated curves from "r V" text files.
         TaskConfigurator& set_potential_files(const std::vector<std::string>& file_names, uint32_t point_count) {
             configurator->setPotentialSource(std::make_shared<cpp::PotentialFileLoader<FP>>(file_names, point_count));

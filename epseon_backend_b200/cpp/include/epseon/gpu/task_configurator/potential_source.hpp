@@ -200,6 +200,56 @@ namespace epseon::gpu::cpp {
         }
     };
 
+    // Curves handed over in memory (additive; the natural source for ab initio data already held in
+    // an array): n_curves rows of point_count values on the uniform grid r_i = min_r + i*h,
+    // h = (max_r - min_r)/(point_count - 1).  Values are kept in double and cast to FP on request, so
+    // the float64 task sees the caller's bits.
+    template <typename FP>
+    class TabulatedPotentialSource : public PotentialSource<FP> {
+        std::vector<std::vector<double>> tables = {};
+        double                           min_r  = 0.0;
+        double                           max_r  = 0.0;
+
+      public:
+        TabulatedPotentialSource() noexcept = default;
+        TabulatedPotentialSource(std::vector<std::vector<double>> tables_, double min_r_, double max_r_) :
+            tables(std::move(tables_)), min_r(min_r_), max_r(max_r_) {
+            if (!(max_r > min_r)) throw std::runtime_error("TabulatedPotentialSource: max_r must exceed min_r");
+            for (const auto& t : tables) {
+                if (t.size() < 3) throw std::runtime_error("TabulatedPotentialSource: a curve needs at least 3 points");
+                if (t.size() != tables.front().size())
+                    throw std::runtime_error("TabulatedPotentialSource: all curves must have the same point count");
+            }
+        }
+        ~TabulatedPotentialSource() override = default;
+
+        bool equals(const PotentialSource<FP>& other) const override {
+            const auto* o = dynamic_cast<const TabulatedPotentialSource<FP>*>(&other);
+            return o != nullptr && tables == o->tables && min_r == o->min_r && max_r == o->max_r;
+        }
+
+        std::vector<std::vector<FP>> get_potential_data() override {
+            std::vector<std::vector<FP>> out;
+            out.reserve(tables.size());
+            for (const auto& t : tables) out.emplace_back(t.begin(), t.end());
+            return out;
+        }
+
+        std::vector<double> get_grid_steps() const override {
+            if (tables.empty()) return {};
+            return std::vector<double>(tables.size(), (max_r - min_r) / static_cast<double>(tables.front().size() - 1));
+        }
+
+        std::vector<double> get_grid_origins() const override { return std::vector<double>(tables.size(), min_r); }
+
+        std::shared_ptr<PotentialSource<FP>> shared_clone() const override {
+            return std::make_shared<TabulatedPotentialSource<FP>>(*this);
+        }
+        std::unique_ptr<PotentialSource<FP>> unique_clone() const override {
+            return std::make_unique<TabulatedPotentialSource<FP>>(*this);
+        }
+    };
+
     template <typename FP>
     class MorsePotentialConfig {
         static_assert(std::is_floating_point_v<FP>, "FP must be an floating-point type.");

@@ -90,6 +90,18 @@ namespace epseon::gpu::python {
                      "Solve every curve once per rotational quantum number J (effective potential "
                      "V + J(J+1) hbar^2 / (2 mu r^2)); get_levels() rows are then ordered curve-major, "
                      "row = curve * len(j_values) + j.  Default [0].")
+                .def("set_potential_tables",
+                     [](C& self, const py::array_t<double, py::array::c_style | py::array::forcecast>& tables, double min_r,
+                        double max_r) -> C& {
+                         if (tables.ndim() != 2) throw std::runtime_error("tables must be a 2-D array [n_curves][point_count]");
+                         std::vector<std::vector<double>> rows(static_cast<size_t>(tables.shape(0)));
+                         for (py::ssize_t c = 0; c < tables.shape(0); c++)
+                             rows[static_cast<size_t>(c)].assign(tables.data(c, 0), tables.data(c, 0) + tables.shape(1));
+                         return self.set_potential_tables(std::move(rows), min_r, max_r);
+                     },
+                     py::arg("tables"), py::arg("min_r"), py::arg("max_r"), py::return_value_policy::reference,
+                     "Use curves held in memory: a float64 array [n_curves][point_count] of V(r_i) on the uniform grid "
+                     "r_i = min_r + i (max_r - min_r)/(point_count - 1).")
                 .def("set_potential_files", &C::set_potential_files, py::arg("file_names"), py::arg("point_count") = 0,
                      py::return_value_policy::reference,
                      "Use tabulated 'r V' text files (or NumPy .npy arrays of shape (n, 2)) as potential source; "

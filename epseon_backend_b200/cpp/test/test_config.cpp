@@ -71,6 +71,20 @@ void potential_source() {
     CHECK(f == f2 && !(f == f3) && !f.equals(g) && !g.equals(f));
     CHECK(f.shared_clone()->equals(f) && f.unique_clone()->equals(f));
     CHECK(f3.get_potential_data().empty());
+    {   // curves handed over in memory
+        TabulatedPotentialSource<FP> t({{4.0, 1.0, 0.0, 1.0, 4.0}, {8.0, 2.0, 0.0, 2.0, 8.0}}, 1.0, 3.0), t0;
+        auto                         d = t.get_potential_data();
+        CHECK(d.size() == 2 && d[1].size() == 5 && d[1][0] == FP(8) && d[0][2] == FP(0));
+        CHECK(t.get_grid_steps() == (std::vector<double>{0.5, 0.5}) && t.get_grid_origins() == (std::vector<double>{1.0, 1.0}));
+        CHECK(t.equals(*t.shared_clone()) && t.equals(*t.unique_clone()) && !t.equals(t0) && !t.equals(g));
+        bool refused = false;
+        try {
+            TabulatedPotentialSource<FP> bad({{1.0, 2.0, 3.0}, {1.0, 2.0}}, 0.0, 1.0);
+        } catch (const std::runtime_error&) {
+            refused = true;
+        }
+        CHECK(refused);
+    }
     {   // a real table round-trips
         const char* path = "/tmp/epseon_b200_test_curve.txt";
         {

@@ -306,3 +306,31 @@ def test_rotational_states_through_python_api(gpu_mod, oracle):
         F, _, _, vmin = oracle.prep(VJ, s)
         lev_o, *_ = oracle.solve_levels(F, s, vmin, VJ[-1] - 0.1, 1024, 0, 3, 256, 1e-12, 16)
         assert np.array_equal(levels[k].view(np.uint64), lev_o.view(np.uint64)), J
+
+
+@pytest.mark.gpu
+def test_potential_tables_through_python_api(gpu_mod, oracle):
+    """Additive surface: curves handed over as a numpy array [curve][point]; float64 levels carry the
+    bits of the oracle run on the same tables (Morse + Lennard-Jones in one batch, as in config 4)."""
+    N, rmin, rmax = 12000, 0.4, 10.0
+    V = np.stack([W.morse(5500.0, 2.2, 1.6, rmin, rmax, N), W.lj(5200.0, 2.3, rmin, rmax, N)])
+    interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
+    cfg = interface.get_task_configurator("float64")
+    cfg.set_hardware_config(potential_buffer_size=N, group_size=1024, allocation_block_size=1 << 20)
+    assert cfg.set_potential_tables(V, rmin, rmax) is cfg and not cfg.is_configured()
+    cfg.set_vibwa_algorithm(mass_atom_0=20.0, mass_atom_1=20.0, integration_step=0.1,
+                            min_distance_to_asymptote=1.0, min_level=0, max_level=6)
+    assert cfg.is_configured()
+    with pytest.raises(RuntimeError):
+        cfg.set_potential_tables(V[0], rmin, rmax)  # 1-D
+    with pytest.raises(RuntimeError):
+        cfg.set_potential_tables(V, rmax, rmin)
+    handle = interface.submit_task(cfg)
+    handle.wait()
+    assert not handle.has_failed(), handle.get_status_message()
+    levels = np.array(handle.get_levels())
+    s = oracle.scale(20.0, 20.0, W.grid_h(rmin, rmax, N))
+    for c in range(2):
+        F, _, _, vmin = oracle.prep(V[c], s)
+        ref, *_ = oracle.solve_levels(F, s, vmin, V[c][-1] - 1.0, 1024, 0, 6, 256, 1e-12, 16)
+        assert np.array_equal(levels[c].view(np.uint64), ref.view(np.uint64)), c
