@@ -21,7 +21,7 @@ ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EP
 SYMBOLS = [
     "eps_abi_version", "eps_device_count", "eps_device_get_props", "eps_ctx_create",
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_set_potentials_rot", "eps_get_curve_info",
-    "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
+    "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_level_corrections", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe", "eps_host_alloc", "eps_host_free",
 ]
 
@@ -249,6 +249,16 @@ class Context:
         self._ck(self.lib.eps_wavefunctions(self.h, _ptr(E, np.float64), C.c_uint32(E.shape[1]),
                                             _ptr(h, np.float64), _ptr(psi, np.float64), _ptr(mi, np.uint32)))
         return psi, mi
+
+    def level_corrections(self, E, grid_step) -> np.ndarray:
+        """E[nC, nlev] -> dE[nC, nlev]: first-order (Cooley / Rayleigh-quotient) energy corrections."""
+        E = np.ascontiguousarray(np.atleast_2d(E), dtype=np.float64)
+        assert E.shape[0] == self.n_curves
+        h = _vec(grid_step, self.n_curves)
+        dE = np.empty(E.shape, dtype=np.float64)
+        self._ck(self.lib.eps_level_corrections(self.h, _ptr(E, np.float64), C.c_uint32(E.shape[1]),
+                                                _ptr(h, np.float64), _ptr(dE, np.float64)))
+        return dE
 
     def spline_resample(self, r, V, r_min: float, r_max: float, n_points: int) -> np.ndarray:
         """Natural cubic spline through (r, V), evaluated on the device on n_points uniform points."""

@@ -100,7 +100,7 @@ struct eps_ctx {
     uint64_t            cbank_launches = 0;
 
     // wavefunction scratch
-    DevBuf<double>   d_wfE, d_wfraw, d_wfin, d_wfpsi, d_wfh;
+    DevBuf<double>   d_wfE, d_wfraw, d_wfin, d_wfpsi, d_wfh, d_wfdE;
     DevBuf<int32_t>  d_wfbexp, d_wfinexp;
     DevBuf<uint32_t> d_wfmatch;
 
@@ -642,6 +642,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_wfin.release();
         ctx->d_wfpsi.release();
         ctx->d_wfh.release();
+        ctx->d_wfdE.release();
         ctx->d_wfbexp.release();
         ctx->d_wfinexp.release();
         ctx->d_wfmatch.release();
@@ -944,11 +945,15 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
     return solve_rows(ctx, p, GridSpec{E0, dE, true, j0}, levels, widths, n_last, n_first);
 }
 
-int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
-                      double* psi, uint32_t* match_index) {
-    if (int rc = bind(ctx)) return rc;
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Validates, uploads E / grid_step and runs the two wavefunction kernels; the normalised psi stays
+// in ctx->d_wfpsi ([item][n_points]), the window-relative matching indices in ctx->d_wfmatch.
+int run_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step, uint32_t& items_out) {
     EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
-    EPS_REQUIRE(ctx, E && grid_step && psi && n_levels >= 1, EPS_ERR_INVALID, "null argument / no levels");
+    EPS_REQUIRE(ctx, E && grid_step && n_levels >= 1, EPS_ERR_INVALID, "null argument / no levels");
     const uint64_t items64 = static_cast<uint64_t>(ctx->nC) * n_levels;
     EPS_REQUIRE(ctx, items64 < 65536ull * 16, EPS_ERR_INVALID, "too many (curve, level) pairs in one call");
     const uint32_t items = static_cast<uint32_t>(items64);
@@ -984,6 +989,21 @@ int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const do
         ctx->d_wfmatch.p, ctx->d_wfin.p, ctx->d_wfinexp.p, ctx->d_wfpsi.p);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches += 2;
+    items_out = items;
+    return EPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
+                      double* psi, uint32_t* match_index) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, psi, EPS_ERR_INVALID, "psi is null");
+    uint32_t items = 0;
+    if (int rc = run_wavefunctions(ctx, E, n_levels, grid_step, items)) return rc;
+    const size_t n_psi = static_cast<size_t>(items) * ctx->N;
     EPS_CUDA(ctx, cudaMemcpyAsync(psi, ctx->d_wfpsi.p, n_psi * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += n_psi * sizeof(double);
     if (match_index) {
@@ -994,6 +1014,22 @@ int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const do
     if (match_index)  // report the matching point as an index of the full r grid
         for (uint32_t it = 0; it < items; it++)
             if (match_index[it] != kNone) match_index[it] += ctx->curves[it / n_levels].i0;
+    return EPS_OK;
+}
+
+int eps_level_corrections(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step, double* dE) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, dE, EPS_ERR_INVALID, "dE is null");
+    uint32_t items = 0;
+    if (int rc = run_wavefunctions(ctx, E, n_levels, grid_step, items)) return rc;
+    EPS_CUDA(ctx, ctx->d_wfdE.reserve(items));
+    level_correction_kernel<<<items, kWfThreads, 0, ctx->stream>>>(ctx->d_F.p, ctx->d_curves.p, ctx->d_wfE.p, n_levels, ctx->N,
+                                                                  ctx->d_wfmatch.p, ctx->d_wfpsi.p, ctx->d_wfdE.p);
+    EPS_CUDA(ctx, cudaGetLastError());
+    ctx->stats.other_launches++;
+    EPS_CUDA(ctx, cudaMemcpyAsync(dE, ctx->d_wfdE.p, items * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += items * sizeof(double);
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EPS_OK;
 }
 

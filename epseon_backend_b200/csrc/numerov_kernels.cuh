@@ -1090,6 +1090,46 @@ wavefunction_finish_kernel(const CurveDev* __restrict__ curves, uint32_t n_lev, 
         dst[i] = (i >= i0 && i < i0 + n) ? __ddiv_rn(dst[i], nrm) : 0.0;
 }
 
+// A-posteriori energy correction of located levels (spec DESIGN.md section 3.8; oracle:
+// orc_level_correction): residual of the Numerov equation at the matching point times psi_m over
+// the B-norm of psi.  One CTA per (curve, level); reads the normalised psi the finish kernel left on
+// the full grid.  The B-norm is a tree reduction, so dE agrees with the oracle's serial sum to
+// rounding, not bit for bit.
+__global__ void __launch_bounds__(kWfThreads)
+level_correction_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves, const double* __restrict__ E,
+                        uint32_t n_lev, uint32_t n_points, const uint32_t* __restrict__ match,
+                        const double* __restrict__ psi, double* __restrict__ dE) {
+    __shared__ double red_d[kWfThreads / 32];
+    const uint32_t item = blockIdx.x, tid = threadIdx.x;
+    const CurveDev cv = curves[item / n_lev];
+    const uint32_t n = cv.n_steps, m = match[item];
+    if (m == kNone || m < 1 || m + 2 > n) {
+        if (tid == 0) dE[item] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const double* p = psi + static_cast<uint64_t>(item) * n_points + cv.i0;
+    double        D = 0.0;
+    for (uint32_t k = tid; k < n; k += kWfThreads) {
+        const double left = k > 0 ? p[k - 1] : 0.0, right = k + 1 < n ? p[k + 1] : 0.0;
+        D = __fma_rn(p[k], __fma_rn(10.0, p[k], __dadd_rn(left, right)), D);
+    }
+    for (int o = 16; o > 0; o >>= 1) D = __dadd_rn(D, __shfl_xor_sync(0xffffffffu, D, o));
+    if ((tid & 31) == 0) red_d[tid >> 5] = D;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kWfThreads / 32; w++) t = __dadd_rn(t, red_d[w]);
+        t = __ddiv_rn(t, 12.0);
+        const double* f  = F + cv.f_off;
+        const double  ep = __ddiv_rn(__dmul_rn(cv.s, E[item]), 12.0);
+        const double  f0 = __dadd_rn(f[m], ep), fl = __dadd_rn(f[m - 1], ep), fr = __dadd_rn(f[m + 1], ep);
+        const double  u0 = __dmul_rn(f0, p[m]), ul = __dmul_rn(fl, p[m - 1]), ur = __dmul_rn(fr, p[m + 1]);
+        const double  r  = __dsub_rn(__dsub_rn(__dsub_rn(ur, u0), __dsub_rn(u0, ul)),
+                                     __dmul_rn(__dsub_rn(1.0, __dmul_rn(12.0, f0)), p[m]));
+        dE[item] = -__ddiv_rn(__ddiv_rn(__dmul_rn(p[m], r), t), cv.s);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // DFMA-saturating probe: measures the FP64 (non-tensor) roofline denominator,
 // which MEASURED_PEAKS.json does not carry.  8 independent chains per thread.

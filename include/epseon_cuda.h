@@ -213,6 +213,15 @@ int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);
 int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
                       double* psi, uint32_t* match_index);
 
+/* ---- a-posteriori energy correction of located levels (the Cooley step of an
+ * outward/inward-matching search; additive).  For every E[n_curves][n_levels] (NaN rows give NaN) the
+ * matched outward/inward solution leaves a residual of the Numerov equation at the matching point;
+ * dE = -psi_m r_m / (psi^T B psi) / scale is the first-order correction of E (error quadratic in the
+ * energy error): |dE| is an error estimate of a located level, and E + dE polishes a level found
+ * with a loose tolerance.  dE[n_curves][n_levels] (host). */
+int eps_level_corrections(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
+                          double* dE);
+
 /* ---- page-locked host buffers (optional) ---------------------------------
  * Every entry point accepts ANY host pointer.  Tables and result arrays that live in memory
  * from eps_host_alloc are page-locked, so their host<->device copies run at the full PCIe rate

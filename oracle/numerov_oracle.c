@@ -424,6 +424,32 @@ int64_t orc_wavefunction(const double* F, uint32_t n_steps, double s, double E, 
     return m;
 }
 
+/* A-posteriori energy correction of a located level (Cooley's correction
+ * written as the Rayleigh quotient of the Numerov pencil).  On the window, with u_k = fp_k psi_k,
+ * fp_k = F_k + e/12 and psi_{-1} = psi_n = 0, the matched solution satisfies the Numerov equation
+ *     u_{k+1} - 2 u_k + u_{k-1} = (1 - 12 fp_k) psi_k
+ * at every k except the matching point m, where it leaves the residual r_m.  The pencil is
+ * (A + e B) psi = 0 with B = tridiag(1, 10, 1)/12, so to first order the eigenvalue is
+ *     e + de,   de = - psi_m r_m / D,   D = sum_k psi_k (psi_{k-1} + 10 psi_k + psi_{k+1}) / 12,
+ * and dE = de / s with an error quadratic in the energy error.  psi is the output of
+ * orc_wavefunction (window part), m its return value.  NaN when there is no matching point. */
+double orc_level_correction(const double* F, uint32_t n_steps, double s, double E, const double* psi,
+                            int64_t m) {
+    const uint32_t n = n_steps;
+    if (m < 1 || m > (int64_t)n - 2) return NAN;
+    const double ep = (s * E) / 12.0;
+    const double f0 = F[m] + ep, fl = F[m - 1] + ep, fr = F[m + 1] + ep;
+    const double u0 = f0 * psi[m], ul = fl * psi[m - 1], ur = fr * psi[m + 1];
+    const double r  = ((ur - u0) - (u0 - ul)) - (1.0 - 12.0 * f0) * psi[m];
+    double       D  = 0.0;
+    for (uint32_t k = 0; k < n; k++) {
+        const double left = k > 0 ? psi[k - 1] : 0.0, right = k + 1 < n ? psi[k + 1] : 0.0;
+        D = fma(psi[k], fma(10.0, psi[k], left + right), D);
+    }
+    D = D / 12.0;
+    return -((psi[m] * r) / D) / s;
+}
+
 /* N1 (tabulated sources).  Natural cubic spline through the knots (r_k, V_k), k = 0..K-1 (r strictly
  * increasing), resampled on r_i = rmin + i*h, h = (rmax - rmin)/(N - 1).  Fills the slot of
  * PotentialFileLoader::get_potential_data (potential_source.hpp:89-91) for ab initio tables on

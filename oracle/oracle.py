@@ -85,6 +85,8 @@ class Oracle:
         L.orc_spline_resample.restype = C.c_int
         L.orc_spline_resample.argtypes = [_f64p, _f64p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, _f64p]
         L.orc_centrifugal.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32, _f64p]
+        L.orc_level_correction.restype = C.c_double
+        L.orc_level_correction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, _f64p, C.c_int64]
         L.orc_wavefunction.restype = C.c_int64
         L.orc_wavefunction.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, _f64p]
 
@@ -169,6 +171,11 @@ class Oracle:
         psi = np.empty(AB.size, dtype=np.float64)
         m = self.lib.orc_wavefunction(AB, AB.size, s, float(E), float(h), psi)
         return psi, int(m)
+
+    def level_correction(self, AB, s, E, h):
+        """First-order energy correction dE of a trial level E (Rayleigh quotient of the Numerov pencil)."""
+        psi, m = self.wavefunction(AB, s, E, h)
+        return float(self.lib.orc_level_correction(AB, AB.size, float(s), float(E), psi, m))
 
     def spline_resample(self, r, V, rmin, rmax, N):
         """Natural cubic spline through (r, V) resampled on N uniform points of [rmin, rmax]."""
