@@ -64,6 +64,8 @@ struct eps_ctx {
     DevBuf<double>              d_F, d_V, d_scale, d_spl, d_Vraw, d_rot;
     DevBuf<uint32_t>            d_J;
     DevBuf<PrepOut>             d_prep;
+    DevBuf<PrepPart>            d_prep_parts;
+    int64_t                     opt_prep_parts = 0;  // 0 auto (chunked prep for few long curves), 1 never
     DevBuf<CurveDev>            d_curves;
     std::vector<eps_curve_info> curves;
 
@@ -483,9 +485,22 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
     EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
     EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
     EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
-    prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
-    EPS_CUDA(ctx, cudaGetLastError());
-    ctx->stats.other_launches++;
+    // few long curves: cut every curve into chunks (one CTA each) instead of one CTA per curve
+    const uint32_t parts = (N >= 65536 && n_curves <= 64) ? std::min<uint32_t>(kPrepPartsMax, (N + 8191) / 8192) : 1;
+    if (parts > 1 && ctx->opt_prep_parts != 1) {
+        EPS_CUDA(ctx, ctx->d_prep_parts.reserve(static_cast<size_t>(parts) * n_curves));
+        const dim3 grid(parts, n_curves);
+        prep_part_argmin_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, parts, ctx->d_prep_parts.p);
+        prep_part_window_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, parts, kTMax, ctx->d_prep_parts.p);
+        prep_part_finish_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, parts, ctx->d_prep_parts.p,
+                                                                       ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches += 3;
+    } else {
+        prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches++;
+    }
     std::vector<PrepOut> po(n_curves);
     EPS_CUDA(ctx, cudaMemcpyAsync(po.data(), ctx->d_prep.p, n_curves * sizeof(PrepOut), cudaMemcpyDeviceToHost, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -613,6 +628,7 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         ctx->d_V.release();
         ctx->d_scale.release();
         ctx->d_spl.release();
+        ctx->d_prep_parts.release();
         ctx->d_Vraw.release(); ctx->d_rot.release(); ctx->d_J.release();
         ctx->d_prep.release();
         ctx->d_curves.release();
@@ -1102,6 +1118,10 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
         case EPS_OPT_CBANK:
             EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "cbank: 0 auto, 1 always, 2 never");
             ctx->opt_cbank = value;
+            return EPS_OK;
+        case EPS_OPT_PREP_PARTS:
+            EPS_REQUIRE(ctx, value == 0 || value == 1, EPS_ERR_INVALID, "prep parts: 0 auto, 1 never");
+            ctx->opt_prep_parts = value;
             return EPS_OK;
         case EPS_OPT_CBANK_PDL:
             ctx->cb_pdl = value < 0 ? 0 : value > 18 ? 18 : static_cast<int>(value);

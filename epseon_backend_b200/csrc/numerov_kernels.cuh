@@ -888,8 +888,173 @@ prep_curves_kernel(const double* __restrict__ V, const double* __restrict__ scal
     for (uint64_t k = tid; k < slot; k += kPrepThreads)
         dst[k] = (k < n) ? __ddiv_rn(__dsub_rn(1.0, __dmul_rn(s, v[i0 + k])), 12.0) : 1.0 / 12.0;
     if (tid == 0) {
-        curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, v[m]};
-        out[c]    = PrepOut{i0, n, status, 0u, v[m], v[N - 1]};
+        const double vm = (m != kNone) ? v[m] : __longlong_as_double(0x7ff8000000000000LL);  // no finite value at all
+        curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, vm};
+        out[c]    = PrepOut{i0, n, status, 0u, vm, v[N - 1]};
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Preparation of a FEW LONG curves (C3: one curve of 10^6 points): prep_curves_kernel gives one CTA
+// per curve, i.e. one SM for the whole table (0.84 ms for 10^6 points).  The same three passes are
+// cut into `parts` contiguous chunks per curve, one CTA each, with the tiny cross-chunk reductions
+// redone by every CTA of the next pass (parts <= 128).  Same operations per element, same tie rules
+// (first minimum; window bounds as max / min of indices) => the same bits as prep_curves_kernel.
+// ---------------------------------------------------------------------------
+struct PrepPart {
+    double   q;         // chunk minimum of q = s V (+inf when the chunk is empty)
+    uint32_t idx, bad;  // its first index; non-finite value seen
+    uint32_t a, b;      // window partials: (last j < m above thr) + 1, first j > m above thr (N = none)
+    uint32_t pad[2];
+};
+
+constexpr uint32_t kPrepPartsMax = 128;
+
+__device__ __forceinline__ void prep_chunk(uint32_t N, uint32_t parts, uint32_t part, uint32_t& lo, uint32_t& hi) {
+    const uint32_t chunk = (N + parts - 1) / parts;
+    lo = min(N, part * chunk);
+    hi = min(N, lo + chunk);
+}
+
+// first argmin over the chunk partials of one curve (every thread computes the same value)
+__device__ __forceinline__ void prep_reduce_argmin(const PrepPart* __restrict__ pp, uint32_t parts, double& q, uint32_t& m,
+                                                   uint32_t& bad) {
+    q   = pp[0].q;
+    m   = pp[0].idx;
+    bad = pp[0].bad;
+    for (uint32_t k = 1; k < parts; k++) {
+        bad |= pp[k].bad;
+        if (pp[k].q < q || (pp[k].q == q && pp[k].idx < m)) {
+            q = pp[k].q;
+            m = pp[k].idx;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+prep_part_argmin_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint32_t parts,
+                        PrepPart* __restrict__ out) {
+    __shared__ double   red_q[kPrepThreads / 32];
+    __shared__ uint32_t red_i[kPrepThreads / 32], red_bad[kPrepThreads / 32];
+    const uint32_t c = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double*  v = V + static_cast<uint64_t>(c) * N;
+    const double   s = scale[c];
+    uint32_t       lo, hi;
+    prep_chunk(N, parts, part, lo, hi);
+    double   bq = __longlong_as_double(0x7ff0000000000000LL);
+    uint32_t bi = kNone, bad = 0;
+    for (uint32_t i = lo + tid; i < hi; i += kPrepThreads) {
+        const double vi = v[i];
+        if (!isfinite(vi)) bad = 1;
+        const double q = __dmul_rn(s, vi);
+        if (q < bq) {
+            bq = q;
+            bi = i;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double   oq = __shfl_xor_sync(0xffffffffu, bq, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        if (oq < bq || (oq == bq && oi < bi)) {
+            bq = oq;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        red_q[warp]   = bq;
+        red_i[warp]   = bi;
+        red_bad[warp] = bad;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double   q = red_q[0];
+        uint32_t i = red_i[0], b = red_bad[0];
+        for (int w = 1; w < kPrepThreads / 32; w++) {
+            b |= red_bad[w];
+            if (red_q[w] < q || (red_q[w] == q && red_i[w] < i)) {
+                q = red_q[w];
+                i = red_i[w];
+            }
+        }
+        PrepPart& o = out[static_cast<uint64_t>(c) * parts + part];
+        o.q   = q;
+        o.idx = i;
+        o.bad = b;
+    }
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+prep_part_window_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint32_t parts,
+                        double t_max, PrepPart* __restrict__ pp_all) {
+    __shared__ uint32_t red_a[kPrepThreads / 32], red_b[kPrepThreads / 32];
+    const uint32_t c = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double*  v  = V + static_cast<uint64_t>(c) * N;
+    const double   s  = scale[c];
+    PrepPart*      pp = pp_all + static_cast<uint64_t>(c) * parts;
+    double         qmin;
+    uint32_t       m, bad;
+    prep_reduce_argmin(pp, parts, qmin, m, bad);
+    const double thr = __dadd_rn(qmin, t_max);
+    uint32_t     lo, hi;
+    prep_chunk(N, parts, part, lo, hi);
+    uint32_t a = 0, b = N;
+    for (uint32_t i = lo + tid; i < hi; i += kPrepThreads) {
+        const double q = __dmul_rn(s, v[i]);
+        if (q > thr) {
+            if (i < m) a = max(a, i + 1);
+            else if (i > m) b = min(b, i);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) {
+        red_a[warp] = a;
+        red_b[warp] = b;
+    }
+    __syncthreads();  // (also orders every thread's reads of pp[].q/idx before the writes below: disjoint fields)
+    if (tid == 0) {
+        uint32_t aa = 0, bb = N;
+        for (int w = 0; w < kPrepThreads / 32; w++) {
+            aa = max(aa, red_a[w]);
+            bb = min(bb, red_b[w]);
+        }
+        pp[part].a = aa;
+        pp[part].b = bb;
+    }
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+prep_part_finish_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint64_t slot,
+                        uint32_t parts, const PrepPart* __restrict__ pp_all, double* __restrict__ F,
+                        CurveDev* __restrict__ curves, PrepOut* __restrict__ out) {
+    const uint32_t  c = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const double*   v  = V + static_cast<uint64_t>(c) * N;
+    const double    s  = scale[c];
+    const PrepPart* pp = pp_all + static_cast<uint64_t>(c) * parts;
+    double          qmin;
+    uint32_t        m, bad;
+    prep_reduce_argmin(pp, parts, qmin, m, bad);
+    uint32_t aa = 0, bb = N;
+    for (uint32_t k = 0; k < parts; k++) {
+        aa = max(aa, pp[k].a);
+        bb = min(bb, pp[k].b);
+    }
+    const uint32_t ilo = aa, ihi = bb == N ? N - 1 : bb - 1;
+    const uint32_t i0   = ilo < 1 ? 1 : ilo;
+    const uint32_t iend = (ihi + 1 < N - 1) ? ihi + 1 : N - 1;
+    const uint32_t status = bad ? 1u : (iend >= i0 + 2 ? 0u : 2u);
+    const uint32_t n      = status ? 0u : iend - i0;
+    const uint64_t chunk = (slot + parts - 1) / parts, k_lo = min(slot, part * chunk), k_hi = min(slot, k_lo + chunk);
+    double*        dst = F + static_cast<uint64_t>(c) * slot;
+    for (uint64_t k = k_lo + tid; k < k_hi; k += kPrepThreads)
+        dst[k] = (k < n) ? __ddiv_rn(__dsub_rn(1.0, __dmul_rn(s, v[i0 + k])), 12.0) : 1.0 / 12.0;
+    if (part == 0 && tid == 0) {
+        const double vm = (m != kNone) ? v[m] : __longlong_as_double(0x7ff8000000000000LL);
+        curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, vm};
+        out[c]    = PrepOut{i0, n, status, 0u, vm, v[N - 1]};
     }
 }
 

@@ -196,8 +196,12 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  * EPS_OPT_CBANK: sweeps over ONE resident curve can feed the coefficient table through the
  *   kernel-parameter constant bank (uniform-register operand, chunked launches) instead of the
  *   TMA / shared-memory ring; identical results.  0 = automatic (large sweeps), 1 = whenever
- *   the launch qualifies, 2 = never.  EPS_OPT_CBANK_SHAPE: tuning knob. */
-enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5 };
+ *   the launch qualifies, 2 = never.  EPS_OPT_CBANK_SHAPE, EPS_OPT_CBANK_PDL: tuning knobs.
+ * EPS_OPT_PREP_PARTS: eps_set_potentials* prepares few long curves (<= 64 curves of >= 65 536
+ *   points) with every curve cut into chunks over many CTAs; 0 = automatic, 1 = never (one CTA
+ *   per curve).  Identical results. */
+enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5,
+       EPS_OPT_PREP_PARTS = 6 };
 enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2, EPS_CNT_CBANK_LAUNCHES = 3 };
 int eps_set_option(eps_ctx* ctx, int option, int64_t value);
 int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);

@@ -197,3 +197,60 @@ def test_device_prep_ties_and_plateaus(oracle, gpu_ctx):
     s = W.scale(15.0, 15.0, 4.0 / 5000)
     E = np.linspace(10.0, 3900.0, 300)
     _check_sweep(oracle, gpu_ctx, V, s, E)
+
+
+@pytest.mark.parametrize("N", [65536, 65537, 100_000, 262_145, 1_000_000])
+def test_chunked_prep_of_long_curves(oracle, gpu_ctx, N):
+    """Few long curves are prepared with every curve cut into chunks over many CTAs
+    (EPS_OPT_PREP_PARTS): window, table and sweeps identical to the one-CTA-per-curve kernel and to
+    the oracle; first-minimum tie rule kept across chunk boundaries."""
+    rmin, rmax = 0.2, 12.0
+    h = W.grid_h(rmin, rmax, N)
+    V = np.stack([W.morse(W.H2["De"], W.H2["re"], W.H2["a"], rmin, rmax, N),
+                  W.lj(30000.0, 1.1, rmin, rmax, N)])
+    # a flat bottom straddling chunk boundaries: many equal minima, the first index must win
+    k = int(np.argmin(V[1]))
+    V[1][k - 9000:k + 9000] = V[1][k]
+    s = W.scale(W.H2["m0"], W.H2["m1"], h)
+    info, nodes = [], []
+    for mode in (0, 1):
+        gpu_ctx.set_option(gpu_ctx.OPT_PREP_PARTS, mode)
+        gpu_ctx.set_potentials(V, s)
+        info.append([(ci.i0, ci.n_steps, ci.v_min, ci.v_last) for ci in (gpu_ctx.curve_info(0), gpu_ctx.curve_info(1))])
+        lo = np.array([c[2] for c in info[-1]])
+        n, m, x = gpu_ctx.sweep_uniform(lo, lo + 0.4 / s, 96)
+        nodes.append((n, m, x))
+    gpu_ctx.set_option(gpu_ctx.OPT_PREP_PARTS, 0)
+    assert info[0] == info[1]
+    assert np.array_equal(nodes[0][0], nodes[1][0]) and _same_bits(nodes[0][1], nodes[1][1]) and np.array_equal(nodes[0][2], nodes[1][2])
+    for c in range(2):
+        F, i0, nst, vmin = oracle.prep(V[c], s)
+        assert info[0][c][:3] == (i0, nst, vmin)
+        dE = (0.4 / s) / 95
+        n_o, m_o, x_o = oracle.sweep_uniform(F, s, vmin, dE, 0, 96)
+        assert np.array_equal(nodes[0][0][c], n_o) and _same_bits(nodes[0][1][c], m_o) and np.array_equal(nodes[0][2][c], x_o)
+
+
+def test_chunked_prep_rejects_bad_tables(gpu_ctx):
+    from epseon_backend_b200.cabi import EpsError
+
+    N = 200_000
+    V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, N)
+    s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, N))
+    for poison in (np.nan, np.inf):
+        bad = V.copy()
+        bad[150_001] = poison
+        with pytest.raises(EpsError) as ei:
+            gpu_ctx.set_potentials(bad, s)
+        assert ei.value.code == 3
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.set_potentials(np.full(N, np.nan), s)  # nothing finite at all
+    assert ei.value.code == 3
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.set_potentials(np.full(3000, np.inf), s)  # same through the one-CTA kernel
+    assert ei.value.code == 3
+    spike = np.full(N, 1e12)
+    spike[77_777] = 0.0
+    with pytest.raises(EpsError) as ei:
+        gpu_ctx.set_potentials(spike, 1.0)
+    assert ei.value.code == 3
