@@ -334,3 +334,20 @@ def test_potential_tables_through_python_api(gpu_mod, oracle):
         F, _, _, vmin = oracle.prep(V[c], s)
         ref, *_ = oracle.solve_levels(F, s, vmin, V[c][-1] - 1.0, 1024, 0, 6, 256, 1e-12, 16)
         assert np.array_equal(levels[c].view(np.uint64), ref.view(np.uint64)), c
+
+
+@pytest.mark.gpu
+def test_concurrent_tasks_on_one_device(gpu_mod):
+    """The reference documents concurrent tasks on one device as unsupported
+    (python/epseon_backend/device/gpu/_libepseon_gpu.pyi:156-158).  Here every task owns its worker
+    thread, CUDA stream and device buffers, so tasks submitted together all finish with the same bits."""
+    interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
+    handles = [interface.submit_task(_configure_task(gpu_mod, interface.get_task_configurator("float64"), max_level=9))
+               for _ in range(4)]
+    for h in handles:
+        h.wait()
+        assert h.is_done() and not h.has_failed(), h.get_status_message()
+    ref = np.array(handles[0].get_levels())
+    assert np.all(np.isfinite(ref))
+    for h in handles[1:]:
+        assert np.array_equal(np.array(h.get_levels()).view(np.uint64), ref.view(np.uint64))
