@@ -13,6 +13,9 @@
 // contracts or re-associates, so node counts AND tails are bit-identical to
 // the oracle.
 #pragma once
+#ifndef EPS_STEP_NEGATED
+#define EPS_STEP_NEGATED 1
+#endif
 #include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -127,12 +130,25 @@ struct Chain {
 
 // One step of the 4-operation X form (1 DADD, 1 DMUL, 2 DFMA = 6 FLOP):
 //   fp = F_k + e/12;  Q = fma(10, X, S);  X' = fma(-fp, Q, X);  S' = fp * X.
+// The ORDER OF THE STATEMENTS matters to ptxas, not to the arithmetic.  A DFMA with three distinct
+// register operands holds the FP64 pipe for 3 cycles instead of 2 (one 64-bit register read per
+// cycle; scripts/microbench3.cu) unless one operand comes from the operand reuse cache, i.e. was
+// read in the same operand slot by the warp's previous instruction.  ptxas orders the operands of
+// commutative instructions by the age of their virtual registers: with Q defined BEFORE fp the
+// pair becomes  DMUL S', X, fp.reuse ; DFMA X', Q, fp, X  -- fp in slot B of both -- and the DFMA
+// reads two registers (profiles/r1_microbench4_order.log; SASS check: scripts/sass_reuse.py).
 __device__ __forceinline__ void numerov_step(Chain& c, const double Fk, const double ep) {
-    const double fp = __dadd_rn(Fk, ep);
     const double Q  = __fma_rn(10.0, c.X, c.S);
-    const double Xn = __fma_rn(-fp, Q, c.X);
-    c.S = __dmul_rn(fp, c.X);
-    c.X = Xn;
+#if EPS_STEP_NEGATED
+    const double fn = __dsub_rn(-Fk, ep);  // -(F_k + e/12): round-to-nearest is sign-symmetric, same bits
+    const double Sn = -__dmul_rn(fn, c.X);
+    c.X = __fma_rn(fn, Q, c.X);
+#else
+    const double fp = __dadd_rn(Fk, ep);
+    const double Sn = __dmul_rn(fp, c.X);
+    c.X = __fma_rn(-fp, Q, c.X);
+#endif
+    c.S = Sn;
 }
 
 // Scale (X, S) by the power of two that brings |X| into [1,2); exact.
@@ -317,15 +333,25 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
                 for (int p = 0; p < 16; p++) {
                     const double2 ff = t2[p];  // two consecutive grid steps, warp-broadcast
+                    if (kScan) {  // the two basis chains share fp: both steps of a chain back to back
+#pragma unroll              // (30 instead of 3 of the 83 three-register DFMAs then take fp from the reuse cache)
+                        for (int i = 0; i < kEpt; i++) {
+                            numerov_step(c[i], ff.x, ep[0]);
+                            if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                            numerov_step(c[i], ff.y, ep[0]);
+                            if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < kEpt; i++) {
-                        numerov_step(c[i], ff.x, ep[kScan ? 0 : i]);
-                        if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
-                    }
+                        for (int i = kEpt - 1; i >= 0; i--) {
+                            numerov_step(c[i], ff.x, ep[i]);
+                            if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        }
 #pragma unroll
-                    for (int i = 0; i < kEpt; i++) {
-                        numerov_step(c[i], ff.y, ep[kScan ? 0 : i]);
-                        if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        for (int i = 0; i < kEpt; i++) {
+                            numerov_step(c[i], ff.y, ep[i]);
+                            if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
+                        }
                     }
                     if (kStride == 8 && (p & 3) == 3) {
 #pragma unroll
