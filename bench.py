@@ -60,9 +60,9 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1
 #       carries the per-energy state (28 B read + 28 B written per energy) through HBM by design:
 #       881 MB per chunk launch at 2^24 energies = 58 GB/s, under 1 % of the HBM peak.
 KERNEL_META = {
-    "c2": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=32> (TMA ring, flat refinement rows)", 826_112, "profiles/r1c_ncu.md"),
+    "c2": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)", 826_112, "profiles/r1c_ncu.md"),
     "c3": ("eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)", 8_028_416, "profiles/r1c_scan_ncu.md"),
-    "c4": ("eps::numerov_sweep_kernel<EPT=2,WARPS=8,STRIDE=8> (TMA ring, packed refinement rows)", 346_653_184,
+    "c4": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)", 346_653_184,
            "profiles/r1e_c4_ncu.md (1-GPU shape: 4096 curves per launch)"),
     "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", 51 * 881_415_680,
            "profiles/r1e_c5_cbank_ncu.md (1-GPU shape: 51 chunk launches x 881 MB of per-energy state carry)"),

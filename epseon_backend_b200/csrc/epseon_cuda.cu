@@ -203,14 +203,15 @@ cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, u
     return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails, out, pack_log2);
 }
 
-// CTA shape (energies per thread, consumer warps).  Register-file bandwidth is the binding
-// resource of the FP64 pipe on B200 (scripts/microbench.cu), so more chains per thread amortise
-// the F-table loads; rows too short to fill such CTAs fall back to smaller shapes.
+// CTA shape (energies per thread, consumer warps).  512 energies per CTA as 4 chains x 4 warps:
+// with four chains per thread ptxas feeds 65 % of the three-register DFMAs from the operand reuse
+// cache (50 % with two), measured 0.93 against 0.89 of the FP64 pipe on many-wave sweeps and a tie
+// on one wave (profiles/r1_quick3_shapes.log); rows too short to fill such CTAs use 256-energy CTAs.
 struct Shape { int ept, warps; };
 Shape pick_shape(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE) {
     if (ctx->force_ept) return Shape{ctx->force_ept, ctx->force_warps ? ctx->force_warps : 8};
     (void)n_jobs;
-    return nE > 256u ? Shape{2, 8} : Shape{1, 8};
+    return nE > 256u ? Shape{4, 4} : Shape{2, 4};
 }
 
 // Sign-sampling stride from theta_max^2 = 12 * t_max, t_max = max over rows of s*(E_max - V_min):
@@ -233,7 +234,7 @@ uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows) {
 
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                               bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0) {
-    if (pack_log2) return launch_sweep_s<2, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
+    if (pack_log2) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     const Shape sh = pick_shape(ctx, n_jobs, nE);
     if (sh.ept == 4 && sh.warps == 4) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
     if (sh.ept == 4) return launch_sweep_s<4, 8>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
