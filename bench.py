@@ -52,18 +52,18 @@ CPU_SAMPLE_SECONDS = 10.0  # bounded CPU sample of the same workload (cpu_baseli
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 
 # dominant kernel per workload + its DRAM traffic per launch from the committed `ncu --set full`
-# captures (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1c_ncu.md, r1c_scan_ncu.md,
-# r1e_c4_ncu.md, r1e_c5_cbank_ncu.md).  Algorithmic bytes = every resident curve's coefficient table
+# captures (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1g_ncu.md, r1c_scan_ncu.md,
+# r1g_c4_ncu.md, r1e_c5_cbank_ncu.md).  Algorithmic bytes = every resident curve's coefficient table
 # once per launch (8 B x grid steps x curves).
 #   c4: one launch streams the tables of all 4096 curves (measured on the 1-GPU shape).
 #   c5: a "launch" of the bench is one sweep = 51 chunk launches of the constant-bank kernel; each
 #       carries the per-energy state (28 B read + 28 B written per energy) through HBM by design:
 #       881 MB per chunk launch at 2^24 energies = 58 GB/s, under 1 % of the HBM peak.
 KERNEL_META = {
-    "c2": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)", 826_112, "profiles/r1c_ncu.md"),
+    "c2": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)", 839_936, "profiles/r1g_ncu.md"),
     "c3": ("eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)", 8_028_416, "profiles/r1c_scan_ncu.md"),
-    "c4": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)", 346_653_184,
-           "profiles/r1e_c4_ncu.md (1-GPU shape: 4096 curves per launch)"),
+    "c4": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)", 348_472_832,
+           "profiles/r1g_c4_ncu.md (1-GPU shape: 4096 curves per launch)"),
     "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", 51 * 881_415_680,
            "profiles/r1e_c5_cbank_ncu.md (1-GPU shape: 51 chunk launches x 881 MB of per-energy state carry)"),
 }
