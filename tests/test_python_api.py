@@ -7,6 +7,7 @@ the ``format`` helper and ``_libepseon_cpu.greet``.
 """
 import gc
 import re
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -14,6 +15,7 @@ import pytest
 from tests import workloads as W
 
 COMPUTE_GROUP_AXES_COUNT = 3
+ROOT = Path(__file__).resolve().parent.parent
 
 REFERENCE_CLASSES = {
     "EpseonComputeContext", "ComputeDeviceInterface", "TaskConfiguratorFloat32", "TaskConfiguratorFloat64",
@@ -351,3 +353,15 @@ def test_concurrent_tasks_on_one_device(gpu_mod):
     assert np.all(np.isfinite(ref))
     for h in handles[1:]:
         assert np.array_equal(np.array(h.get_levels()).view(np.uint64), ref.view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_example_script_runs():
+    """examples/morse_levels.py: the reference example's call sequence plus the additive accessors."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, str(ROOT / "examples" / "morse_levels.py")], capture_output=True, text=True,
+                       cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert "curve 1 J=1" in r.stdout and "rotational constant" in r.stdout
