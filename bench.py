@@ -70,7 +70,7 @@ KERNEL_META = {
 
 C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
 C3 = dict(N=1_000_000, nE=4096)
-C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=64, rel_tol=1e-10, max_rounds=8, v_max=7)
+C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=32, rel_tol=1e-10, max_rounds=8, v_max=7)
 C5 = dict(N=200_000, nE=1 << 24)
 
 

@@ -226,14 +226,15 @@ int pick_stride(const eps_ctx* ctx, double t_max) {
 
 // Rows-per-CTA packing of short rows (2^g rows of nE <= 512 >> g energies in one 512-energy CTA);
 // only for callers that lay their rows out [curve][level padded to 2^g] (pack_rows > 1).
-uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows) {
+uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows, uint32_t per_cta = 512) {
     uint32_t g = 0;
-    while ((2u << g) <= pack_rows && (512u >> (g + 1)) >= nE) g++;
+    while ((2u << g) <= pack_rows && (per_cta >> (g + 1)) >= nE) g++;
     return g;
 }
 
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                              bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0) {
+                              bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0, uint32_t pack_cta = 512) {
+    if (pack_log2 && pack_cta == 256) return launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     if (pack_log2) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     const Shape sh = pick_shape(ctx, n_jobs, nE);
     if (sh.ept == 4 && sh.warps == 4) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, 0);
@@ -319,9 +320,9 @@ int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
 // Constant-bank kernel policy: measured on the C2 table (profiles/r1_cbank.log) it overtakes the TMA
 // kernel once a launch carries >= ~2 CTAs of 512 energies per SM (+1 % at 151 552 energies, +5 % at
 // 303 104, +9 % at 2^20); below that the per-chunk launch overhead (26 launches per 100k steps) loses.
-bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_rows) {
+bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_rows, uint32_t pack_cta) {
     if (ctx->opt_cbank == 2 || ctx->nC != 1 || ctx->force_ept) return false;
-    if (pack_rows != kFlatRows && pack_log2_for(nE, pack_rows) != 0) return false;  // (flat rows: cbank uses per-row CTAs instead)
+    if (pack_rows != kFlatRows && pack_log2_for(nE, pack_rows, pack_cta) != 0) return false;  // (flat rows: cbank uses per-row CTAs instead)
     if (ctx->opt_cbank == 1) return true;
     return static_cast<uint64_t>(n_jobs) * nE >= 2ull * 512 * ctx->sm_count;
 }
@@ -409,7 +410,8 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
 // t_max = max over the rows of s * (E_max - V_min) (see pick_stride).  fix_flagged: on the scan
 // path, recompute ill-conditioned energies with the sequential kernel (one host sync).
 int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
-                 bool tails, double t_max, bool fix_flagged = true, uint32_t n_rows_active = 0, uint32_t pack_rows = 1) {
+                 bool tails, double t_max, bool fix_flagged = true, uint32_t n_rows_active = 0, uint32_t pack_rows = 1,
+                 uint32_t pack_cta = 512) {
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
     if (tails) {
@@ -437,11 +439,11 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     const SweepOut out{ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p};
     if (n_seg >= 2) {
         if (int rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out)) return rc;
-    } else if (use_cbank(ctx, n_jobs, nE, pack_rows)) {
+    } else if (use_cbank(ctx, n_jobs, nE, pack_rows, pack_cta)) {
         if (int rc = launch_cbank(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out)) return rc;
     } else {
-        const uint32_t pk = ctx->force_ept ? 0 : pack_rows == kFlatRows ? kFlatRows : pack_log2_for(nE, pack_rows);
-        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out, pk));
+        const uint32_t pk = ctx->force_ept ? 0 : pack_rows == kFlatRows ? kFlatRows : pack_log2_for(nE, pack_rows, pack_cta);
+        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out, pk, pack_cta));
     }
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
     ctx->stats.sweep_launches++;
@@ -882,8 +884,13 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     // One curve resident: the active brackets are compacted into rows that are swept with the
     // flat-row mapping (full CTAs).  Several curves: dense rows [curve][level padded to the CTA
     // packing] so that the 2^g short rows packed into a CTA share a curve.
+    // CTAs of 256 instead of 512 energies when the rows of one curve (nlev x M energies) would leave
+    // half of a 512-energy CTA idle: a round then costs half as much, so fewer points per level per
+    // round (less total work for the same final width) pay off on many-curve batches.
     const bool     flat      = nC == 1 && !ctx->force_ept;
-    const uint32_t pack_rows = flat ? kFlatRows : 1u << pack_log2_for(M, 512);
+    const uint32_t rows512   = 1u << pack_log2_for(M, 512, 512);
+    const uint32_t pack_cta  = (!flat && M <= 128 && nlev <= rows512 / 2) ? 256u : 512u;
+    const uint32_t pack_rows = flat ? kFlatRows : 1u << pack_log2_for(M, 512, pack_cta);
     const uint32_t nlev_pad  = flat ? nlev : (nlev + pack_rows - 1) / pack_rows * pack_rows;
     const uint32_t n_dense   = nC * nlev_pad;
     EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_dense));
@@ -905,7 +912,9 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         const uint32_t n_active = ctx->h_pinned[0];
         if (n_active == 0) break;
         const uint32_t n_rows = flat ? n_active : n_dense;
-        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows)) return rc;
+        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows,
+                                  pack_cta))
+            return rc;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_rows * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;
         crossing_kernel<<<bpr * n_rows, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);

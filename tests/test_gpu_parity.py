@@ -254,3 +254,22 @@ def test_chunked_prep_rejects_bad_tables(gpu_ctx):
     with pytest.raises(EpsError) as ei:
         gpu_ctx.set_potentials(spike, 1.0)
     assert ei.value.code == 3
+
+
+@pytest.mark.parametrize("nlev,M", [(8, 32), (8, 16), (3, 64), (5, 8), (2, 128), (16, 16), (8, 64)])
+def test_packed_rows_in_small_ctas(oracle, gpu_ctx, nlev, M):
+    """Many-curve refinement with few points per level: rows are packed into 256-energy CTAs when
+    they would leave half of a 512-energy CTA idle ((8, 64) is the 512-energy control).  Levels and
+    widths bit-identical to the oracle for every curve."""
+    n = 3000
+    rng = np.random.default_rng(nlev * 100 + M)
+    V = np.stack([W.morse(5500.0 * (1 + 0.04 * rng.random()), 2.2, 1.6, 0.4, 10.0, n) if c % 2 == 0
+                  else W.lj(5200.0 * (1 + 0.04 * rng.random()), 2.3, 0.4, 10.0, n) for c in range(5)])
+    s = W.scale(20.0, 20.0, W.grid_h(0.4, 10.0, n))
+    gpu_ctx.set_potentials(V, s)
+    lo, hi = V.min(axis=1), V[:, -1] - 1.0
+    lev_g, wid_g, nb_g = gpu_ctx.solve_levels(lo, hi, 700, 1, nlev, M, 1e-11, 12)
+    for c in range(5):
+        F, *_ = oracle.prep(V[c], s)
+        lev_o, wid_o, nb_o, *_ = oracle.solve_levels(F, s, lo[c], hi[c], 700, 1, nlev, M, 1e-11, 12)
+        assert _same_bits(lev_g[c], lev_o) and _same_bits(wid_g[c], wid_o) and nb_g[c] == nb_o, (c, nlev, M)
