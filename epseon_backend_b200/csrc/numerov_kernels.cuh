@@ -171,9 +171,10 @@ __device__ __forceinline__ void renorm(Chain& c, int& expo) {
 // Energy j of a CTA's chunk sits in thread (j % (32 kWarps)), chain (j / (32 kWarps)), so the
 // result stores of every chain are coalesced.
 //
-// Node counting.  The FP64 pipe shares register-file bandwidth with every other
-// instruction (measured: one integer SHF per step costs 16 % of the DFMA rate),
-// so the sign of X is sampled every kStride steps.  That is EXACTLY the per-step
+// Node counting.  An integer SHF per step between the FP64 instructions costs 16 % of the
+// DFMA rate (it takes issue cycles, and it separates the DMUL/DFMA pairs that share an
+// operand through the reuse cache, see numerov_step), so the sign of X is sampled every
+// kStride steps.  That is EXACTLY the per-step
 // sign-flip count of the spec whenever two zeros of a solution are more than
 // kStride steps apart, which Sturm separation guarantees for
 //     kStride * theta_max < pi,   theta_max^2 = 12 * s * (E_max - V_min);
