@@ -57,30 +57,35 @@ def replay(F, s, E):
     return nodes, float(man * 2), int(ex - 1)  # mantissa in [1,2)
 
 
-cases = []
-specs = [
-    dict(name="h2_morse_N2000", V=W.morse(38267.0, 0.7414, 1.9426, 0.2, 6.0, 2000),
-         s=W.scale(1.00783, 1.00783, W.grid_h(0.2, 6.0, 2000)),
-         E=[10.0, 2166.0, 2200.0, 6309.0, 6400.0, 13839.5, 20000.0, 30000.0, 36000.0, 38000.0, 38266.0]),
-    dict(name="sr2_fixture_N1500", V=W.morse(5500.0, 0.6, 10.0, 0.0, 10.0, 1500),
-         s=W.scale(87.62, 87.62, W.grid_h(0.0, 10.0, 1500)),
-         E=[1.0, 300.0, 1000.0, 2500.0, 4000.0, 5400.0]),
-    dict(name="lj_N1300", V=W.lj(800.0, 3.0, 2.2, 12.0, 1300),
-         s=W.scale(40.0, 40.0, W.grid_h(2.2, 12.0, 1300)),
-         E=[5.0, 100.0, 400.0, 700.0, 790.0]),
-]
-for sp in specs:
-    F, i0, n = prep(sp["V"], sp["s"])
-    rows = []
-    for E in sp["E"]:
-        nodes, man, ex = replay(F, sp["s"], E)
-        rows.append(dict(E=float(E).hex(), nodes=nodes, tail_mant=man.hex(), tail_exp=ex))
-        print(sp["name"], E, nodes, man, ex, flush=True)
-    cases.append(dict(name=sp["name"], s=float(sp["s"]).hex(), i0=i0, n_steps=n,
-                      V=[float(v).hex() for v in sp["V"]], rows=rows))
+def main():
+    cases = []
+    specs = [
+        dict(name="h2_morse_N2000", V=W.morse(38267.0, 0.7414, 1.9426, 0.2, 6.0, 2000),
+             s=W.scale(1.00783, 1.00783, W.grid_h(0.2, 6.0, 2000)),
+             E=[10.0, 2166.0, 2200.0, 6309.0, 6400.0, 13839.5, 20000.0, 30000.0, 36000.0, 38000.0, 38266.0]),
+        dict(name="sr2_fixture_N1500", V=W.morse(5500.0, 0.6, 10.0, 0.0, 10.0, 1500),
+             s=W.scale(87.62, 87.62, W.grid_h(0.0, 10.0, 1500)),
+             E=[1.0, 300.0, 1000.0, 2500.0, 4000.0, 5400.0]),
+        dict(name="lj_N1300", V=W.lj(800.0, 3.0, 2.2, 12.0, 1300),
+             s=W.scale(40.0, 40.0, W.grid_h(2.2, 12.0, 1300)),
+             E=[5.0, 100.0, 400.0, 700.0, 790.0]),
+    ]
+    for sp in specs:
+        F, i0, n = prep(sp["V"], sp["s"])
+        rows = []
+        for E in sp["E"]:
+            nodes, man, ex = replay(F, sp["s"], E)
+            rows.append(dict(E=float(E).hex(), nodes=nodes, tail_mant=man.hex(), tail_exp=ex))
+            print(sp["name"], E, nodes, man, ex, flush=True)
+        cases.append(dict(name=sp["name"], s=float(sp["s"]).hex(), i0=i0, n_steps=n,
+                          V=[float(v).hex() for v in sp["V"]], rows=rows))
 
-exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
-out = dict(comment="mpmath 60-digit replay of the Numerov recurrence; see make_golden.py",
-           cases=cases, morse_c1_levels=[float(x) for x in exact])
-Path(__file__).with_name("numerov_mpmath.json").write_text(json.dumps(out))
-print("wrote", Path(__file__).with_name("numerov_mpmath.json"))
+    exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+    out = dict(comment="mpmath 60-digit replay of the Numerov recurrence; see make_golden.py",
+               cases=cases, morse_c1_levels=[float(x) for x in exact])
+    Path(__file__).with_name("numerov_mpmath.json").write_text(json.dumps(out))
+    print("wrote", Path(__file__).with_name("numerov_mpmath.json"))
+
+
+if __name__ == "__main__":  # prep / replay are also imported by make_golden_rot.py
+    main()

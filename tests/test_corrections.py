@@ -73,3 +73,37 @@ def test_gpu_level_corrections_batch_after_solve(oracle, gpu_ctx):
     lev, wid, nb = gpu_ctx.solve_levels(V.min(axis=1), V[:, -1] - 1.0, 1024, 0, 9, 64, 1e-12, 10)
     dE = gpu_ctx.level_corrections(lev, h)
     assert dE.shape == lev.shape and np.all(np.abs(dE) < 1e-9 * np.abs(lev))
+
+
+# --------------------------------------------------------------------------- committed golden vectors
+
+import json  # noqa: E402
+from pathlib import Path  # noqa: E402
+
+GOLD_ROT = json.loads((Path(__file__).parent / "golden" / "rotation_mpmath.json").read_text())
+
+
+@pytest.mark.parametrize("case", GOLD_ROT["corrections"], ids=lambda c: c["name"])
+def test_mpmath_golden_corrections(oracle, case):
+    """dE from a 60-digit evaluation of the matched solution and the Rayleigh quotient
+    (tests/golden/make_golden_rot.py), for trial energies 0.05 .. 0.4 cm^-1 off a level."""
+    V = np.array([float.fromhex(v) for v in case["V"]])
+    s, h = float.fromhex(case["s"]), float.fromhex(case["h"])
+    F, *_ = oracle.prep(V, s)
+    for r in case["rows"]:
+        E, ref = float.fromhex(r["E"]), float.fromhex(r["dE"])
+        psi, m = oracle.wavefunction(F, s, E, h)
+        assert m == r["m"]
+        assert oracle.level_correction(F, s, E, h) == pytest.approx(ref, rel=1e-7, abs=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD_ROT["corrections"], ids=lambda c: c["name"])
+def test_gpu_against_golden_corrections(gpu_ctx, case):
+    V = np.array([float.fromhex(v) for v in case["V"]])
+    s, h = float.fromhex(case["s"]), float.fromhex(case["h"])
+    gpu_ctx.set_potentials(V, s)
+    E = np.array([float.fromhex(r["E"]) for r in case["rows"]])
+    dE = gpu_ctx.level_corrections(E[None, :], h)[0]
+    for k, r in enumerate(case["rows"]):
+        assert dE[k] == pytest.approx(float.fromhex(r["dE"]), rel=1e-7, abs=1e-8 * abs(E[k]))

@@ -172,3 +172,46 @@ def test_gpu_rot_origin_wall_and_errors(oracle, gpu_ctx):
     with pytest.raises(cabi.EpsError) as e:
         gpu_ctx.set_potentials_rot(V, s, 0.0, h, [1 << 26])
     assert e.value.code == 1
+
+
+# --------------------------------------------------------------------------- committed golden vectors
+
+import json  # noqa: E402
+from pathlib import Path  # noqa: E402
+
+GOLD_ROT = json.loads((Path(__file__).parent / "golden" / "rotation_mpmath.json").read_text())
+
+
+@pytest.mark.parametrize("case", GOLD_ROT["rotation"], ids=lambda c: c["name"])
+def test_mpmath_golden_rotating_curves(oracle, case):
+    """tests/golden/rotation_mpmath.json (make_golden_rot.py): V_J from an independent numpy statement,
+    node counts from a 60-digit replay of the recurrence on it."""
+    V = np.array([float.fromhex(v) for v in case["V"]])
+    s, h = float.fromhex(case["s"]), float.fromhex(case["h"])
+    VJ = oracle.centrifugal(V, s, case["rmin"], h, case["J"])
+    assert VJ[0] == float.fromhex(case["VJ_first"]) and VJ[V.size // 2] == float.fromhex(case["VJ_mid"])
+    F, i0, n, _ = oracle.prep(VJ, s)
+    assert (i0, n) == (case["i0"], case["n_steps"])
+    E = np.array([float.fromhex(r["E"]) for r in case["rows"]])
+    nodes, mant, expo = oracle.sweep(F, s, E)
+    for k, r in enumerate(case["rows"]):
+        assert nodes[k] == r["nodes"]
+        ref = float.fromhex(r["tail_mant"]) * 2.0 ** (r["tail_exp"] - int(expo[k]))
+        assert mant[k] == pytest.approx(ref, rel=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD_ROT["rotation"], ids=lambda c: c["name"])
+def test_gpu_against_golden_rotating_curves(gpu_ctx, case):
+    """The CUDA path against the same committed vectors (no oracle involved)."""
+    V = np.array([float.fromhex(v) for v in case["V"]])
+    s, h = float.fromhex(case["s"]), float.fromhex(case["h"])
+    gpu_ctx.set_potentials_rot(V, s, case["rmin"], h, [case["J"]])
+    ci = gpu_ctx.curve_info(0)
+    assert (ci.i0, ci.n_steps) == (case["i0"], case["n_steps"])
+    E = np.array([float.fromhex(r["E"]) for r in case["rows"]])
+    nodes, mant, expo = gpu_ctx.sweep(E)
+    for k, r in enumerate(case["rows"]):
+        assert nodes[0][k] == r["nodes"]
+        ref = float.fromhex(r["tail_mant"]) * 2.0 ** (r["tail_exp"] - int(expo[0][k]))
+        assert mant[0][k] == pytest.approx(ref, rel=1e-7)
