@@ -733,7 +733,7 @@ int eps_set_potentials_rot(eps_ctx* ctx, const double* V, uint32_t n_curves, uin
     EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_J.p, J, n_J * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (n_raw + 3 * static_cast<size_t>(n_curves)) * sizeof(double) + n_J * sizeof(uint32_t);
     const uint32_t bx = std::min<uint32_t>((n_points + 255) / 256, 64u);
-    centrifugal_kernel<<<dim3(bx, n_eff), 256, 0, ctx->stream>>>(ctx->d_Vraw.p, d_s, d_r0, d_h, ctx->d_J.p, n_J, n_points,
+    centrifugal_kernel<<<dim3(n_eff, bx), 256, 0, ctx->stream>>>(ctx->d_Vraw.p, d_s, d_r0, d_h, ctx->d_J.p, n_J, n_points,
                                                                  ctx->d_V.p, ctx->d_scale.p);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;

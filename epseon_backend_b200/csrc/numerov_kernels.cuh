@@ -787,15 +787,15 @@ __global__ void __launch_bounds__(256)
 centrifugal_kernel(const double* __restrict__ Vraw, const double* __restrict__ scale, const double* __restrict__ rmin,
                    const double* __restrict__ hstep, const uint32_t* __restrict__ J, uint32_t n_J, uint32_t N,
                    double* __restrict__ Vout, double* __restrict__ scale_out) {
-    const uint32_t row = blockIdx.y, c = row / n_J, j = row - c * n_J;
+    const uint32_t row = blockIdx.x, c = row / n_J, j = row - c * n_J;  // rows on grid.x: up to 2^31 - 1 of them
     const uint32_t Jv  = J[j];
     const double   s = scale[c], h = hstep[c], r0 = rmin[c];
     const double   jj = static_cast<double>(static_cast<unsigned long long>(Jv) * (static_cast<unsigned long long>(Jv) + 1ull));
     const double   cj = __ddiv_rn(__dmul_rn(jj, __dmul_rn(h, h)), __dmul_rn(12.0, s));
     const double*  src = Vraw + static_cast<uint64_t>(c) * N;
     double*        dst = Vout + static_cast<uint64_t>(row) * N;
-    if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[row] = s;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) scale_out[row] = s;
+    for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x) {
         double v = src[i];
         if (Jv != 0) {
             const double r = __dadd_rn(r0, __dmul_rn(static_cast<double>(i), h));

@@ -215,3 +215,22 @@ def test_gpu_against_golden_rotating_curves(gpu_ctx, case):
         assert nodes[0][k] == r["nodes"]
         ref = float.fromhex(r["tail_mant"]) * 2.0 ** (r["tail_exp"] - int(expo[0][k]))
         assert mant[0][k] == pytest.approx(ref, rel=1e-7)
+
+
+@pytest.mark.gpu
+def test_gpu_rot_many_rows(oracle, gpu_ctx):
+    """More (curve, J) rows than a grid's y extent allows (65 535): rows ride on grid.x."""
+    n, nC, nJ = 64, 1100, 64
+    rng = np.random.default_rng(9)
+    x = np.linspace(0.5, 3.5, n)
+    V = (rng.uniform(50.0, 150.0, (nC, 1)) * (x[None, :] - 2.0) ** 2).astype(np.float64)
+    h = W.grid_h(0.5, 3.5, n)
+    s = W.scale(10.0, 12.0, h)
+    Js = np.arange(nJ, dtype=np.uint32)
+    gpu_ctx.set_potentials_rot(V, s, 0.5, h, Js)
+    assert gpu_ctx.n_curves == nC * nJ > 65535
+    for c, j in ((0, 0), (0, 63), (517, 31), (1099, 63), (1023, 1)):
+        VJ = oracle.centrifugal(V[c], s, 0.5, h, int(Js[j]))
+        F, i0, nst, vmin = oracle.prep(VJ, s)
+        ci = gpu_ctx.curve_info(c * nJ + j)
+        assert (ci.i0, ci.n_steps) == (i0, nst) and _same_bits([ci.v_min, ci.v_last], [vmin, VJ[-1]])
