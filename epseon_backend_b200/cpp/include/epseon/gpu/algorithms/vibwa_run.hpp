@@ -102,6 +102,23 @@ namespace epseon::gpu::cpp {
         p.max_rounds    = 16;
         p.rel_tol       = std::is_same_v<FP, float> ? 1e-8 : 1e-12;
         const uint32_t        nlev = p.v_max - p.v_min + 1;
+        // A handful of curves: a refinement round is latency-bound, so many points per round (few
+        // rounds) win.  Hundreds of curves: rounds are throughput-bound and k-section with fewer
+        // points per round needs less total work -- take just enough points for one curve's rows to
+        // fill a 256-energy CTA ("small packed CTAs").
+        {
+            eps_device_props props{};
+            detail::check(eps_device_get_props(handle->getDeviceInterface().getCudaOrdinal(), &props), nullptr,
+                          "eps_device_get_props");
+            const uint64_t wave = static_cast<uint64_t>(props.sm_count) * 512u;
+            if (nC > 1 && static_cast<uint64_t>(nC) * nlev * p.refine_points >= 4u * wave) {
+                uint32_t rows = 1;
+                while (rows < nlev) rows <<= 1;
+                p.refine_points = std::max<uint32_t>(16u, 256u / std::min<uint32_t>(rows, 256u));
+                p.max_rounds    = 24;
+            }
+        }
+        handle->setSearchParameters(p.n_coarse, p.refine_points, p.max_rounds, p.rel_tol);
         std::vector<double>   lev(static_cast<size_t>(nC) * nlev);
         std::vector<uint32_t> below(nC);
         detail::check(eps_timer_start(ctx), ctx, "eps_timer_start");

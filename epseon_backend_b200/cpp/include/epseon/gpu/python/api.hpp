@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <variant>
+#include <tuple>
 #include <vector>
 
 namespace epseon::gpu::python {
@@ -44,6 +45,13 @@ namespace epseon::gpu::python {
         std::shared_ptr<cpp::TaskHandle<FP>> getHandle() const { return handle; }
         bool                         has_failed() { return handle->hasFailed(); }
         double                       get_device_milliseconds() { return handle->getDeviceMilliseconds(); }
+        // (n_coarse, refine_points, max_rounds, rel_tol) the level search ran with
+        std::tuple<uint32_t, uint32_t, uint32_t, double> get_search_parameters() {
+            uint32_t v[3] = {0, 0, 0};
+            double   tol  = 0.0;
+            handle->getSearchParameters(v, tol);
+            return {v[0], v[1], v[2], tol};
+        }
     };
 
     using TaskHandleFloat32 = TaskHandle<float>;

@@ -38,6 +38,8 @@ namespace epseon::gpu::cpp {
         std::vector<std::vector<FP>> levels;       // [curve][level - min_level], NaN = not found
         std::vector<uint32_t>        level_counts; // [curve] levels below the search ceiling
         double                       device_ms = 0.0;
+        uint32_t                     search_n_coarse = 0, search_refine_points = 0, search_max_rounds = 0;
+        double                       search_rel_tol = 0.0; // parameters eps_solve_levels ran with
         std::vector<double>          wavefunctions;           // [curve][level][point], flat; empty unless requested
         uint32_t                     wf_curves = 0, wf_levels = 0, wf_points = 0;
 
@@ -110,6 +112,21 @@ namespace epseon::gpu::cpp {
             levels       = std::move(levels_);
             level_counts = std::move(counts_);
             device_ms    = ms;
+        }
+        void setSearchParameters(uint32_t n_coarse, uint32_t refine_points, uint32_t max_rounds, double rel_tol) {
+            std::lock_guard<std::mutex> g(result_mutex);
+            search_n_coarse      = n_coarse;
+            search_refine_points = refine_points;
+            search_max_rounds    = max_rounds;
+            search_rel_tol       = rel_tol;
+        }
+        // {n_coarse, refine_points, max_rounds} and rel_tol of the level search the task ran.
+        void getSearchParameters(uint32_t out[3], double& rel_tol) const {
+            std::lock_guard<std::mutex> g(result_mutex);
+            out[0]  = search_n_coarse;
+            out[1]  = search_refine_points;
+            out[2]  = search_max_rounds;
+            rel_tol = search_rel_tol;
         }
         void setWavefunctions(std::vector<double> psi, uint32_t n_curves, uint32_t n_levels, uint32_t n_points) {
             std::lock_guard<std::mutex> g(result_mutex);

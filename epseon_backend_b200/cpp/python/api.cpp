@@ -70,6 +70,10 @@ namespace epseon::gpu::python {
                      "(empty unless set_wavefunction_output(True) was configured).")
                 .def("has_failed", &H::has_failed, "True when the worker stopped with an error (see status message).")
                 .def("get_device_milliseconds", &H::get_device_milliseconds, "CUDA-event time of the level solve.")
+                .def("get_search_parameters", &H::get_search_parameters,
+                     "(n_coarse, refine_points, max_rounds, rel_tol) of the level search the task ran: 1024-point "
+                     "coarse grid and 256 points per level per round for a few curves, fewer points per round for "
+                     "batches of hundreds of curves.")
                 .doc() = "Handle object for referencing GPU compute task.";
         }
 

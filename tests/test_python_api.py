@@ -365,3 +365,36 @@ def test_example_script_runs():
                        cwd=ROOT, timeout=300)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
     assert "curve 1 J=1" in r.stdout and "rotational constant" in r.stdout
+
+
+@pytest.mark.gpu
+def test_batch_task_uses_fewer_points_per_round(gpu_mod, oracle):
+    """Hundreds of curves in one task: the search runs with fewer points per level per round
+    (get_search_parameters), and the levels still carry the oracle's bits for those parameters."""
+    N, nC = 3000, 640
+    rng = np.random.default_rng(12)
+    De = 5500.0 * (1 + 0.05 * (2 * rng.random(nC) - 1))
+    interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
+    cfg = interface.get_task_configurator("float64")
+    cfg.set_hardware_config(potential_buffer_size=N, group_size=1024, allocation_block_size=1 << 20)
+    cfg.set_morse_potential([gpu_mod.MorsePotentialConfig(dissociation_energy=float(d), equilibrium_bond_distance=2.2,
+                                                          well_width=1.6, min_r=0.4, max_r=10.0, point_count=N) for d in De])
+    cfg.set_vibwa_algorithm(mass_atom_0=20.0, mass_atom_1=20.0, integration_step=0.1,
+                            min_distance_to_asymptote=1.0, min_level=0, max_level=7)
+    handle = interface.submit_task(cfg)
+    handle.wait()
+    assert not handle.has_failed(), handle.get_status_message()
+    n_coarse, M, rounds, tol = handle.get_search_parameters()
+    assert (n_coarse, M, tol) == (1024, 32, 1e-12) and rounds >= 16
+    levels = np.array(handle.get_levels())
+    assert levels.shape == (nC, 8) and np.all(np.isfinite(levels))
+    s = oracle.scale(20.0, 20.0, W.grid_h(0.4, 10.0, N))
+    for c in (0, 1, 317, 639):
+        V = oracle.morse(float(De[c]), 2.2, 1.6, 0.4, 10.0, N)
+        F, _, _, vmin = oracle.prep(V, s)
+        ref, *_ = oracle.solve_levels(F, s, vmin, V[-1] - 1.0, n_coarse, 0, 7, M, tol, rounds)
+        assert np.array_equal(levels[c].view(np.uint64), ref.view(np.uint64)), c
+    # a small task keeps the 256-point rounds
+    small = interface.submit_task(_configure_task(gpu_mod, interface.get_task_configurator("float64"), max_level=3))
+    small.wait()
+    assert small.get_search_parameters()[:3] == (1024, 256, 16)
