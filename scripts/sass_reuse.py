@@ -1,33 +1,61 @@
-import re, subprocess, sys
-def analyze(path, kern="_ZN3eps20numerov_sweep_kernelILi2ELi8ELi32ELb0ELb0E"):
-    txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-    m = re.search(r"Function : " + kern + r".*?(?=Function :|\Z)", txt, re.S)
-    lines = [l for l in m.group(0).splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
-    ins = []
-    for l in lines:
-        body = l.split("*/", 1)[1].split(";")[0].strip()
-        ins.append(body)
+#!/usr/bin/env python
+"""Count how many three-register DFMAs of a kernel are fed by the operand reuse cache.
+
+On B200 an FP64 instruction reads one 64-bit register operand per cycle, so a DFMA with three
+distinct register sources holds the FP64 pipe for 3 cycles instead of 2 -- unless one source was
+read in the same operand slot by the warp's previous instruction and that one carries the `.reuse`
+flag (scripts/microbench3.cu).  For the Numerov step this is the pair
+
+    DMUL S', X, fp.reuse ;  DFMA X', Q, fp, X
+
+    python scripts/sass_reuse.py LIB.so [mangled-name-fragment ...]
+
+prints (reuse-fed, not reuse-fed) per kernel; `analyze()` is used by tests/test_sass.py.
+"""
+from __future__ import annotations
+
+import functools
+import os
+import re
+import subprocess
+import sys
+
+
+def _strip(op: str) -> str:
+    return re.sub(r"[-|]|\.reuse", "", op)
+
+
+@functools.lru_cache(maxsize=4)
+def _dump(path: str, mtime: float) -> str:
+    return subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+
+
+def analyze(path: str, kern: str) -> tuple[int, int]:
+    """(good, bad) for the first function of `path` whose mangled name contains `kern`."""
+    txt = _dump(path, os.path.getmtime(path))
+    m = re.search(r"Function : \S*" + re.escape(kern) + r".*?(?=Function :|\Z)", txt, re.S)
+    if m is None:
+        raise KeyError(f"no function matching {kern!r} in {path}")
+    ins = [line.split("*/", 1)[1].split(";")[0].strip() for line in m.group(0).splitlines()
+           if re.match(r"\s+/\*[0-9a-f]{4}\*/", line)]
     good = bad = 0
-    for i, b in enumerate(ins):
-        if not b.startswith("DFMA"):
+    for i, body in enumerate(ins):
+        if not body.startswith("DFMA") or i == 0:
             continue
-        ops = [o.strip() for o in b[4:].split(",")]
-        srcs = ops[1:]
-        regs = [re.sub(r"[-|]|\.reuse", "", o) for o in srcs]
+        regs = [_strip(o.strip()) for o in body[4:].split(",")][1:]
         if not all(r.startswith("R") for r in regs) or len(set(regs)) < 3:
-            continue  # immediate / constant operand or repeated register: <= 2 RF reads
-        # previous FP64 instruction
+            continue  # immediate / constant / uniform operand or a repeated register: at most 2 reads
         prev = ins[i - 1]
-        pops = [o.strip() for o in prev.split(None, 1)[1].split(",")][1:] if " " in prev else []
-        hit = False
-        for slot, o in enumerate(pops):
-            if ".reuse" in o and slot < len(regs) and re.sub(r"[-|]|\.reuse", "", o) == regs[slot]:
-                hit = True
-        if hit:
-            good += 1
-        else:
-            bad += 1
+        prev_ops = [o.strip() for o in prev.split(None, 1)[1].split(",")][1:] if " " in prev else []
+        fed = any(".reuse" in o and slot < len(regs) and _strip(o) == regs[slot] for slot, o in enumerate(prev_ops))
+        good, bad = good + fed, bad + (not fed)
     return good, bad
+
+
 if __name__ == "__main__":
-    for p in sys.argv[1:]:
-        print(p, "3-reg DFMA fed by reuse / not:", analyze(p))
+    lib = sys.argv[1]
+    names = sys.argv[2:] or ["numerov_sweep_kernelILi4ELi4ELi32ELb0ELb0E", "numerov_sweep_kernelILi4ELi4ELi8ELb0ELb0E",
+                             "numerov_sweep_kernelILi2ELi4ELi8ELb0ELb0E", "numerov_cbank_kernelILi4ELi128ELi32ELb0E",
+                             "numerov_sweep_kernelILi2ELi8ELi32ELb0ELb1E"]
+    for n in names:
+        print(n, "three-register DFMAs fed by the reuse cache / not:", analyze(lib, n))
