@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -19,11 +21,70 @@ namespace epseon::gpu::cpp {
     namespace detail {
         constexpr double kHbar2Over2 = 16.857629206; // amu * Angstrom^2 * cm^-1
 
-        struct CtxGuard {
-            eps_ctx* ctx = nullptr;
-            ~CtxGuard() {
-                if (ctx != nullptr) eps_ctx_destroy(ctx);
+        // Contexts are pooled per device: creating one (stream, events, a dozen device buffers) and
+        // tearing it down costs ~10 ms per task against ~2 ms of solve for a small task.  A task
+        // takes an idle context of its device or creates one, and hands it back when it is done;
+        // at most kMaxIdle stay parked per device, so concurrent tasks still get a context each.
+        // Idle contexts are deliberately not destroyed at process exit (the CUDA runtime may
+        // already be gone when static destructors run).
+        class CtxPool {
+            static constexpr size_t kMaxIdle = 2;
+            std::mutex                                 mutex;
+            std::map<int, std::vector<eps_ctx*>>       idle;
+
+          public:
+            static CtxPool& instance() {
+                static CtxPool* pool = new CtxPool(); // never destroyed, see above
+                return *pool;
             }
+            eps_ctx* acquire(int device) {
+                {
+                    std::lock_guard<std::mutex> g(mutex);
+                    auto&                       v = idle[device];
+                    if (!v.empty()) {
+                        eps_ctx* ctx = v.back();
+                        v.pop_back();
+                        return ctx;
+                    }
+                }
+                eps_ctx* ctx = nullptr;
+                if (eps_ctx_create(device, &ctx) != EPS_OK)
+                    throw std::runtime_error(std::string("eps_ctx_create: ") + eps_last_error(nullptr));
+                return ctx;
+            }
+            void release(int device, eps_ctx* ctx, bool healthy) {
+                if (ctx == nullptr) return;
+                if (healthy) {
+                    std::lock_guard<std::mutex> g(mutex);
+                    auto&                       v = idle[device];
+                    if (v.size() < kMaxIdle) {
+                        v.push_back(ctx);
+                        return;
+                    }
+                }
+                eps_ctx_destroy(ctx);
+            }
+        };
+
+        // SM count per device, asked once (cudaGetDeviceProperties costs milliseconds per call).
+        inline int sm_count_of(int device) {
+            static std::mutex         mutex;
+            static std::map<int, int> cache;
+            std::lock_guard<std::mutex> g(mutex);
+            auto                        it = cache.find(device);
+            if (it != cache.end()) return it->second;
+            eps_device_props props{};
+            if (eps_device_get_props(device, &props) != EPS_OK)
+                throw std::runtime_error(std::string("eps_device_get_props: ") + eps_last_error(nullptr));
+            cache[device] = props.sm_count;
+            return props.sm_count;
+        }
+
+        struct CtxGuard {
+            int      device  = 0;
+            eps_ctx* ctx     = nullptr;
+            bool     healthy = false; // set once the task ran to its end: only then is the context reused
+            ~CtxGuard() { CtxPool::instance().release(device, ctx, healthy); }
         };
 
         inline void check(int rc, eps_ctx* ctx, const char* what) {
@@ -70,7 +131,8 @@ namespace epseon::gpu::cpp {
         // ---- device: resident coefficient tables ----
         handle->setStatus("uploading potentials");
         detail::CtxGuard guard;
-        detail::check(eps_ctx_create(handle->getDeviceInterface().getCudaOrdinal(), &guard.ctx), nullptr, "eps_ctx_create");
+        guard.device = handle->getDeviceInterface().getCudaOrdinal();
+        guard.ctx    = detail::CtxPool::instance().acquire(guard.device);
         eps_ctx* ctx = guard.ctx;
         if (rotating) {
             const std::vector<double> origins = source->get_grid_origins();
@@ -107,10 +169,7 @@ namespace epseon::gpu::cpp {
         // points per round needs less total work -- take just enough points for one curve's rows to
         // fill a 256-energy CTA ("small packed CTAs").
         {
-            eps_device_props props{};
-            detail::check(eps_device_get_props(handle->getDeviceInterface().getCudaOrdinal(), &props), nullptr,
-                          "eps_device_get_props");
-            const uint64_t wave = static_cast<uint64_t>(props.sm_count) * 512u;
+            const uint64_t wave = static_cast<uint64_t>(detail::sm_count_of(guard.device)) * 512u;
             if (nC > 1 && static_cast<uint64_t>(nC) * nlev * p.refine_points >= 4u * wave) {
                 uint32_t rows = 1;
                 while (rows < nlev) rows <<= 1;
@@ -141,6 +200,7 @@ namespace epseon::gpu::cpp {
                           "eps_wavefunctions");
             handle->setWavefunctions(std::move(psi), nC, nlev, N);
         }
+        guard.healthy = true;
         handle->setStatus("done");
     }
 } // namespace epseon::gpu::cpp
