@@ -1,0 +1,55 @@
+"""The bench JSON contract (one line per run): keys the driver reads, checked on the committed lines
+of the last GPU runs (profiles/r1_bench_*.json) and on a live `--impl reference` run (CPU only)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BASE = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "e2e"}
+LINES = sorted((ROOT / "profiles").glob("r1_bench_c*.json"))
+
+
+@pytest.mark.parametrize("path", LINES, ids=lambda p: p.name)
+def test_committed_bench_lines(path):
+    text = path.read_text().strip()
+    assert text.count("\n") == 0, "exactly one JSON line"
+    d = json.loads(text)
+    assert BASE <= d.keys(), BASE - d.keys()
+    assert d["metric"] == "numerov_grid_steps_x_trial_energies_per_s" and d["unit"] == "steps/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["scaling"] in ("weak", "strong") and d["warmup"] >= 3 and d["value"] > 0
+    assert d["config"]["workload"].startswith(path.name.split("_")[2][:2]) and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= d["e2e"].keys()
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.001
+    assert d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= r.keys()
+    assert r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 0.75
+    c = d["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= c.keys()
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    if "cpu_baseline" in d:
+        assert {"value", "unit", "cores", "kind", "sample"} <= d["cpu_baseline"].keys()
+        assert d["cpu_baseline"]["kind"] == "port"
+        for k in ("levels_bit_identical_to_gpu", "nodes_bit_identical_to_gpu"):
+            if k in d["cpu_baseline"]:
+                assert d["cpu_baseline"][k] is True
+
+
+def test_reference_arm_line_live():
+    """`bench.py --impl reference` runs without a GPU: same metric / config as the CUDA arm, one line."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE <= d.keys()
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"] and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    committed = json.loads((ROOT / "profiles" / "r1_bench_c2.json").read_text())
+    assert d["config"] == committed["config"] and d["metric"] == committed["metric"] and d["unit"] == committed["unit"]
