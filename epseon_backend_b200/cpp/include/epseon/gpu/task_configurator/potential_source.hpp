@@ -61,6 +61,19 @@ namespace epseon::gpu::cpp {
             double              h  = 0.0;
             double              r0 = 0.0;
         };
+        // every file is read and resampled once per loader (copies share the result): a task asks
+        // for the tables, the grid steps and the grid origins
+        mutable std::shared_ptr<const std::vector<Table>> loaded = {};
+
+        const std::vector<Table>& tables() const {
+            if (!loaded) {
+                auto all = std::make_shared<std::vector<Table>>();
+                all->reserve(file_names.size());
+                for (const auto& name : file_names) all->push_back(load(name));
+                loaded = std::move(all);
+            }
+            return *loaded;
+        }
 
         // NumPy .npy (format 1.0 / 2.0 / 3.0): a C-ordered little-endian float64 array of shape (n, 2),
         // column 0 = r, column 1 = V.
@@ -171,8 +184,7 @@ namespace epseon::gpu::cpp {
 
         std::vector<std::vector<FP>> get_potential_data() override {
             std::vector<std::vector<FP>> out;
-            for (const auto& name : file_names) {
-                const Table t = load(name);
+            for (const Table& t : tables()) {
                 if (!out.empty() && out.front().size() != t.v.size())
                     throw std::runtime_error("PotentialFileLoader: all curves must have the same point count");
                 out.emplace_back(t.v.begin(), t.v.end());
@@ -182,13 +194,13 @@ namespace epseon::gpu::cpp {
 
         std::vector<double> get_grid_steps() const override {
             std::vector<double> out;
-            for (const auto& name : file_names) out.push_back(load(name).h);
+            for (const Table& t : tables()) out.push_back(t.h);
             return out;
         }
 
         std::vector<double> get_grid_origins() const override {
             std::vector<double> out;
-            for (const auto& name : file_names) out.push_back(load(name).r0);
+            for (const Table& t : tables()) out.push_back(t.r0);
             return out;
         }
 
