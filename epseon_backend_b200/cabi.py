@@ -15,7 +15,8 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libepseon_cuda.so"
 
 EPS_OK = 0
 ERR_NAMES = {1: "EPS_ERR_INVALID", 2: "EPS_ERR_CUDA", 3: "EPS_ERR_RANGE", 4: "EPS_ERR_STATE",
-             5: "EPS_ERR_NOMEM"}
+             5: "EPS_ERR_NOMEM", 6: "EPS_ERR_CANCELLED"}
+EPS_ERR_CANCELLED = 6
 
 # every symbol include/epseon_cuda.h declares
 SYMBOLS = [
@@ -23,6 +24,7 @@ SYMBOLS = [
     "eps_ctx_destroy", "eps_last_error", "eps_sync", "eps_set_potentials", "eps_set_potentials_rot", "eps_get_curve_info",
     "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_level_corrections", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe", "eps_host_alloc", "eps_host_free",
+    "eps_request_stop", "eps_reset_stop", "eps_ctx_device_bytes", "eps_ctx_trim",
 ]
 
 
@@ -136,6 +138,23 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.eps_sync(self.h))
+
+    def request_stop(self):
+        """Callable from any thread while another thread runs a compute call on this context."""
+        self._ck(self.lib.eps_request_stop(self.h))
+
+    def reset_stop(self):
+        self._ck(self.lib.eps_reset_stop(self.h))
+
+    def device_bytes(self) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.eps_ctx_device_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def trim(self, drop_potentials: bool = False):
+        self._ck(self.lib.eps_ctx_trim(self.h, C.c_int(1 if drop_potentials else 0)))
+        if drop_potentials:
+            self.n_curves = 0
 
     def set_potentials(self, V: np.ndarray, scale) -> None:
         V = np.ascontiguousarray(np.atleast_2d(V), dtype=np.float64)

@@ -4,7 +4,8 @@
 // one descriptor set, prints "Thread finished" and returns -- no compute.  Here run() is the real
 // hot path: tabulate -> C ABI (include/epseon_cuda.h) -> CUDA sweep / bracketing / refinement ->
 // results stored on the TaskHandle.  The definition lives in vibwa_run.hpp (it needs the complete
-// TaskHandle type) and is pulled in by task_handle.hpp.
+// TaskHandle type); like the reference (vibwa.hpp:8,11) this header pulls in algorithm_config.hpp
+// and task_handle.hpp, so including it alone is enough to call run().
 #pragma once
 #include "epseon/gpu/predecl.hpp"
 
@@ -21,3 +22,6 @@ namespace epseon::gpu::cpp {
         void run(const std::stop_token& stop_token, TaskHandle<FP>* handle) override;
     };
 } // namespace epseon::gpu::cpp
+
+#include "epseon/gpu/task_configurator/algorithm_config.hpp"
+#include "epseon/gpu/task_handle.hpp"

@@ -52,8 +52,27 @@ namespace epseon::gpu::cpp {
                     throw std::runtime_error(std::string("eps_ctx_create: ") + eps_last_error(nullptr));
                 return ctx;
             }
+            // Bytes a parked context may keep (its grow-only scratch is trimmed above that): a small
+            // task re-reserves a few MB in microseconds, a wavefunction task's GBs must not stay pinned.
+            static constexpr uint64_t kMaxParkedBytes = 64ull << 20;
+
+            void clear() {
+                std::map<int, std::vector<eps_ctx*>> all;
+                {
+                    std::lock_guard<std::mutex> g(mutex);
+                    all.swap(idle);
+                }
+                for (auto& [dev, v] : all)
+                    for (eps_ctx* ctx : v) eps_ctx_destroy(ctx);
+            }
             void release(int device, eps_ctx* ctx, bool healthy) {
                 if (ctx == nullptr) return;
+                if (healthy) {
+                    uint64_t bytes = 0;
+                    if (eps_ctx_device_bytes(ctx, &bytes) != EPS_OK ||
+                        (bytes > kMaxParkedBytes && eps_ctx_trim(ctx, /*drop_potentials=*/1) != EPS_OK))
+                        healthy = false;
+                }
                 if (healthy) {
                     std::lock_guard<std::mutex> g(mutex);
                     auto&                       v = idle[device];
@@ -87,6 +106,9 @@ namespace epseon::gpu::cpp {
             ~CtxGuard() { CtxPool::instance().release(device, ctx, healthy); }
         };
 
+        // Releases every idle pooled context (additive; Python: release_device_memory()).
+        inline void trim_context_pool() { CtxPool::instance().clear(); }
+
         inline void check(int rc, eps_ctx* ctx, const char* what) {
             if (rc != EPS_OK) throw std::runtime_error(std::string(what) + ": " + eps_last_error(ctx));
         }
@@ -94,7 +116,7 @@ namespace epseon::gpu::cpp {
 
     template <typename FP>
     void VibwaAlgorithm<FP>::run(const std::stop_token& stop_token, TaskHandle<FP>* handle) {
-        if (stop_token.stop_requested()) return;
+        if (stop_token.stop_requested()) return handle->setCancelled();
 
         const TaskConfigurator<FP>& configurator = handle->getTaskConfigurator();
         const auto                  hardware     = configurator.getHardwareConfig();
@@ -108,9 +130,12 @@ namespace epseon::gpu::cpp {
         const auto                table = source->get_potential_data();
         const std::vector<double> steps = source->get_grid_steps();
         const uint32_t            nT    = static_cast<uint32_t>(table.size()); // tables (one per configured curve)
-        if (nT == 0) throw std::runtime_error("potential source holds no curves");
+        if (nT == 0) {
+            const std::string why = source->get_last_error();
+            throw std::runtime_error("potential source holds no curves" + (why.empty() ? std::string() : ": " + why));
+        }
         // additive: every table is solved once per rotational state J; row = table*nJ + j
-        const std::vector<uint32_t>& J  = configurator.getRotationalStates();
+        const std::vector<uint32_t>  J  = configurator.getRotationalStates(); // by value
         const uint32_t               nJ = static_cast<uint32_t>(J.size());
         const bool     rotating = std::any_of(J.begin(), J.end(), [](uint32_t j) { return j != 0; }) || nJ > 1;
         const uint32_t nC       = nT * nJ;
@@ -126,7 +151,7 @@ namespace epseon::gpu::cpp {
             for (uint32_t i = 0; i < N; i++) V[static_cast<size_t>(k) * N + i] = static_cast<double>(table[k][i]);
             scale[k] = ((steps[k] * steps[k]) * c) / 12.0;
         }
-        if (stop_token.stop_requested()) return;
+        if (stop_token.stop_requested()) return handle->setCancelled();
 
         // ---- device: resident coefficient tables ----
         handle->setStatus("uploading potentials");
@@ -134,6 +159,15 @@ namespace epseon::gpu::cpp {
         guard.device = handle->getDeviceInterface().getCudaOrdinal();
         guard.ctx    = detail::CtxPool::instance().acquire(guard.device);
         eps_ctx* ctx = guard.ctx;
+        // cancel() -> stop_token -> eps_request_stop: the C ABI tests the flag between refinement
+        // rounds and the sweep CTAs test it on entry, so a running solve stops within a round.
+        detail::check(eps_reset_stop(ctx), ctx, "eps_reset_stop");
+        const std::stop_callback on_stop(stop_token, [ctx] { eps_request_stop(ctx); });
+        const auto run_step = [&](int rc, const char* what) { // -> true when the step was cancelled
+            if (rc == EPS_ERR_CANCELLED) return true;
+            detail::check(rc, ctx, what);
+            return false;
+        };
         if (rotating) {
             const std::vector<double> origins = source->get_grid_origins();
             detail::check(eps_set_potentials_rot(ctx, V.data(), nT, N, scale.data(), origins.data(), steps.data(),
@@ -152,7 +186,7 @@ namespace epseon::gpu::cpp {
             E_lo[k] = info.v_min;
             E_hi[k] = std::max(info.v_min, info.v_last - margin);
         }
-        if (stop_token.stop_requested()) return;
+        if (stop_token.stop_requested()) return handle->setCancelled();
 
         // ---- N2..N6: coarse sweep, bracketing, k-section refinement ----
         handle->setStatus("solving levels");
@@ -181,8 +215,12 @@ namespace epseon::gpu::cpp {
         std::vector<double>   lev(static_cast<size_t>(nC) * nlev);
         std::vector<uint32_t> below(nC);
         detail::check(eps_timer_start(ctx), ctx, "eps_timer_start");
-        detail::check(eps_solve_levels(ctx, &p, E_lo.data(), E_hi.data(), lev.data(), nullptr, below.data()), ctx,
-                      "eps_solve_levels");
+        if (run_step(eps_solve_levels(ctx, &p, E_lo.data(), E_hi.data(), lev.data(), nullptr, below.data()),
+                     "eps_solve_levels")) {
+            eps_sync(ctx); // let the drained launches finish before the context is parked
+            guard.healthy = eps_reset_stop(ctx) == EPS_OK;
+            return handle->setCancelled();
+        }
         float ms = 0.f;
         detail::check(eps_timer_stop(ctx, &ms), ctx, "eps_timer_stop");
 

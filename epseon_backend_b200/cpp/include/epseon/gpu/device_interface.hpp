@@ -35,3 +35,22 @@ namespace epseon::gpu::cpp {
         [[nodiscard]] const ComputeContextState& getComputeContextState() const { return *computeContextState; }
     };
 } // namespace epseon::gpu::cpp
+
+// submitTask needs the complete TaskHandle; the reference's device_interface.hpp includes
+// task_handle.hpp too (:9).  Placed after the class so that either header may come first.
+#include "epseon/gpu/task_handle.hpp"
+
+namespace epseon::gpu::cpp {
+    template <typename FP>
+    std::shared_ptr<epseon::gpu::cpp::TaskHandle<FP>>
+    ComputeDeviceInterface::submitTask(std::shared_ptr<TaskConfigurator<FP>> task_config) {
+        if (!task_config->isConfigured())
+            throw std::runtime_error("TaskConfigurator wasn't fully configured before submitting for execution.");
+        // Snapshot: the task owns a deep copy of the configuration (the copy constructor clones all
+        // three parts), so the caller may go on mutating / reusing its builder while the worker runs.
+        // (The reference hands the live builder to the handle and copies it inside run(),
+        // vibwa.hpp:615 -- on the worker thread, i.e. after submit has returned.)
+        return std::make_shared<TaskHandle<FP>>(this->shared_from_this(),
+                                                std::make_shared<TaskConfigurator<FP>>(*task_config));
+    }
+} // namespace epseon::gpu::cpp

@@ -37,7 +37,8 @@ namespace epseon::gpu::python {
         std::string get_status_message() { return handle->getStatusMessage(); }
         bool        is_done() { return handle->isDone(); }
         bool        is_running() { return handle->isRunning(); }
-        void        cancel() { handle->cancel(); }
+        bool        cancel() { return handle->cancel(); }
+        bool        was_cancelled() { return handle->wasCancelled(); }
         void        wait() { handle->wait(); }
         // additive
         std::vector<std::vector<FP>> get_levels() { return handle->getLevels(); }

@@ -119,3 +119,29 @@ namespace epseon::gpu::cpp {
         return lhs.equals(rhs);
     }
 } // namespace epseon::gpu::cpp
+
+// Include closure of the reference: there, this header pulls in algorithms/vibwa.hpp (:7), which
+// pulls in task_handle.hpp (vibwa.hpp:11) and through it task_configurator.hpp and
+// device_interface.hpp -- a translation unit that includes ONLY algorithm_config.hpp sees complete
+// TaskConfigurator / TaskHandle types and the definitions of VibwaAlgorithm<FP>::run and
+// getShaderBufferRequirements (the reference's test_task_configurator.cpp and
+// test_algorithm_confgu.cpp rely on exactly that).  Same closure here, placed after the class
+// definitions so that it is order-independent.
+#include "epseon/gpu/task_configurator/task_configurator.hpp"
+#include "epseon/gpu/task_handle.hpp"
+
+namespace epseon::gpu::cpp {
+    template <typename FP>
+    std::vector<ShaderBuffersRequirements<FP>>
+    VibwaAlgorithmConfig<FP>::getShaderBufferRequirements(const TaskConfigurator<FP>& config) const {
+        const auto hw = config.getHardwareConfig();
+        ShaderBuffersRequirements<FP> one{};
+        one.stagingBuffersCount               = 1;
+        one.stagingBuffersElementCount        = hw->getPotentialBufferSize();
+        one.gpuOnlyStorageBuffersCount        = 5;
+        one.gpuOnlyStorageBuffersElementCount = hw->getPotentialBufferSize();
+        one.outputBuffersCount                = 1;
+        one.outputBuffersElementCount         = getLevelCount();
+        return std::vector<ShaderBuffersRequirements<FP>>(hw->getGroupSize(), one);
+    }
+} // namespace epseon::gpu::cpp

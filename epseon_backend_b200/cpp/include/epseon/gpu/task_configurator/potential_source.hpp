@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <span>
 #include <sstream>
 #include <stdexcept>
@@ -42,6 +43,8 @@ namespace epseon::gpu::cpp {
         virtual std::vector<double>          get_grid_origins() const                       = 0;
         [[nodiscard]] virtual std::shared_ptr<PotentialSource<FP>> shared_clone() const     = 0;
         [[nodiscard]] virtual std::unique_ptr<PotentialSource<FP>> unique_clone() const     = 0;
+        // Why get_potential_data() came back empty, if it did (additive).
+        [[nodiscard]] virtual std::string get_last_error() const { return {}; }
     };
 
     // Tabulated curves from files: text with one "r V" pair per line ('#' comments allowed), or a
@@ -61,18 +64,47 @@ namespace epseon::gpu::cpp {
             double              h  = 0.0;
             double              r0 = 0.0;
         };
-        // every file is read and resampled once per loader (copies share the result): a task asks
-        // for the tables, the grid steps and the grid origins
-        mutable std::shared_ptr<const std::vector<Table>> loaded = {};
+        // Every file is read and resampled once per loader; copies share the result AND the lock, so
+        // the same configuration submitted to two devices (two worker threads) loads once.
+        struct Shared {
+            std::mutex                                mutex;
+            bool                                      tried = false;
+            std::shared_ptr<const std::vector<Table>> tables;
+            std::string                               error; // why loading failed
+        };
+        mutable std::shared_ptr<Shared> shared = std::make_shared<Shared>();
+
+        Shared& state() const {
+            if (!shared) shared = std::make_shared<Shared>(); // moved-from object
+            return *shared;
+        }
+
+        // nullptr when the files cannot be loaded (reason in state().error)
+        std::shared_ptr<const std::vector<Table>> try_tables() const {
+            Shared&                     st = state();
+            std::lock_guard<std::mutex> g(st.mutex);
+            if (!st.tried) {
+                st.tried = true;
+                try {
+                    auto all = std::make_shared<std::vector<Table>>();
+                    all->reserve(file_names.size());
+                    for (const auto& name : file_names) {
+                        all->push_back(load(name));
+                        if (all->front().v.size() != all->back().v.size())
+                            throw std::runtime_error("PotentialFileLoader: all curves must have the same point count");
+                    }
+                    st.tables = std::move(all);
+                } catch (const std::exception& e) {
+                    st.error = e.what();
+                }
+            }
+            return st.tables;
+        }
 
         const std::vector<Table>& tables() const {
-            if (!loaded) {
-                auto all = std::make_shared<std::vector<Table>>();
-                all->reserve(file_names.size());
-                for (const auto& name : file_names) all->push_back(load(name));
-                loaded = std::move(all);
-            }
-            return *loaded;
+            const auto t = try_tables();
+            if (!t) throw std::runtime_error(state().error);
+            return *t;
         }
 
         // NumPy .npy (format 1.0 / 2.0 / 3.0): a C-ordered little-endian float64 array of shape (n, 2),
@@ -182,14 +214,25 @@ namespace epseon::gpu::cpp {
             return o != nullptr && file_names == o->file_names && point_count == o->point_count;
         }
 
+        // Like the reference's (potential_source.hpp:89-91) this never throws: files that cannot be
+        // read give an empty result -- which is all the reference ever returns -- and the reason is
+        // kept for get_last_error(); a task over such a source fails with that reason in its status.
+        // load() is the strict variant.
         std::vector<std::vector<FP>> get_potential_data() override {
             std::vector<std::vector<FP>> out;
-            for (const Table& t : tables()) {
-                if (!out.empty() && out.front().size() != t.v.size())
-                    throw std::runtime_error("PotentialFileLoader: all curves must have the same point count");
-                out.emplace_back(t.v.begin(), t.v.end());
-            }
+            const auto                   t = try_tables();
+            if (!t) return out;
+            for (const Table& tb : *t) out.emplace_back(tb.v.begin(), tb.v.end());
             return out;
+        }
+
+        // Read (once) and validate every file; throws std::runtime_error with the reason.
+        void load() const { (void)tables(); }
+
+        [[nodiscard]] std::string get_last_error() const override {
+            Shared&                     st = state();
+            std::lock_guard<std::mutex> g(st.mutex);
+            return st.error;
         }
 
         std::vector<double> get_grid_steps() const override {

@@ -120,18 +120,4 @@ namespace epseon::gpu::cpp {
             return algorithm_config->getShaderBufferRequirements(*this);
         }
     };
-
-    template <typename FP>
-    std::vector<ShaderBuffersRequirements<FP>>
-    VibwaAlgorithmConfig<FP>::getShaderBufferRequirements(const TaskConfigurator<FP>& config) const {
-        const auto hw = config.getHardwareConfig();
-        ShaderBuffersRequirements<FP> one{};
-        one.stagingBuffersCount               = 1;
-        one.stagingBuffersElementCount        = hw->getPotentialBufferSize();
-        one.gpuOnlyStorageBuffersCount        = 5;
-        one.gpuOnlyStorageBuffersElementCount = hw->getPotentialBufferSize();
-        one.outputBuffersCount                = 1;
-        one.outputBuffersElementCount         = getLevelCount();
-        return std::vector<ShaderBuffersRequirements<FP>>(hw->getGroupSize(), one);
-    }
 } // namespace epseon::gpu::cpp

@@ -35,6 +35,7 @@ namespace epseon::gpu::cpp {
         mutable std::mutex           result_mutex;
         std::string                  status = "created";
         bool                         failed = false;
+        bool                         cancelled = false;
         std::vector<std::vector<FP>> levels;       // [curve][level - min_level], NaN = not found
         std::vector<uint32_t>        level_counts; // [curve] levels below the search ceiling
         double                       device_ms = 0.0;
@@ -102,6 +103,17 @@ namespace epseon::gpu::cpp {
             std::lock_guard<std::mutex> g(result_mutex);
             if (!failed) status = s;
         }
+        // The task stopped on its stop_token (cancel()): is_done() becomes true, has_failed() stays
+        // false, the status reads "cancelled" and was_cancelled() is true; results may be missing.
+        void setCancelled() {
+            std::lock_guard<std::mutex> g(result_mutex);
+            if (!failed) status = "cancelled";
+            cancelled = true;
+        }
+        [[nodiscard]] bool wasCancelled() const {
+            std::lock_guard<std::mutex> g(result_mutex);
+            return cancelled;
+        }
         void setFailure(const std::string& s) {
             std::lock_guard<std::mutex> g(result_mutex);
             status = s;
@@ -165,14 +177,6 @@ namespace epseon::gpu::cpp {
             return device_ms;
         }
     };
-
-    template <typename FP>
-    std::shared_ptr<epseon::gpu::cpp::TaskHandle<FP>>
-    ComputeDeviceInterface::submitTask(std::shared_ptr<TaskConfigurator<FP>> task_config) {
-        if (!task_config->isConfigured())
-            throw std::runtime_error("TaskConfigurator wasn't fully configured before submitting for execution.");
-        return std::make_shared<TaskHandle<FP>>(this->shared_from_this(), task_config);
-    }
 } // namespace epseon::gpu::cpp
 
 #include "epseon/gpu/algorithms/vibwa_run.hpp"

@@ -53,7 +53,11 @@ namespace epseon::gpu::python {
                 .def("is_done", &H::is_done, "Check if task already finished execution.")
                 .def("wait", &H::wait, py::call_guard<py::gil_scoped_release>(), "Block and wait for task to finish.")
                 .def("is_running", &H::is_running, "Check if task is still running.")
-                .def("cancel", &H::cancel, "Request cooperative cancellation of the task.")
+                .def("cancel", &H::cancel,
+                     "Request cooperative cancellation; True when the request reached a running task. The solve "
+                     "stops between refinement rounds (queued sweeps drain), is_done() becomes True, the status "
+                     "reads 'cancelled'.")
+                .def("was_cancelled", &H::was_cancelled, "True when the task stopped on a cancel() request.")
                 .def("get_levels", &H::get_levels,
                      "Vibrational level energies [curve][level - min_level] (NaN where a level was not found).")
                 .def("get_level_counts", &H::get_level_counts, "Number of levels below the search ceiling, per curve.")
@@ -249,6 +253,9 @@ namespace epseon::gpu::python {
                  "Submit task for execution. Will raise RuntimeError upon receiving not fully configured "
                  "TaskConfigurator.")
             .doc() = "Interface to particular CUDA device.";
+
+        m.def("release_device_memory", &cpp::detail::trim_context_pool,
+              "Destroy the idle pooled CUDA contexts of finished tasks (their device memory is returned).");
 
         py::class_<EpseonComputeContext>(m, "EpseonComputeContext")
             .def_static("create", &EpseonComputeContext::create, "Create instance of the compute context.")

@@ -123,7 +123,9 @@ void potential_source() {
         bool refused = false;
         try {
             const std::vector<std::string> bad{"/tmp/epseon_b200_test_curve.txt.npy"};
-            PotentialFileLoader<FP>(bad).get_potential_data();
+            PotentialFileLoader<FP> missing(bad);
+            CHECK(missing.get_potential_data().empty() && !missing.get_last_error().empty());
+            missing.load();
         } catch (const std::runtime_error&) {
             refused = true;
         }

@@ -12,6 +12,7 @@
 #include "numerov_cbank.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +107,13 @@ struct eps_ctx {
     DevBuf<int32_t>  d_wfbexp, d_wfinexp;
     DevBuf<uint32_t> d_wfmatch;
 
+    // cooperative cancellation (eps_request_stop): host flag + a device copy the sweep kernels test
+    // when a CTA starts, so the launches already queued behind a stop request drain in microseconds
+    std::atomic<int> stop{0};
+    int*             d_stop      = nullptr;
+    int*             h_stop_src  = nullptr;  // pinned {0, 1}
+    cudaStream_t     stop_stream = nullptr;
+
     // measurement
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEvent_t ev[kEventPairs][2];
@@ -114,6 +122,19 @@ struct eps_ctx {
     void*       d_flush = nullptr;
     int         force_ept = 0, force_stride = 0, force_warps = 0;  // tuning overrides (EPS_FORCE_EPT / EPS_FORCE_STRIDE)
 };
+
+// Device buffers of a context.  RESIDENT: what the uploaded curves need to stay usable (tables,
+// curve descriptors, small bookkeeping).  SCRATCH: grow-only work areas that any later call
+// re-reserves on demand (eps_ctx_trim releases them).
+#define EPS_RESIDENT_BUFS(X) \
+    X(d_F) X(d_scale) X(d_prep) X(d_prep_parts) X(d_curves) X(d_J) X(d_rot) X(d_jobs) X(d_jobs_ref) X(d_Elo) X(d_Ehi) \
+    X(d_lo) X(d_hi) X(d_levels) X(d_widths) X(d_state) X(d_jstar) X(d_nbelow) X(d_nactive) X(d_nflag)
+#define EPS_SCRATCH_BUFS(X) \
+    X(d_V) X(d_Vraw) X(d_spl) X(d_E) X(d_mant) X(d_nodes) X(d_exp) \
+    X(d_segXA) X(d_segSA) X(d_segXB) X(d_segSB) X(d_segeA) X(d_segeB) X(d_segnA) \
+    X(d_fixm) X(d_fixE) X(d_fixe) X(d_fixn) X(d_flagged) X(d_jobs_fix) \
+    X(d_cbX) X(d_cbS) X(d_cbexp) X(d_cbnodes) X(d_cbprev) \
+    X(d_wfE) X(d_wfraw) X(d_wfin) X(d_wfpsi) X(d_wfh) X(d_wfdE) X(d_wfbexp) X(d_wfinexp) X(d_wfmatch)
 
 namespace {
 
@@ -136,6 +157,13 @@ int fail(eps_ctx* ctx, int code, const std::string& msg) {
         if (!(cond)) return fail(ctx, code, msg); \
     } while (0)
 
+bool stop_requested(const eps_ctx* ctx) { return ctx->stop.load(std::memory_order_acquire) != 0; }
+
+#define EPS_CHECK_STOP(ctx)                                                                     \
+    do {                                                                                        \
+        if (stop_requested(ctx)) return fail(ctx, EPS_ERR_CANCELLED, "stopped by eps_request_stop"); \
+    } while (0)
+
 int bind(eps_ctx* ctx) {
     if (!ctx) return fail(nullptr, EPS_ERR_INVALID, "null context");
     EPS_CUDA(ctx, cudaSetDevice(ctx->dev));
@@ -146,12 +174,13 @@ int bind(eps_ctx* ctx) {
 int fold_events(eps_ctx* ctx) {
     if (ctx->ev_used == 0) return EPS_OK;
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < ctx->ev_used; i++) {
+    const int n  = ctx->ev_used;
+    ctx->ev_used = 0;  // whatever happens below, the pairs are free again
+    for (int i = 0; i < n; i++) {
         float ms = 0.f;
         EPS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]));
         ctx->stats.sweep_ms += ms;
     }
-    ctx->ev_used = 0;
     return EPS_OK;
 }
 
@@ -183,7 +212,7 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     }
     kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
         ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
-        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2);
+        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2, ctx->d_stop);
     return cudaGetLastError();
 }
 
@@ -273,7 +302,7 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
         cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails>, chunk, d_jobs,
                                            static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
                                            k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, pdl_late, st, out.nodes, kTails ? out.mant : nullptr,
-                                           kTails ? out.expo : nullptr, ctx->d_steps);
+                                           kTails ? out.expo : nullptr, ctx->d_steps, static_cast<const int*>(ctx->d_stop));
         if (e != cudaSuccess) return e;
         ctx->cbank_launches++;
     }
@@ -349,6 +378,7 @@ uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool ta
 
 int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp, bool tails,
                 int stride, uint32_t n_seg, bool fix_flagged, const SweepOut& out) {
+    EPS_REQUIRE(ctx, (nE + 127) / 128 <= 65535u, EPS_ERR_INVALID, "scan path: at most 8 388 480 energies per row");
     const uint32_t tiles_per_seg = (ctx->n_tiles_max + n_seg - 1) / n_seg;
     const size_t   n_so          = static_cast<size_t>(n_jobs) * n_seg * nE;
     EPS_CUDA(ctx, ctx->d_segXA.reserve(n_so));
@@ -368,7 +398,7 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
     else e = launch_sweep_variant<2, 8, 1, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
     EPS_CUDA(ctx, e);
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nflag.p, 0, sizeof(uint32_t), ctx->stream));
-    segment_combine_kernel<<<dim3((nE + 127) / 128, n_jobs), 128, 0, ctx->stream>>>(
+    segment_combine_kernel<<<dim3(n_jobs, (nE + 127) / 128), 128, 0, ctx->stream>>>(
         so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
         ctx->d_nflag.p, ctx->d_flagged.p, cap);
     EPS_CUDA(ctx, cudaGetLastError());
@@ -433,19 +463,24 @@ int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
         int rc = fold_events(ctx);
         if (rc) return rc;
     }
-    cudaEvent_t* pair = ctx->ev[ctx->ev_used++];
+    cudaEvent_t* pair = ctx->ev[ctx->ev_used];
     EPS_CUDA(ctx, cudaEventRecord(pair[0], ctx->stream));
     const int      stride = pick_stride(ctx, t_max);
     const SweepOut out{ctx->d_nodes.p, ctx->d_mant.p, ctx->d_exp.p};
+    // the pair only counts once BOTH events are recorded: a failure in between leaves ev_used alone
+    int rc = EPS_OK;
     if (n_seg >= 2) {
-        if (int rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out)) return rc;
+        rc = launch_scan(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, n_seg, fix_flagged, out);
     } else if (use_cbank(ctx, n_jobs, nE, pack_rows, pack_cta)) {
-        if (int rc = launch_cbank(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out)) return rc;
+        rc = launch_cbank(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out);
     } else {
         const uint32_t pk = ctx->force_ept ? 0 : pack_rows == kFlatRows ? kFlatRows : pack_log2_for(nE, pack_rows, pack_cta);
-        EPS_CUDA(ctx, launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out, pk, pack_cta));
+        const cudaError_t e = launch_sequential(ctx, d_jobs, n_jobs, nE, d_Eexp, tails, stride, out, pk, pack_cta);
+        if (e != cudaSuccess) rc = fail(ctx, EPS_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
     }
+    if (rc) return rc;
     EPS_CUDA(ctx, cudaEventRecord(pair[1], ctx->stream));
+    ctx->ev_used++;
     ctx->stats.sweep_launches++;
     return EPS_OK;
 }
@@ -473,8 +508,21 @@ int fetch_sweep(eps_ctx* ctx, size_t n, uint32_t* nodes, double* mant, int32_t* 
         EPS_CUDA(ctx, cudaMemcpyAsync(expo, ctx->d_exp.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += n * sizeof(int32_t);
     }
-    if (nodes || mant || expo) EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nodes || mant || expo) {
+        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        EPS_CHECK_STOP(ctx);
+    }
     return EPS_OK;
+}
+
+// The resident state is invalid from the moment a new upload starts until it has fully succeeded:
+// DevBuf::reserve frees before it allocates and the prep kernels overwrite d_F / d_curves, so a
+// failure half-way must not leave the old curve count and curve_info behind.
+void invalidate_resident(eps_ctx* ctx) {
+    ctx->nC = 0;
+    ctx->curves.clear();
+    ctx->h_F.clear();
+    ctx->n_tiles_max = 0;
 }
 
 // Second half of eps_set_potentials*: the tables are in d_V, the scales in d_scale (both on the
@@ -485,6 +533,7 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
     const uint32_t N    = n_points;
     const uint64_t slot = (static_cast<uint64_t>(N) + kTile - 1) / kTile * kTile;
     const size_t   n_f  = static_cast<size_t>(slot) * n_curves;
+    invalidate_resident(ctx);
     EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
     EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
     EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
@@ -508,7 +557,6 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
     EPS_CUDA(ctx, cudaMemcpyAsync(po.data(), ctx->d_prep.p, n_curves * sizeof(PrepOut), cudaMemcpyDeviceToHost, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += n_curves * sizeof(PrepOut);
-    ctx->nC = 0;  // invalid until every curve checked out
     for (uint32_t c = 0; c < n_curves; c++) {
         EPS_REQUIRE(ctx, po[c].status != 1, EPS_ERR_RANGE, "potential table holds a non-finite value");
         EPS_REQUIRE(ctx, po[c].status != 2, EPS_ERR_RANGE, "integration window has fewer than 2 steps");
@@ -610,6 +658,12 @@ int eps_ctx_create(int device, eps_ctx** out) {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_steps), sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemsetAsync(ctx->d_steps, 0, sizeof(unsigned long long), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pinned), 4096)) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_stop), sizeof(int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemsetAsync(ctx->d_stop, 0, sizeof(int), ctx->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stop_src), 2 * sizeof(int))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    ctx->h_stop_src[0] = 0;
+    ctx->h_stop_src[1] = 1;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stop_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if (const char* fe = std::getenv("EPS_FORCE_EPT")) {
         const int v = std::atoi(fe);
         ctx->force_ept = (v == 1 || v == 2 || v == 4) ? v : 0;
@@ -627,47 +681,19 @@ int eps_ctx_destroy(eps_ctx* ctx) {
     if (!ctx) return EPS_OK;
     if (ctx->dev >= 0 && cudaSetDevice(ctx->dev) == cudaSuccess) {
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-        ctx->d_F.release();
-        ctx->d_V.release();
-        ctx->d_scale.release();
-        ctx->d_spl.release();
-        ctx->d_prep_parts.release();
-        ctx->d_Vraw.release(); ctx->d_rot.release(); ctx->d_J.release();
-        ctx->d_prep.release();
-        ctx->d_curves.release();
-        ctx->d_jobs.release();
-        ctx->d_jobs_ref.release();
-        ctx->d_E.release();
-        ctx->d_mant.release();
-        ctx->d_Elo.release();
-        ctx->d_Ehi.release();
-        ctx->d_nodes.release();
-        ctx->d_exp.release();
-        ctx->d_lo.release();
-        ctx->d_hi.release();
-        ctx->d_levels.release();
-        ctx->d_widths.release();
-        ctx->d_state.release();
-        ctx->d_jstar.release();
-        ctx->d_nbelow.release();
-        ctx->d_nactive.release();
-        ctx->d_segXA.release(); ctx->d_segSA.release(); ctx->d_segXB.release(); ctx->d_segSB.release();
-        ctx->d_fixm.release(); ctx->d_fixE.release(); ctx->d_segeA.release(); ctx->d_segeB.release(); ctx->d_fixe.release();
-        ctx->d_segnA.release(); ctx->d_fixn.release(); ctx->d_nflag.release(); ctx->d_flagged.release();
-        ctx->d_jobs_fix.release();
-        ctx->d_cbX.release(); ctx->d_cbS.release(); ctx->d_cbexp.release(); ctx->d_cbnodes.release(); ctx->d_cbprev.release();
-        ctx->d_wfE.release();
-        ctx->d_wfraw.release();
-        ctx->d_wfin.release();
-        ctx->d_wfpsi.release();
-        ctx->d_wfh.release();
-        ctx->d_wfdE.release();
-        ctx->d_wfbexp.release();
-        ctx->d_wfinexp.release();
-        ctx->d_wfmatch.release();
+#define EPS_RELEASE(name) ctx->name.release();
+        EPS_RESIDENT_BUFS(EPS_RELEASE)
+        EPS_SCRATCH_BUFS(EPS_RELEASE)
+#undef EPS_RELEASE
         if (ctx->d_steps) cudaFree(ctx->d_steps);
         if (ctx->d_flush) cudaFree(ctx->d_flush);
         if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        if (ctx->stop_stream) {
+            cudaStreamSynchronize(ctx->stop_stream);
+            cudaStreamDestroy(ctx->stop_stream);
+        }
+        if (ctx->d_stop) cudaFree(ctx->d_stop);
+        if (ctx->h_stop_src) cudaFreeHost(ctx->h_stop_src);
         if (ctx->t0) cudaEventDestroy(ctx->t0);
         if (ctx->t1) cudaEventDestroy(ctx->t1);
         for (auto& pr : ctx->ev)
@@ -676,6 +702,62 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
+    return EPS_OK;
+}
+
+// Cancellation.  eps_request_stop may be called from ANY thread while another thread is inside a
+// compute call on the same context (it is what TaskHandle::cancel binds, reference
+// task_handle.hpp:136-144): it raises the host flag -- tested by eps_solve_levels* between
+// refinement rounds and by every sweep before it returns -- and copies it to the device on a side
+// stream, where every sweep CTA tests it on entry, so sweeps already queued (the 51 chunk launches
+// of a 2^24-energy sweep) drain at once.  The interrupted call returns EPS_ERR_CANCELLED and its
+// outputs are unspecified.  The flag stays up until eps_reset_stop.
+int eps_request_stop(eps_ctx* ctx) {
+    if (!ctx) return fail(nullptr, EPS_ERR_INVALID, "null context");
+    ctx->stop.store(1, std::memory_order_release);
+    if (cudaSetDevice(ctx->dev) == cudaSuccess && ctx->d_stop && ctx->stop_stream)
+        cudaMemcpyAsync(ctx->d_stop, ctx->h_stop_src + 1, sizeof(int), cudaMemcpyHostToDevice, ctx->stop_stream);
+    return EPS_OK;
+}
+
+int eps_reset_stop(eps_ctx* ctx) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stop_stream));
+    ctx->stop.store(0, std::memory_order_release);
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stop, ctx->h_stop_src, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    return EPS_OK;
+}
+
+// Memory held by a context's grow-only device buffers, and a way to give it back: after one large
+// or wavefunction task a context keeps GBs of scratch.  eps_ctx_trim releases every scratch buffer
+// (the next call re-reserves what it needs); with drop_potentials != 0 also the resident tables
+// (the context then needs a new eps_set_potentials*).
+int eps_ctx_device_bytes(eps_ctx* ctx, uint64_t* bytes) {
+    if (!ctx || !bytes) return fail(ctx, EPS_ERR_INVALID, "null argument");
+    uint64_t n = 0;
+#define EPS_COUNT(name) n += static_cast<uint64_t>(ctx->name.cap) * sizeof(*ctx->name.p);
+    EPS_RESIDENT_BUFS(EPS_COUNT)
+    EPS_SCRATCH_BUFS(EPS_COUNT)
+#undef EPS_COUNT
+    if (ctx->d_flush) n += kFlushBytes;
+    *bytes = n;
+    return EPS_OK;
+}
+
+int eps_ctx_trim(eps_ctx* ctx, int drop_potentials) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#define EPS_RELEASE(name) ctx->name.release();
+    EPS_SCRATCH_BUFS(EPS_RELEASE)
+    if (drop_potentials) {
+        invalidate_resident(ctx);
+        EPS_RESIDENT_BUFS(EPS_RELEASE)
+    }
+#undef EPS_RELEASE
+    if (ctx->d_flush) {
+        cudaFree(ctx->d_flush);
+        ctx->d_flush = nullptr;
+    }
     return EPS_OK;
 }
 
@@ -696,6 +778,7 @@ int eps_set_potentials(eps_ctx* ctx, const double* V, uint32_t n_curves, uint32_
     for (uint32_t c = 0; c < n_curves; c++)
         EPS_REQUIRE(ctx, std::isfinite(scale[c]) && scale[c] > 0.0, EPS_ERR_INVALID, "scale must be finite and positive");
     const size_t n_v = static_cast<size_t>(n_points) * n_curves;
+    invalidate_resident(ctx);
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     EPS_CUDA(ctx, ctx->d_V.reserve(n_v));
     EPS_CUDA(ctx, ctx->d_scale.reserve(n_curves));
@@ -719,6 +802,7 @@ int eps_set_potentials_rot(eps_ctx* ctx, const double* V, uint32_t n_curves, uin
     for (uint32_t j = 0; j < n_J; j++) EPS_REQUIRE(ctx, J[j] < (1u << 26), EPS_ERR_INVALID, "J must be below 2^26");
     const uint32_t n_eff = n_curves * n_J;
     const size_t   n_raw = static_cast<size_t>(n_points) * n_curves, n_v = static_cast<size_t>(n_points) * n_eff;
+    invalidate_resident(ctx);
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     EPS_CUDA(ctx, ctx->d_Vraw.reserve(n_raw));
     EPS_CUDA(ctx, ctx->d_rot.reserve(3 * static_cast<size_t>(n_curves)));
@@ -910,6 +994,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->stats.d2h_bytes += sizeof(uint32_t);
         const uint32_t n_active = ctx->h_pinned[0];
+        EPS_CHECK_STOP(ctx);
         if (n_active == 0) break;
         const uint32_t n_rows = flat ? n_active : n_dense;
         if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows,
@@ -941,6 +1026,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         ctx->stats.d2h_bytes += nC * sizeof(uint32_t);
     }
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EPS_CHECK_STOP(ctx);
     return EPS_OK;
 }
 

@@ -45,7 +45,7 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
                      const uint64_t out_stride, const double scale, const uint32_t len, const int first,
                      const int last, const int pdl_late, const CbState st, uint32_t* __restrict__ nodes_out,
                      double* __restrict__ mant_out, int32_t* __restrict__ exp_out,
-                     unsigned long long* __restrict__ steps_done) {
+                     unsigned long long* __restrict__ steps_done, const int* __restrict__ stop_flag) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
     constexpr uint32_t kPerCta = kThreads * kEpt;
     // Programmatic dependent launch: the chunk launches of one sweep are chained with
@@ -58,6 +58,7 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
     // is then resident only while this chunk drains, which is all a one-wave sweep can overlap.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pdl_late == 0) asm volatile("griddepcontrol.launch_dependents;");
+    if (*stop_flag != 0) return;  // eps_request_stop: the remaining chunk launches of the sweep drain at once
     const uint32_t job_idx = blockIdx.x / chunks_per_job;
     const uint32_t chunk   = blockIdx.x - job_idx * chunks_per_job;
     const Job      job     = jobs[job_idx];

@@ -217,11 +217,12 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                      int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done,
                      const uint32_t n_seg, const uint32_t tiles_per_seg, const SegOut seg_out,
-                     const uint32_t pack_log2) {
+                     const uint32_t pack_log2, const int* __restrict__ stop_flag) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
     static_assert(!kScan || (kEpt == 2 && !kTails), "scan mode: two basis chains per energy");
     constexpr uint32_t kPerCta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
     constexpr int      kCnt    = kScan ? 1 : kEpt;  // chains whose sign flips are counted
+    if (*stop_flag != 0) return;  // eps_request_stop: queued sweeps drain without marching (uniform per CTA)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double*   ring  = reinterpret_cast<double*>(smem_raw);
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kStages);
@@ -459,8 +460,8 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
                                        uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                                        int32_t* __restrict__ exp_out, uint32_t* __restrict__ n_flagged,
                                        uint2* __restrict__ flagged, uint32_t flagged_cap) {
-    const uint32_t row = blockIdx.y;
-    const uint32_t j   = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t row = blockIdx.x;  // rows on grid.x (up to 2^31 - 1 of them), energy blocks on grid.y
+    const uint32_t j   = blockIdx.y * blockDim.x + threadIdx.x;
     if (row >= n_jobs || j >= jobs[row].nE) return;
     constexpr double kEta = 5.820766091346741e-11;  // 2^-34
     double   X = 1.0, D = -1.0, rho = 0.0;

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EPS_ABI_VERSION 1
+#define EPS_ABI_VERSION 2
 
 enum {
     EPS_OK          = 0,
@@ -45,7 +45,8 @@ enum {
     EPS_ERR_CUDA    = 2, /* CUDA runtime failure / no device               */
     EPS_ERR_RANGE   = 3, /* energy or table outside the validity window    */
     EPS_ERR_STATE   = 4, /* call order (e.g. sweep before set_potentials)  */
-    EPS_ERR_NOMEM   = 5
+    EPS_ERR_NOMEM   = 5,
+    EPS_ERR_CANCELLED = 6 /* interrupted by eps_request_stop                */
 };
 
 typedef struct eps_ctx eps_ctx;
@@ -113,6 +114,21 @@ int         eps_ctx_create(int device, eps_ctx** out);
 int         eps_ctx_destroy(eps_ctx* ctx);
 const char* eps_last_error(const eps_ctx* ctx);
 int         eps_sync(eps_ctx* ctx);
+/* Device memory held by the context's grow-only buffers; eps_ctx_trim releases the scratch ones
+ * (and, with drop_potentials != 0, the resident tables too: a new eps_set_potentials* is then
+ * needed).  The reference frees its VMA buffers when run() returns (vibwa.hpp:236-283); a pooled
+ * context is trimmed before it is parked. */
+int         eps_ctx_device_bytes(eps_ctx* ctx, uint64_t* bytes);
+int         eps_ctx_trim(eps_ctx* ctx, int drop_potentials);
+
+/* ---- cooperative cancellation (binds TaskHandle<FP>::cancel, task_handle.hpp:136-144; the
+ * reference polls its stop_token three times in run(), vibwa.hpp:606,617,632).
+ * eps_request_stop is the ONE entry point that may be called from another thread while a compute
+ * call is running on the context: eps_solve_levels* test the flag between refinement rounds, every
+ * sweep before it returns, and sweep CTAs on entry (queued launches drain in microseconds).  The
+ * interrupted call returns EPS_ERR_CANCELLED; the flag stays up until eps_reset_stop. */
+int eps_request_stop(eps_ctx* ctx);
+int eps_reset_stop(eps_ctx* ctx);
 
 /* ---- potentials (replaces the staging->device upload the reference plans in
  * ShaderResources, vibwa.hpp:57-234; input is the table that
