@@ -1,35 +1,44 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the Numerov hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c3|c4|c5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload all|c2|c3|c4|c5] [--impl reference]
 
 Metric: FP64 Numerov grid-steps x trial-energies per second (whole job, all ranks), plus
-time-to-all-levels.  One "step" = one complete pass of the hot path over the workload:
+time-to-all-levels.  One "step" = one complete pass of the hot path over the workload.
 
-  c2 (default; BASELINE.json configs[1]):  Morse (H2-like) potential, 100 000-point grid,
-      coarse sweep of 65 536 trial energies, bracketing, k-section refinement of all 17 bound
-      levels to 1e-10 relative.  At N GPUs each rank solves its own (slightly perturbed) curve
-      -- sharded by potential curve, no data-path collective, weak scaling -- and the located
-      levels (17 doubles per rank) are gathered to rank 0 over NCCL.
-  c3 (BASELINE.json configs[2]):  tabulated "ab initio" curve (64 knots, natural cubic spline
-      resampled to 1 000 000 points), sweep of 4096 trial energies -- the few-energy / long-grid
-      regime served by the transfer-matrix scan path; replicas at N > 1 (it does not shard).
-  c4 (BASELINE.json configs[3]):  4096 perturbed Morse / LJ curves x 1024 coarse energies each,
-      levels 0..7 refined to 1e-10; curves sharded over the ranks (strong scaling).
-  c5 (BASELINE.json configs[4]):  dense sweep of 2^24 trial energies on a 200 000-point grid,
-      energy-range sharded over the ranks (strong scaling); node-count checksums gathered.
+Headline (`--workload all`, the default): **c5** = BASELINE.json configs[4], the north star's
+"largest energy sweep": 2^24 trial energies on a 200 000-point grid, ENERGY-RANGE SHARDED over the
+ranks (strong scaling: the job is fixed, every rank sweeps a contiguous slice of ONE global uniform
+grid, reproduced bit for bit; no data-path collective).  It fits one GPU (0.75 s per step), so the
+N = 1 line is the same job.  The other BASELINE configs ride in the same JSON line as
+`sub_records` (each measured like the headline, with min(K, 10) timed steps):
 
-value  = steps executed by all ranks / max-over-ranks CUDA-event time, potentials resident in HBM.
-e2e    = same metric through the host-buffer C ABI (eps_set_potentials + eps_solve_levels with
-         host pointers: table upload and result download inside the timed region).
-roofline.bound = "fp64": the path is FP64-pipe bound; the denominator is
-         a DFMA probe measured in this process because MEASURED_PEAKS.json has no FP64 entry.
+  c2 (configs[1]):  Morse (H2-like) 100 000-point grid, 65 536-energy coarse sweep, bracketing,
+      k-section refinement of all 17 bound levels to 1e-10 -> time_to_all_levels_ms.  One (slightly
+      perturbed) curve per rank: curve-sharded, weak scaling; the 17 levels of every rank are
+      gathered to rank 0.
+  c3 (configs[2]):  tabulated curve (64 knots, natural cubic spline) on a 1 000 000-point grid,
+      4096 energies -- the few-energy / long-grid regime of the transfer-matrix scan path;
+      replicas at N > 1 (it does not shard).
+  c4 (configs[3]):  4096 perturbed Morse / LJ curves x 1024 coarse energies, levels 0..7 refined
+      to 1e-10; curves sharded over the ranks (strong scaling), levels gathered to rank 0.
+
+`--workload cX` runs that workload alone as the headline (what the committed profiles use).
+
+value  = steps executed by all ranks / sum over the K steps of the max-over-ranks CUDA-event time,
+         potentials resident in HBM.
+e2e    = same metric through the host-buffer C ABI (eps_set_potentials + eps_solve_levels /
+         eps_sweep_grid with host pointers: table upload and result download inside the timed region).
+roofline.bound = "fp64": the path is FP64-pipe bound; the denominator is a
+         DFMA probe measured in this process because MEASURED_PEAKS.json has no FP64 entry
+         (`measured_peaks` repeats it in that file's form).
 cpu_baseline / --impl reference: the build's own CPU oracle (the reference repository has no
          implementation of this path -- SURVEY.md section 0), OpenMP over all host threads.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -48,30 +57,42 @@ from tests import workloads as W  # noqa: E402
 METRIC = "numerov_grid_steps_x_trial_energies_per_s"
 _REAL_STDOUT = 1  # fd of the run's own stdout (main() moves fd 1 to stderr)
 FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
-CPU_SAMPLE_SECONDS = 10.0  # bounded CPU sample of the same workload (cpu_baseline)
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
-
-# dominant kernel per workload + its DRAM traffic per launch from the committed `ncu --set full`
-# captures (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1g_ncu.md, r1c_scan_ncu.md,
-# r1g_c4_ncu.md, r1e_c5_cbank_ncu.md).  Algorithmic bytes = every resident curve's coefficient table
-# once per launch (8 B x grid steps x curves).
-#   c4: one launch streams the tables of all 4096 curves (measured on the 1-GPU shape).
-#   c5: a "launch" of the bench is one sweep = 51 chunk launches of the constant-bank kernel; each
-#       carries the per-energy state (28 B read + 28 B written per energy) through HBM by design:
-#       881 MB per chunk launch at 2^24 energies = 58 GB/s, under 1 % of the HBM peak.
-KERNEL_META = {
-    "c2": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)", 839_936, "profiles/r1g_ncu.md"),
-    "c3": ("eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)", 8_028_416, "profiles/r1c_scan_ncu.md"),
-    "c4": ("eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)", 348_472_832,
-           "profiles/r1g_c4_ncu.md (1-GPU shape: 4096 curves per launch)"),
-    "c5": ("eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)", 51 * 881_415_680,
-           "profiles/r1e_c5_cbank_ncu.md (1-GPU shape: 51 chunk launches x 881 MB of per-energy state carry)"),
-}
+SUB_STEPS = 10  # timed steps of a sub-record (min with --steps)
 
 C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
 C3 = dict(N=1_000_000, nE=4096)
 C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=32, rel_tol=1e-10, max_rounds=8, v_max=7)
-C5 = dict(N=200_000, nE=1 << 24)
+C5 = dict(N=200_000, nE=1 << 24, check_sample=4096)
+
+KERNELS = {
+    "c2": "eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)",
+    "c3": "eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)",
+    "c4": "eps::numerov_sweep_kernel<EPT=4|2,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)",
+    "c5": "eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)",
+}
+
+
+def csrc_digest() -> str:
+    """Hash of the kernel sources: ties a committed ncu DRAM-traffic figure to the code it was taken on."""
+    h = hashlib.sha256()
+    for p in sorted((ROOT / "epseon_backend_b200" / "csrc").glob("*.cu*")):
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def kernel_traffic(name: str) -> dict:
+    """dram__bytes_read+write per launch of the workload's dominant kernel, from profiles/traffic.json
+    (written by scripts/summarize_profiles.py from an `ncu --set full` capture).  A figure captured on
+    other kernel sources than the ones now in the tree is reported as stale (traffic: null)."""
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())[name]
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None, "traffic_source": "no capture in profiles/traffic.json"}
+    if t.get("csrc_digest") != csrc_digest():
+        return {"traffic": None, "traffic_stale": t.get("dram_bytes_per_launch"),
+                "traffic_source": f"{t.get('source')} (STALE: captured on csrc {t.get('csrc_digest')}, tree is {csrc_digest()})"}
+    return {"traffic": t["dram_bytes_per_launch"], "traffic_source": t["source"]}
 
 
 def workload_config(name: str) -> dict:
@@ -159,11 +180,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0: float, t1: float) -> dict:
+    def window(self, t0: float, t1: float) -> dict:
+        """Clock record of the wall-clock window [t0, t1] (sampling goes on)."""
         if self.nvml is not None:
-            self._stop = True
-            time.sleep(0.02)
-            sel = [r for r in self.rows if t0 <= r[0] <= t1]
+            time.sleep(0.03)
+            sel = [r for r in list(self.rows) if t0 <= r[0] <= t1]
             reasons = sorted({x for r in sel for x in r[3]})
             return {"sm_mhz": float(np.median([r[1] for r in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
                     "samples": len(sel), "power_w_max": max((r[2] for r in sel), default=None), "reasons": reasons,
@@ -171,9 +192,8 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         mhz, mx, reasons, power = [], None, set(), []
-        for ts, line in self.rows:
+        for ts, line in list(self.rows):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -193,6 +213,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "samples": len(mhz),
                 "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
+    def close(self):
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+
 
 def host_threads() -> int:
     """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU legs run on
@@ -203,107 +228,343 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def dist_setup(n_gpus: int):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return dist, torch, world, rank, local
-    return None, None, 1, 0, 0
+def emit(line: dict) -> None:
+    """The ONE JSON line of the run, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-def cpu_solve_c2(orc, V, s, E_lo, E_hi):
-    F, *_ = orc.prep(V, s)
-    t = time.perf_counter()
-    lev, wid, nb, rounds, steps = orc.solve_levels(F, s, E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"],
-                                                   C2["refine_points"], C2["rel_tol"], C2["max_rounds"])
-    return time.perf_counter() - t, steps, lev
-
-
-def run_reference(args) -> None:
-    """--impl reference: the CPU implementation of the path on the host cores.  The reference
-    repository has none (SURVEY.md section 0), so this times the build's oracle port."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import Oracle
-
-    orc = Oracle(omp=True, threads=host_threads())
-    if args.workload == "c5":
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle port): `--impl reference` and the cpu_baseline object of every record
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(name: str, orc):
+    """-> (one() -> (steps, result), description): a bounded sample of the workload on the host cores."""
+    if name == "c5":
         w = W.c5(C5["N"], C5["nE"])
         F, *_ = orc.prep(w["V"], w["s"])
-        n_steps = F.size
         nE = 1 << 16  # bounded sample of the 2^24-energy sweep; work is exactly linear in nE
         dE = (w["E_hi"] - w["E_lo"]) / (C5["nE"] - 1)
 
         def one():
-            t = time.perf_counter()
-            orc.sweep_uniform(F, w["s"], w["E_lo"], dE * (C5["nE"] // nE), 0, nE, tails=False)
-            return time.perf_counter() - t, n_steps * nE
+            n, _, _ = orc.sweep_uniform(F, w["s"], w["E_lo"], dE * (C5["nE"] // nE), 0, nE, tails=False)
+            return F.size * nE, n
 
-        sample = f"2^16 of the 2^24 energies (every 256th) on the 200k grid, {orc.threads} threads"
-        cfg = workload_config("c5")
-    elif args.workload == "c3":
+        return one, f"2^16 of the 2^24 energies (every 256th) on the 200k grid, {orc.threads} threads, OpenMP oracle"
+    if name == "c3":
         w = W.c3(C3["N"], C3["nE"])
         F, *_ = orc.prep(w["V"], w["s"])
         dE = (w["E_hi"] - w["E_lo"]) / (C3["nE"] - 1)
 
         def one():
-            t = time.perf_counter()
-            orc.sweep_uniform(F, w["s"], w["E_lo"], dE, 0, C3["nE"], tails=False)
-            return time.perf_counter() - t, F.size * C3["nE"]
+            n, _, _ = orc.sweep_uniform(F, w["s"], w["E_lo"], dE, 0, C3["nE"], tails=False)
+            return F.size * C3["nE"], n
 
-        sample = f"the full C3 sweep (4096 energies x 1M-point grid), {orc.threads} threads"
-        cfg = workload_config("c3")
-    elif args.workload == "c4":
-        w = W.c4(64, C4["N"], C4["n_coarse"])
+        return one, f"the full C3 sweep (4096 energies x 1M-point grid), {orc.threads} threads, OpenMP oracle"
+    if name == "c4":
+        n_sample = 64
+        w = W.c4(n_sample, C4["N"], C4["n_coarse"])  # the first 64 curves of the seeded batch
 
         def one():
-            t, steps = time.perf_counter(), 0
-            for c in range(64):
+            steps, levs = 0, []
+            for c in range(n_sample):
                 F, *_ = orc.prep(w["V"][c], w["s"])
-                steps += orc.solve_levels(F, w["s"], w["E_lo"][c], w["E_hi"][c], C4["n_coarse"], 0, C4["v_max"],
-                                          C4["refine_points"], C4["rel_tol"], C4["max_rounds"])[4]
-            return time.perf_counter() - t, steps
+                lv, _, _, _, st = orc.solve_levels(F, w["s"], w["E_lo"][c], w["E_hi"][c], C4["n_coarse"], 0, C4["v_max"],
+                                                   C4["refine_points"], C4["rel_tol"], C4["max_rounds"])
+                steps += st
+                levs.append(lv)
+            return steps, np.array(levs)
 
-        sample = f"64 of the 4096 curves (full level solve each), {orc.threads} threads"
-        cfg = workload_config("c4")
-    else:
-        V, s, E_lo, E_hi, _ = rank_curve(0)
+        return one, f"{n_sample} of the 4096 curves (full level solve each), {orc.threads} threads, OpenMP oracle"
+    V, s, E_lo, E_hi, _ = rank_curve(0)
+    F, *_ = orc.prep(V, s)
 
-        def one():
-            dt, steps, _ = cpu_solve_c2(orc, V, s, E_lo, E_hi)
-            return dt, steps
+    def one():
+        lev, _, _, _, steps = orc.solve_levels(F, s, E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
+                                               C2["rel_tol"], C2["max_rounds"])
+        return steps, lev
 
-        sample = f"full C2 solve (coarse 65536 + refinement of 17 levels), {orc.threads} threads"
-        cfg = workload_config("c2")
+    return one, f"the full C2 solve (coarse 65536 + refinement of 17 levels), {orc.threads} threads, OpenMP oracle"
+
+
+def cpu_timed(fn, min_seconds: float):
+    """Repeat fn() -> (steps, result) until min_seconds of CPU work; -> (steps/s, seconds, reps, first result)."""
+    tot_t, tot_s, reps, first = 0.0, 0.0, 0, None
+    while tot_t < min_seconds or reps == 0:
+        t0 = time.perf_counter()
+        st_c, r = fn()
+        tot_t += time.perf_counter() - t0
+        tot_s += st_c
+        reps += 1
+        first = r if first is None else first
+    return tot_s / tot_t, tot_t, reps, first
+
+
+def run_reference(args) -> None:
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference
+    repository has none (SURVEY.md section 0), so this times the build's oracle port."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import Oracle
+
+    name = "c5" if args.workload == "all" else args.workload
+    orc = Oracle(omp=True, threads=host_threads())
+    one, sample = cpu_sample(name, orc)
     for _ in range(args.warmup):
         one()
     tot_t = tot_s = 0.0
     for _ in range(args.steps):
-        dt, st = one()
-        tot_t += dt
+        t0 = time.perf_counter()
+        st, _ = one()
+        tot_t += time.perf_counter() - t0
         tot_s += st
     val = tot_s / tot_t
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
-        "higher_is_better": True, "scaling": "strong" if args.workload in ("c4", "c5") else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": orc.threads, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "strong" if name in ("c4", "c5") else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(name),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": orc.threads, "kind": "port", "sample": "each step = " + sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference repo has no implementation of this path; this is the build's CPU oracle (port)",
     })
 
 
-def emit(line: dict) -> None:
-    """The ONE JSON line of the run, written to the process's original stdout."""
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+# ------------------------------------------------------------------------------------------------
+# Rank plumbing: torch.distributed is used for the rendezvous, the barrier and the reductions of
+# the timing scalars only
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = self.torch = None
+        self._bufs = {}
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist, self.torch = dist, torch
+
+    def barrier(self, ctx):
+        ctx.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce_vec(self, values, op: str) -> np.ndarray:
+        v = np.asarray(values, dtype=np.float64)
+        if self.dist is None:
+            return v
+        t = self.torch.tensor(v, device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def gather(self, arr: np.ndarray):
+        """Gather a small per-rank result to rank 0 (the only inter-GPU traffic of the path): pinned
+        staging, one all-gather over NCCL, one copy back."""
+        if self.dist is None:
+            return [arr]
+        torch, dist = self.torch, self.dist
+        arr = np.ascontiguousarray(arr)
+        key = (arr.shape, arr.dtype.str)
+        if key not in self._bufs:
+            h_in = torch.from_numpy(np.empty_like(arr)).pin_memory()
+            d_in = torch.empty_like(h_in, device="cuda")
+            d_out = torch.empty((self.world,) + tuple(arr.shape), dtype=h_in.dtype, device="cuda")
+            h_out = torch.empty(d_out.shape, dtype=h_in.dtype).pin_memory()
+            self._bufs[key] = (h_in, d_in, d_out, h_out)
+        h_in, d_in, d_out, h_out = self._bufs[key]
+        h_in.copy_(torch.from_numpy(arr))
+        d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in)
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [h_out[r].numpy().copy() for r in range(self.world)] if self.rank == 0 else None
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# Workloads on the device
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """step_resident / step_e2e / digest of one BASELINE config on this rank's context."""
+
+    def __init__(self, name: str, ctx, comm: Comm):
+        from epseon_backend_b200 import multi
+
+        self.name, self.ctx, self.cfg = name, ctx, workload_config(name)
+        world, rank = comm.world, comm.rank
+
+        def pinned(a: np.ndarray) -> np.ndarray:
+            out = ctx.pinned_empty(np.atleast_2d(a).shape, np.float64)
+            out[...] = a
+            return out
+
+        if name == "c2":
+            V, s, E_lo, E_hi, _ = rank_curve(rank)
+            self.V, self.s, self.scaling = pinned(V), s, "weak"
+            self.resident = lambda: ctx.solve_levels(E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
+                                                     C2["rel_tol"], C2["max_rounds"])
+            self.e2e_tail = self.resident
+            self.digest = lambda res: res[0][0]  # 17 level energies
+        elif name == "c3":
+            w = W.c3(C3["N"], C3["nE"])
+            self.w, self.V, self.s, self.scaling = w, pinned(w["V"]), w["s"], "weak"
+            self.resident = lambda: ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=False, tails=False)
+            self.e2e_tail = lambda: ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
+            self.digest = lambda res: np.zeros(1)
+        elif name == "c4":
+            w = W.c4(C4["nC"], C4["N"], C4["n_coarse"])
+            sl = multi.curve_shard(C4["nC"], world, rank)
+            E_lo4, E_hi4 = np.ascontiguousarray(w["E_lo"][sl]), np.ascontiguousarray(w["E_hi"][sl])
+            self.V, self.s, self.scaling, self.curves = pinned(w["V"][sl]), w["s"], "strong", sl
+            self.resident = lambda: ctx.solve_levels(E_lo4, E_hi4, C4["n_coarse"], 0, C4["v_max"], C4["refine_points"],
+                                                     C4["rel_tol"], C4["max_rounds"])
+            self.e2e_tail = self.resident
+            self.digest = lambda res: res[0]  # [curves of this rank][8] level energies
+        else:
+            w = W.c5(C5["N"], C5["nE"])
+            sl = multi.curve_shard(C5["nE"], world, rank)  # contiguous slice of the global energy grid
+            self.j0, self.per = sl.start, sl.stop - sl.start
+            self.dE = float(multi.global_step(w["E_lo"], w["E_hi"], C5["nE"]))
+            self.w, self.V, self.s, self.scaling = w, pinned(w["V"]), w["s"], "strong"
+            self.resident = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=False, tails=False)
+            self.e2e_tail = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=True, tails=False)  # 4 B/energy D2H
+            self.digest = lambda res: np.zeros(1)
+        ctx.set_potentials(self.V, self.s)
+        self.n_steps = ctx.curve_info(0).n_steps
+
+    def e2e(self):
+        self.ctx.set_potentials(self.V, self.s)  # host table -> H2D -> preparation on the device
+        return self.e2e_tail()  # ... -> results D2H
+
+
+def timed_run(wl: Workload, comm: Comm, step_fn, k: int):
+    """K steps; CUDA events on the ctx stream around each step (incl. the gather of its result to
+    rank 0); L2 flushed between steps; -> (per-step ms of THIS rank, last results, last gathered digest)."""
+    ctx, ms, results, digest = wl.ctx, [], None, None
+    for _ in range(k):
+        ctx.l2_flush()
+        comm.barrier(ctx)
+        ctx.timer_start()
+        results = step_fn()
+        digest = comm.gather(wl.digest(results))
+        ms.append(ctx.timer_stop())
+    comm.barrier(ctx)
+    return ms, results, digest
+
+
+def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmup: int, fp64_peak: float,
+            cpu_seconds: float) -> dict | None:
+    """One record (headline or sub-record): resident rate, e2e rate, roofline of the dominant kernel,
+    clocks, CPU oracle beside it, parity flags.  Returned on rank 0 only."""
+    wl = Workload(name, ctx, comm)
+    for _ in range(warmup):
+        comm.gather(wl.digest(wl.resident()))
+    ctx.sync()
+
+    # ---- timed: resident ----
+    comm.barrier(ctx)
+    ctx.stats_reset()
+    t_wall0 = time.time()
+    ms_rank, res, digest = timed_run(wl, comm, wl.resident, steps)
+    t_wall1 = time.time()
+    st = ctx.stats()
+    clocks = sampler.window(t_wall0, t_wall1)
+    ms_res = float(np.sum(comm.reduce_vec(ms_rank, "max")))  # per step: max over ranks; summed over the K steps
+    steps_rank = float(st.grid_steps)
+    steps_all = float(comm.reduce_vec([steps_rank], "sum")[0])
+    value = steps_all / (ms_res * 1e-3)
+    sweep_rate = steps_rank / (st.sweep_ms * 1e-3)  # this rank's dominant kernel, averaged over its launches
+    launches = int(st.sweep_launches + st.other_launches)
+
+    # ---- timed: end-to-end through the host-buffer C ABI ----
+    for _ in range(2):
+        wl.e2e()
+    comm.barrier(ctx)
+    ctx.stats_reset()
+    ms_rank2, res2, _ = timed_run(wl, comm, wl.e2e, steps)
+    st2 = ctx.stats()
+    ms_e2e = float(np.sum(comm.reduce_vec(ms_rank2, "max")))
+    steps2 = float(comm.reduce_vec([float(st2.grid_steps)], "sum")[0])
+
+    # ---- c5: seeded-sample oracle check at FULL size (every rank checks its own slice) ----
+    c5_same = None
+    if name == "c5":
+        from oracle import Oracle
+
+        rng = np.random.default_rng(5000 + comm.rank)
+        idx = np.unique(np.concatenate([[0, wl.per - 1], rng.integers(0, wl.per, C5["check_sample"] - 2)]))
+        E = wl.w["E_lo"] + (wl.j0 + idx).astype(np.float64) * wl.dE  # the device's operations: mul, add
+        orc1 = Oracle(omp=True, threads=max(1, host_threads() // comm.world))
+        F, *_ = orc1.prep(wl.w["V"], wl.s)
+        n_cpu, _, _ = orc1.sweep(F, wl.s, E, tails=False)
+        same = bool(np.array_equal(n_cpu, res2[0][0][idx]))
+        c5_same = bool(comm.reduce_vec([0.0 if same else 1.0], "sum")[0] == 0.0)
+    if comm.rank != 0:
+        return None
+
+    frac = FLOP_PER_STEP * sweep_rate / 1e12 / fp64_peak
+    rec = {
+        "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": comm.world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_res / steps, "higher_is_better": True,
+        "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.cfg,
+        "time_to_all_levels_ms": ms_res / steps if name in ("c2", "c4") else None,
+        "e2e": {"value": steps2 / (ms_e2e * 1e-3), "unit": "steps/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(st2.h2d_bytes // steps), "d2h_bytes_per_step": int(st2.d2h_bytes // steps)},
+        "gpu_launches": launches,
+        "roofline": {
+            "bound": "fp64", "kernel": KERNELS[name],
+            "achieved": FLOP_PER_STEP * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
+            "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_nominal": NOMINAL_FP64_TFLOPS,
+            "frac_of_nominal": FLOP_PER_STEP * sweep_rate / 1e12 / NOMINAL_FP64_TFLOPS,
+            "flop_per_step": FLOP_PER_STEP, "steps_per_s_kernel": sweep_rate,
+            "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
+            "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
+            **kernel_traffic(name),
+            "algorithmic_bytes_per_launch": 8 * int(wl.n_steps) * int(ctx.n_curves),
+        },
+        "clocks": clocks,
+    }
+    if name == "c2":
+        exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+        rec["levels_found"] = int(np.sum(np.isfinite(digest[0])))
+        rec["max_rel_err_vs_analytic_rank0"] = float(np.max(np.abs(digest[0] - exact) / exact))
+    if name == "c3":
+        rec["scan"] = {"launches": ctx.counter(ctx.CNT_SCAN_LAUNCHES), "flagged": ctx.counter(ctx.CNT_SCAN_FLAGGED)}
+    if name == "c5":
+        rec["nodes_bit_identical_to_oracle_full_size_sample"] = c5_same
+        rec["full_size_sample"] = f"{C5['check_sample']} seeded energies of every rank's slice of the 2^24 (incl. both slice ends)"
+    if cpu_seconds > 0:
+        from oracle import Oracle
+
+        orc = Oracle(omp=True, threads=host_threads())
+        one, sample = cpu_sample(name, orc)
+        rate, secs, reps, first = cpu_timed(one, cpu_seconds)
+        cb = {"value": rate, "unit": "steps/s", "cores": orc.threads, "kind": "port",
+              "sample": f"{sample}, repeated {reps}x", "seconds": secs}
+        if name == "c2":
+            cb["levels_bit_identical_to_gpu"] = bool(np.array_equal(first.view(np.uint64), digest[0].view(np.uint64)))
+        elif name == "c4":
+            cb["levels_bit_identical_to_gpu"] = bool(np.array_equal(first.view(np.uint64),
+                                                                    digest[0][: first.shape[0]].view(np.uint64)))
+        elif name == "c3":
+            n_gpu = res2[0][0]
+            cb["nodes_bit_identical_to_gpu"] = bool(np.array_equal(first, n_gpu))
+        else:
+            n_gpu = res2[0][0]  # rank 0's slice starts at global index 0: every 256th energy of the sample lies on the grid
+            stride = C5["nE"] // (1 << 16)
+            k = min(first.size, (n_gpu.size + stride - 1) // stride)
+            cb["nodes_bit_identical_to_gpu"] = bool(np.array_equal(first[:k], n_gpu[::stride][:k]))
+        rec["cpu_baseline"] = cb
+    return rec
 
 
 def main() -> None:
@@ -317,7 +578,7 @@ def main() -> None:
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=["c2", "c3", "c4", "c5"], default="c2")
+    ap.add_argument("--workload", choices=["all", "c2", "c3", "c4", "c5"], default="all")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -328,298 +589,36 @@ def main() -> None:
 
     import __graft_entry__ as ge
 
-    dist, torch, world, rank, local = dist_setup(args.gpus)
-    if rank == 0:
+    comm = Comm()
+    if comm.rank == 0:
         ge.build()
-    if dist is not None:
-        dist.barrier()
+    if comm.dist is not None:
+        comm.dist.barrier()
     from epseon_backend_b200 import cabi
 
-    ctx = cabi.Context(local)
-    sampler = ClockSampler(local)
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def pinned(a: np.ndarray) -> np.ndarray:
-        """The step's input table in page-locked host memory (the e2e leg copies it host -> device
-        inside the timed region, every step)."""
-        out = ctx.pinned_empty(np.atleast_2d(a).shape, np.float64)
-        out[...] = a
-        return out
-
-    if args.workload == "c2":
-        V, s, E_lo, E_hi, (De, a) = rank_curve(rank)
-        V = pinned(V)
-        ctx.set_potentials(V, s)
-        n_steps = ctx.curve_info(0).n_steps
-
-        def step_resident():
-            return ctx.solve_levels(E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
-                                    C2["rel_tol"], C2["max_rounds"])
-
-        def step_e2e():
-            ctx.set_potentials(V, s)  # host table -> prep -> H2D
-            return step_resident()  # ... -> levels, widths, counts D2H
-
-        cfg = workload_config("c2")
-        scaling = "weak"
-    elif args.workload == "c3":
-        w = W.c3(C3["N"], C3["nE"])
-        V, s = pinned(w["V"]), w["s"]
-        ctx.set_potentials(V, s)
-        n_steps = ctx.curve_info(0).n_steps
-        dE = (w["E_hi"] - w["E_lo"]) / (C3["nE"] - 1)
-
-        def step_resident():
-            return ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=False, tails=False)
-
-        def step_e2e():
-            ctx.set_potentials(V, s)
-            n, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
-            return n
-
-        cfg = workload_config("c3")
-        scaling = "weak"
-    elif args.workload == "c4":
-        w = W.c4(C4["nC"], C4["N"], C4["n_coarse"])
-        per = C4["nC"] // world
-        sl = slice(rank * per, (rank + 1) * per)
-        V, s = pinned(w["V"][sl]), w["s"]
-        E_lo4, E_hi4 = np.ascontiguousarray(w["E_lo"][sl]), np.ascontiguousarray(w["E_hi"][sl])
-        ctx.set_potentials(V, s)
-        n_steps = ctx.curve_info(0).n_steps
-
-        def step_resident():
-            return ctx.solve_levels(E_lo4, E_hi4, C4["n_coarse"], 0, C4["v_max"], C4["refine_points"], C4["rel_tol"],
-                                    C4["max_rounds"])
-
-        def step_e2e():
-            ctx.set_potentials(V, s)
-            return step_resident()
-
-        cfg = workload_config("c4")
-        scaling = "strong"
-    else:
-        w = W.c5(C5["N"], C5["nE"])
-        ctx.set_potentials(w["V"], w["s"])
-        n_steps = ctx.curve_info(0).n_steps
-        from epseon_backend_b200 import multi
-
-        sl = multi.curve_shard(C5["nE"], world, rank)  # contiguous slice of the global energy grid
-        j0, per = sl.start, sl.stop - sl.start
-        dE = float(multi.global_step(w["E_lo"], w["E_hi"], C5["nE"]))
-        V, s = pinned(w["V"]), w["s"]
-
-        def step_resident():
-            return ctx.sweep_grid(w["E_lo"], dE, j0, per, nodes=False, tails=False)
-
-        def step_e2e():
-            ctx.set_potentials(V, s)
-            n, _, _ = ctx.sweep_grid(w["E_lo"], dE, j0, per, nodes=True, tails=False)  # 4 B/energy D2H
-            return n
-
-        cfg = workload_config("c5")
-        scaling = "strong"
-
-    gather_bufs = {}
-
-    def gather_small(arr: np.ndarray):
-        """Gather a small per-rank result (the only inter-GPU traffic of the path): pinned staging,
-        one all-gather over NCCL, one copy back; every rank ends up holding all ranks' rows."""
-        if dist is None:
-            return [arr]
-        arr = np.ascontiguousarray(arr)
-        key = (arr.shape, arr.dtype.str)
-        if key not in gather_bufs:
-            h_in = torch.from_numpy(np.empty_like(arr)).pin_memory()
-            d_in = torch.empty_like(h_in, device="cuda")
-            d_out = torch.empty((world,) + tuple(arr.shape), dtype=h_in.dtype, device="cuda")
-            h_out = torch.empty(d_out.shape, dtype=h_in.dtype).pin_memory()
-            gather_bufs[key] = (h_in, d_in, d_out, h_out)
-        h_in, d_in, d_out, h_out = gather_bufs[key]
-        h_in.copy_(torch.from_numpy(arr))
-        d_in.copy_(h_in, non_blocking=True)
-        dist.all_gather_into_tensor(d_out, d_in)
-        h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return [h_out[r].numpy().copy() for r in range(world)] if rank == 0 else None
-
-    def result_digest(res) -> np.ndarray:
-        if args.workload == "c2":
-            return res[0][0]  # 17 level energies
-        if args.workload == "c4":
-            return res[0]  # [curves of this rank][8] level energies
-        return np.zeros(1)
-
-    # ---- warm-up (incl. the NCCL communicator behind the result gather), FP64 probe ----
-    for _ in range(args.warmup):
-        res = step_resident()
-        gather_small(result_digest(res))
-    ctx.sync()
-    fp64_peak, _ = ctx.fp64_probe()
-
-    def timed_run(step_fn, k: int):
-        """K steps; CUDA events on the ctx stream around each step; L2 flushed between steps."""
-        ms_total, results = 0.0, None
-        for _ in range(k):
-            ctx.l2_flush()
-            barrier()
-            ctx.timer_start()
-            results = step_fn()
-            digest = gather_small(result_digest(results))
-            ms = ctx.timer_stop()
-            if dist is not None:
-                t = torch.tensor([ms], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            ms_total += ms
-        return ms_total, results, digest
-
-    # ---- timed: resident ----
-    barrier()
-    ctx.stats_reset()
+    ctx = cabi.Context(comm.local)
+    sampler = ClockSampler(comm.local)
     sampler.start()
-    t_wall0 = time.time()
-    ms_res, res, digest = timed_run(step_resident, args.steps)
-    t_wall1 = time.time()
-    st = ctx.stats()
-    clocks = sampler.stop(t_wall0, t_wall1)
-    steps_rank = float(st.grid_steps)
-    if dist is not None:
-        t = torch.tensor([steps_rank], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        steps_all = float(t.item())
-    else:
-        steps_all = steps_rank
-    value = steps_all / (ms_res * 1e-3)
-    sweep_rate = steps_rank / (st.sweep_ms * 1e-3)  # this rank's dominant kernel, averaged over its launches
-    launches = int(st.sweep_launches + st.other_launches)
-
-    # ---- timed: end-to-end through the host-buffer C ABI ----
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    ctx.stats_reset()
-    ms_e2e, _, _ = timed_run(step_e2e, args.steps)
-    st2 = ctx.stats()
-    steps2 = float(st2.grid_steps)
-    if dist is not None:
-        t = torch.tensor([steps2], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        steps2 = float(t.item())
-    e2e_value = steps2 / (ms_e2e * 1e-3)
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "time_to_all_levels_ms": ms_res / args.steps if args.workload in ("c2", "c4") else None,
-            "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(st2.h2d_bytes // args.steps),
-                    "d2h_bytes_per_step": int(st2.d2h_bytes // args.steps)},
-            "gpu_launches": launches,
-            "roofline": {
-                "bound": "fp64", "kernel": KERNEL_META[args.workload][0],
-                "achieved": FLOP_PER_STEP * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": FLOP_PER_STEP * sweep_rate / 1e12 / fp64_peak,
-                "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "peak_nominal": NOMINAL_FP64_TFLOPS,
-                "frac_of_nominal": FLOP_PER_STEP * sweep_rate / 1e12 / NOMINAL_FP64_TFLOPS,
-                "flop_per_step": FLOP_PER_STEP, "steps_per_s_kernel": sweep_rate,
-                "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
-                "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
-                "traffic": KERNEL_META[args.workload][1], "traffic_source": KERNEL_META[args.workload][2],
-                "algorithmic_bytes_per_launch": 8 * int(n_steps) * int(ctx.n_curves),
-            },
-            "clocks": clocks,
-        }
-        if args.workload == "c2":
-            exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
-            lev0 = digest[0]
-            line["levels_found"] = int(np.sum(np.isfinite(lev0)))
-            line["max_rel_err_vs_analytic_rank0"] = float(np.max(np.abs(lev0 - exact) / exact))
-        if not args.no_cpu_baseline:
-            from oracle import Oracle
-
-            orc = Oracle(omp=True, threads=host_threads())
-
-            def cpu_timed(fn, min_seconds=CPU_SAMPLE_SECONDS):
-                """Repeat fn() -> (steps, result) until min_seconds of CPU work; -> (steps/s, seconds, reps, first result)."""
-                tot_t, tot_s, reps, first = 0.0, 0.0, 0, None
-                while tot_t < min_seconds:
-                    t0 = time.perf_counter()
-                    st_c, r = fn()
-                    tot_t += time.perf_counter() - t0
-                    tot_s += st_c
-                    reps += 1
-                    first = r if first is None else first
-                return tot_s / tot_t, tot_t, reps, first
-
-            if args.workload == "c2":
-                Vc, sc, El, Eh, _ = rank_curve(0)
-
-                def one():
-                    _, csteps, clev = cpu_solve_c2(orc, Vc, sc, El, Eh)
-                    return csteps, clev
-
-                rate, secs, reps, clev = cpu_timed(one)
-                line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": orc.threads, "kind": "port",
-                                        "sample": f"the full C2 solve (coarse 65536 + refinement), repeated {reps}x, OpenMP oracle",
-                                        "seconds": secs,
-                                        "levels_bit_identical_to_gpu": bool(np.array_equal(
-                                            clev.view(np.uint64), digest[0].view(np.uint64)))}
-            elif args.workload == "c3":
-                F, *_ = orc.prep(V[0], s)
-
-                def one():
-                    n_c, _, _ = orc.sweep_uniform(F, s, w["E_lo"], dE, 0, C3["nE"], tails=False)
-                    return F.size * C3["nE"], n_c
-
-                rate, secs, reps, n_cpu = cpu_timed(one)
-                n_gpu, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
-                line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": orc.threads,
-                                        "kind": "port", "sample": f"the full C3 sweep, repeated {reps}x, OpenMP oracle",
-                                        "seconds": secs,
-                                        "nodes_bit_identical_to_gpu": bool(np.array_equal(n_cpu, n_gpu[0]))}
-                line["scan"] = {"launches": ctx.counter(ctx.CNT_SCAN_LAUNCHES), "flagged": ctx.counter(ctx.CNT_SCAN_FLAGGED)}
-            elif args.workload == "c4":
-                n_sample = 64
-
-                def one():
-                    csteps, same = 0, True
-                    for c in range(n_sample):
-                        F, *_ = orc.prep(V[c], s)
-                        lv, _, _, _, st_c = orc.solve_levels(F, s, E_lo4[c], E_hi4[c], C4["n_coarse"], 0, C4["v_max"],
-                                                             C4["refine_points"], C4["rel_tol"], C4["max_rounds"])
-                        csteps += st_c
-                        same &= bool(np.array_equal(lv.view(np.uint64), digest[0][c].view(np.uint64)))
-                    return csteps, same
-
-                rate, secs, reps, same = cpu_timed(one)
-                line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": orc.threads, "kind": "port",
-                                        "sample": f"{n_sample} of the 4096 curves (full level solve each), repeated {reps}x, OpenMP oracle",
-                                        "seconds": secs, "levels_bit_identical_to_gpu": same}
-            else:
-                F, *_ = orc.prep(V[0], s)
-                nE = 1 << 18
-
-                def one():
-                    n_c, _, _ = orc.sweep_uniform(F, s, w["E_lo"], dE * (C5["nE"] // nE), 0, nE, tails=False)
-                    return F.size * nE, n_c
-
-                rate, secs, reps, _ = cpu_timed(one)
-                line["cpu_baseline"] = {"value": rate, "unit": "steps/s", "cores": orc.threads,
-                                        "kind": "port", "sample": f"2^18 of the 2^24 energies (every 64th), repeated {reps}x",
-                                        "seconds": secs}
+    fp64_peak, _ = ctx.fp64_probe()
+    head = "c5" if args.workload == "all" else args.workload
+    cpu_s = 0.0 if args.no_cpu_baseline else 10.0
+    line = measure(head, ctx, comm, sampler, args.steps, args.warmup, fp64_peak, cpu_s)
+    if args.workload == "all":
+        subs = {}
+        for name in ("c2", "c4", "c3"):
+            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, cpu_s / 2)
+            if rec is not None:
+                subs[name] = rec
+        if line is not None:
+            line["sub_records"] = subs
+            line["time_to_all_levels_ms"] = {"c2": subs["c2"]["time_to_all_levels_ms"], "c4": subs["c4"]["time_to_all_levels_ms"]}
+    if line is not None:
+        line["measured_peaks"] = {"fp64_tflops": fp64_peak, "fp64_tflops_nominal": NOMINAL_FP64_TFLOPS,
+                                  "how": "eps_fp64_probe: 148*8 CTAs x 256 threads x 8 independent DFMA chains x 4096 x 8 "
+                                         "iterations, best of 11 after one warm-up (CUDA events)"}
         emit(line)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    sampler.close()
+    comm.close()
     ctx.close()
 
 

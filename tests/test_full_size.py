@@ -88,6 +88,33 @@ def test_c5_quarter_size_routes_and_slices(ctx):
     assert int(tma[0].astype(np.uint64).sum()) == int(cb[0].astype(np.uint64).sum())  # checksum of the run
 
 
+def test_c5_full_size_sampled_against_oracle(oracle, ctx):
+    """BASELINE configs[4] at its FULL size: 2^24 trial energies on the 200k-point grid (the auto
+    policy selects the constant-bank kernel).  Node counts monotone from 0 to 17, a level-count jump
+    of exactly one at each of the 17 analytic levels, and a seeded sample of 4096 of the 2^24
+    energies -- plus the two grid points around every jump -- bit-identical to the oracle."""
+    nE = 1 << 24
+    w = W.c5(nE=nE)
+    ctx.set_potentials(w["V"], w["s"])
+    before = ctx.counter(ctx.CNT_CBANK_LAUNCHES)
+    nodes, _, _ = ctx.sweep_uniform(w["E_lo"], w["E_hi"], nE, tails=False)
+    assert ctx.counter(ctx.CNT_CBANK_LAUNCHES) > before
+    n = nodes[0]
+    d = np.diff(n.astype(np.int64))
+    assert n[0] == 0 and n[-1] == 17 and np.all(d >= 0) and np.all(d <= 1)
+    jumps = np.flatnonzero(d)  # last grid index below each level
+    assert jumps.size == 17
+    dE = multi.global_step(w["E_lo"], w["E_hi"], nE)
+    exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+    located = w["E_lo"] + (jumps + 0.5) * dE
+    assert np.max(np.abs(located - exact) / exact) < 5e-8 + float(dE) / exact[0]
+    pick = np.unique(np.concatenate([np.random.default_rng(24).integers(0, nE, 4096), jumps, jumps + 1, [0, nE - 1]]))
+    E = w["E_lo"] + pick.astype(np.float64) * dE  # the device's operations: one multiplication, one addition
+    F, *_ = oracle.prep(w["V"], w["s"])
+    n_o, _, _ = oracle.sweep(F, w["s"], E, tails=False)
+    assert np.array_equal(n[pick], n_o)
+
+
 def test_c3_full_size_scan_equals_sequential(ctx):
     """1M-point tabulated curve x 4096 energies: transfer-matrix scan path == sequential march."""
     w = W.c3()
