@@ -482,7 +482,7 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
     steps_all = float(comm.reduce_vec([steps_rank], "sum")[0])
     value = steps_all / (ms_res * 1e-3)
     sweep_rate = steps_rank / (st.sweep_ms * 1e-3)  # this rank's dominant kernel, averaged over its launches
-    launches = int(st.sweep_launches + st.other_launches)
+    launches = int(st.kernel_launches)
 
     # ---- timed: end-to-end through the host-buffer C ABI ----
     for _ in range(2):

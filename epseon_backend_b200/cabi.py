@@ -25,6 +25,10 @@ SYMBOLS = [
     "eps_sweep", "eps_sweep_uniform", "eps_sweep_grid", "eps_solve_levels", "eps_solve_levels_grid", "eps_wavefunctions", "eps_level_corrections", "eps_spline_coefficients", "eps_spline_resample", "eps_set_option", "eps_get_counter", "eps_timer_start", "eps_timer_stop",
     "eps_stats_get", "eps_stats_reset", "eps_l2_flush", "eps_fp64_probe", "eps_host_alloc", "eps_host_free",
     "eps_request_stop", "eps_reset_stop", "eps_ctx_device_bytes", "eps_ctx_trim",
+    "eps_group_create", "eps_group_destroy", "eps_group_size", "eps_group_ctx", "eps_group_last_error", "eps_group_last_ms",
+    "eps_group_set_option", "eps_group_set_potentials", "eps_group_sweep_uniform", "eps_group_solve_levels",
+    "eps_mailbox_create", "eps_mailbox_open", "eps_mailbox_destroy", "eps_mailbox_post_levels", "eps_mailbox_post",
+    "eps_mailbox_collect", "eps_mailbox_slot_bytes",
 ]
 
 
@@ -59,7 +63,7 @@ class SolveParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("sweep_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("grid_steps", C.c_uint64), ("sweep_ms", C.c_double), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
 _lib = None
@@ -75,6 +79,14 @@ def load() -> C.CDLL:
         lib = C.CDLL(str(LIB_PATH))
         lib.eps_last_error.restype = C.c_char_p
         lib.eps_last_error.argtypes = [C.c_void_p]
+        lib.eps_group_last_error.restype = C.c_char_p
+        lib.eps_group_last_error.argtypes = [C.c_void_p]
+        lib.eps_group_ctx.restype = C.c_void_p
+        lib.eps_group_ctx.argtypes = [C.c_void_p, C.c_uint32]
+        lib.eps_group_size.restype = C.c_uint32
+        lib.eps_group_size.argtypes = [C.c_void_p]
+        lib.eps_mailbox_slot_bytes.restype = C.c_size_t
+        lib.eps_mailbox_slot_bytes.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -290,7 +302,7 @@ class Context:
                                               _ptr(out, np.float64)))
         return out
 
-    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE, OPT_CBANK_PDL, OPT_PREP_PARTS = 1, 2, 3, 4, 5, 6
+    OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE, OPT_CBANK_PDL, OPT_PREP_PARTS, OPT_FORM = 1, 2, 3, 4, 5, 6, 7
     CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED, CNT_CBANK_LAUNCHES = 1, 2, 3
 
     def set_option(self, option: int, value: int) -> None:
@@ -324,3 +336,123 @@ class Context:
         t, ms = C.c_double(), C.c_float()
         self._ck(self.lib.eps_fp64_probe(self.h, C.byref(t), C.byref(ms)))
         return t.value, ms.value
+
+
+SHARD_CURVES, SHARD_ENERGY = 0, 1
+
+
+class Group:
+    """``eps_group``: several CUDA devices in one process -- one context and one host thread per device,
+    levels gathered on the first device with peer copies (include/epseon_cuda.h)."""
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        rc = self.lib.eps_group_create(devs, C.c_uint32(len(devices)), C.byref(self.h))
+        if rc != EPS_OK:
+            raise EpsError(rc, (self.lib.eps_last_error(None) or b"").decode())
+        self.devices, self.n_curves, self.n_points = list(devices), 0, 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eps_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != EPS_OK:
+            raise EpsError(rc, (self.lib.eps_group_last_error(self.h) or b"").decode())
+
+    @property
+    def size(self) -> int:
+        return int(self.lib.eps_group_size(self.h))
+
+    def last_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.eps_group_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, option: int, value: int) -> None:
+        self._ck(self.lib.eps_group_set_option(self.h, C.c_int(option), C.c_int64(value)))
+
+    def counter(self, rank: int, which: int) -> int:
+        v = C.c_uint64()
+        rc = self.lib.eps_get_counter(C.c_void_p(self.lib.eps_group_ctx(self.h, rank)), C.c_int(which), C.byref(v))
+        self._ck(rc)
+        return v.value
+
+    def set_potentials(self, V: np.ndarray, scale, shard: int) -> None:
+        V = np.ascontiguousarray(np.atleast_2d(V), dtype=np.float64)
+        scale = _vec(scale, V.shape[0])
+        self._ck(self.lib.eps_group_set_potentials(self.h, _ptr(V, np.float64), C.c_uint32(V.shape[0]),
+                                                   C.c_uint32(V.shape[1]), _ptr(scale, np.float64), C.c_int(shard)))
+        self.n_curves, self.n_points = V.shape
+
+    def sweep_uniform(self, E_lo, E_hi, nE: int, nodes: bool = True):
+        lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
+        n = np.empty((self.n_curves, nE), dtype=np.uint32) if nodes else None
+        self._ck(self.lib.eps_group_sweep_uniform(self.h, _ptr(lo, np.float64), _ptr(hi, np.float64), C.c_uint64(nE),
+                                                  _ptr(n, np.uint32)))
+        return n
+
+    def solve_levels(self, E_lo, E_hi, n_coarse: int, v_min: int, v_max: int, refine_points: int,
+                     rel_tol: float = 1e-12, max_rounds: int = 8):
+        """-> (levels[nC, nlev], widths[nC, nlev], n_below[nC]) of the WHOLE job"""
+        lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
+        nlev = v_max - v_min + 1
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        levels = np.empty((self.n_curves, nlev), dtype=np.float64)
+        widths = np.empty((self.n_curves, nlev), dtype=np.float64)
+        nb = np.empty(self.n_curves, dtype=np.uint32)
+        self._ck(self.lib.eps_group_solve_levels(self.h, C.byref(p), _ptr(lo, np.float64), _ptr(hi, np.float64),
+                                                 _ptr(levels, np.float64), _ptr(widths, np.float64), _ptr(nb, np.uint32)))
+        return levels, widths, nb
+
+
+class Mailbox:
+    """``eps_mailbox``: gather of small per-rank results into rank 0's device memory across PROCESSES
+    (CUDA IPC + peer writes).  Rank 0: ``Mailbox.create(ctx, world, nbytes)`` -> ``.handle`` (64 bytes
+    to hand to the other ranks by any means); rank r > 0: ``Mailbox.open(ctx, handle, world, r, nbytes)``."""
+
+    def __init__(self, ctx: "Context", h, world: int, rank: int, handle: bytes):
+        self.ctx, self.h, self.world, self.rank, self.handle = ctx, h, world, rank, handle
+        self.slot = int(ctx.lib.eps_mailbox_slot_bytes(h))
+
+    @classmethod
+    def create(cls, ctx: "Context", world: int, bytes_per_rank: int) -> "Mailbox":
+        h, buf = C.c_void_p(), (C.c_ubyte * 64)()
+        ctx._ck(ctx.lib.eps_mailbox_create(ctx.h, C.c_uint32(world), C.c_size_t(bytes_per_rank), C.byref(h), buf))
+        return cls(ctx, h, world, 0, bytes(buf))
+
+    @classmethod
+    def open(cls, ctx: "Context", handle: bytes, world: int, rank: int, bytes_per_rank: int) -> "Mailbox":
+        h, buf = C.c_void_p(), (C.c_ubyte * 64).from_buffer_copy(handle)
+        ctx._ck(ctx.lib.eps_mailbox_open(ctx.h, buf, C.c_uint32(world), C.c_uint32(rank), C.c_size_t(bytes_per_rank), C.byref(h)))
+        return cls(ctx, h, world, rank, handle)
+
+    def post_levels(self, seq: int) -> None:
+        self.ctx._ck(self.ctx.lib.eps_mailbox_post_levels(self.h, C.c_uint32(seq)))
+
+    def post(self, payload: np.ndarray, seq: int) -> None:
+        a = np.ascontiguousarray(payload)
+        self.ctx._ck(self.ctx.lib.eps_mailbox_post(self.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), C.c_uint32(seq)))
+
+    def collect(self, seq: int, timeout_s: float = 60.0) -> np.ndarray:
+        """Rank 0: -> uint8 array [world, slot_bytes] once every rank has posted `seq`."""
+        out = np.empty((self.world, self.slot), dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.eps_mailbox_collect(self.h, C.c_uint32(seq), out.ctypes.data_as(C.c_void_p), C.c_double(timeout_s)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.eps_mailbox_destroy(self.h)
+            self.h = None

@@ -168,6 +168,12 @@ namespace epseon::gpu::cpp {
             detail::check(rc, ctx, what);
             return false;
         };
+        // The drop-in path runs the ACCURATE recurrence (D form): its
+        // eigenvalues sit within ~1e-14 of the discrete problem's at every grid size, which is what
+        // makes the 1e-12 tolerance below meaningful (the 4-operation X form carries a rounding-noise
+        // floor of 1e-9 .. 2e-8 on 2e5 .. 1e6-point grids); it costs 5 instead of 4 FP64 operations
+        // per grid step.
+        detail::check(eps_set_option(ctx, EPS_OPT_FORM, 1), ctx, "eps_set_option(EPS_OPT_FORM)");
         if (rotating) {
             const std::vector<double> origins = source->get_grid_origins();
             detail::check(eps_set_potentials_rot(ctx, V.data(), nT, N, scale.data(), origins.data(), steps.data(),
@@ -215,8 +221,30 @@ namespace epseon::gpu::cpp {
         std::vector<double>   lev(static_cast<size_t>(nC) * nlev);
         std::vector<uint32_t> below(nC);
         detail::check(eps_timer_start(ctx), ctx, "eps_timer_start");
-        if (run_step(eps_solve_levels(ctx, &p, E_lo.data(), E_hi.data(), lev.data(), nullptr, below.data()),
-                     "eps_solve_levels")) {
+        int solve_rc;
+        if (configurator.getEnergyShardWorld() > 1) {
+            // energy-range shard: this task owns a contiguous block of the n_coarse - 1 intervals of the
+            // global coarse grid (the remainder to the first ranks) and sweeps its end points, sharing
+            // one point with its right neighbour -- every bracket lies in exactly one slice, and the
+            // affine grid (E0, dE, j0) reproduces the global energies bit for bit.
+            const uint32_t world = configurator.getEnergyShardWorld(), rank = configurator.getEnergyShardRank();
+            const uint32_t n_int = p.n_coarse - 1, base = n_int / world, rem = n_int % world;
+            const uint32_t a = rank * base + std::min(rank, rem), cnt = base + (rank < rem ? 1u : 0u);
+            if (cnt == 0) { // more ranks than intervals: nothing to search here
+                std::fill(lev.begin(), lev.end(), std::numeric_limits<double>::quiet_NaN());
+                std::fill(below.begin(), below.end(), 0u);
+                solve_rc = EPS_OK;
+            } else {
+                std::vector<double> dE(nC);
+                for (uint32_t k = 0; k < nC; k++) dE[k] = (E_hi[k] - E_lo[k]) / static_cast<double>(p.n_coarse - 1);
+                eps_solve_params q = p;
+                q.n_coarse         = cnt + 1;
+                solve_rc = eps_solve_levels_grid(ctx, &q, E_lo.data(), dE.data(), a, lev.data(), nullptr, below.data(), nullptr);
+            }
+        } else {
+            solve_rc = eps_solve_levels(ctx, &p, E_lo.data(), E_hi.data(), lev.data(), nullptr, below.data());
+        }
+        if (run_step(solve_rc, "eps_solve_levels")) {
             eps_sync(ctx); // let the drained launches finish before the context is parked
             guard.healthy = eps_reset_stop(ctx) == EPS_OK;
             return handle->setCancelled();

@@ -135,6 +135,12 @@ namespace epseon::gpu::python {
         }
 
         // Additive: tabulated curves from "r V" text files.
+        // additive: energy-range sharding of one problem over several devices (multi.py)
+        TaskConfigurator& set_energy_shard(uint32_t rank, uint32_t world) {
+            configurator->setEnergyShard(rank, world);
+            return *this;
+        }
+
         TaskConfigurator& set_potential_files(const std::vector<std::string>& file_names, uint32_t point_count) {
             configurator->setPotentialSource(std::make_shared<cpp::PotentialFileLoader<FP>>(file_names, point_count));
             return *this;

@@ -28,6 +28,10 @@ namespace epseon::gpu::cpp {
         // additive: rotational quantum numbers J; every curve is solved once per J with
         // V_J = V + J(J+1) hbar^2/(2 mu r^2).  Default {0}: the reference's J-less problem.
         std::vector<uint32_t> rotational_states = {0};
+        // additive: this task searches only slice `shard_rank` of `shard_world` contiguous
+        // slices of the coarse energy grid (energy-range sharding of ONE problem over several devices;
+        // the reference gives one device per task, device_interface.hpp:22).  Default: the whole grid.
+        uint32_t shard_rank = 0, shard_world = 1;
 
         template <typename T>
         static std::shared_ptr<T> clone_or_null(const std::shared_ptr<T>& p) {
@@ -48,7 +52,9 @@ namespace epseon::gpu::cpp {
             potential_source(std::move(o.potential_source)),
             algorithm_config(std::move(o.algorithm_config)),
             wavefunction_output(o.wavefunction_output),
-            rotational_states(std::move(o.rotational_states)) {}
+            rotational_states(std::move(o.rotational_states)),
+            shard_rank(o.shard_rank),
+            shard_world(o.shard_world) {}
         TaskConfigurator& operator=(TaskConfigurator&& o) noexcept {
             if (this != &o) {
                 hardware_config     = std::move(o.hardware_config);
@@ -56,6 +62,8 @@ namespace epseon::gpu::cpp {
                 algorithm_config    = std::move(o.algorithm_config);
                 wavefunction_output = o.wavefunction_output;
                 rotational_states   = std::move(o.rotational_states);
+                shard_rank          = o.shard_rank;
+                shard_world         = o.shard_world;
             }
             return *this;
         }
@@ -65,7 +73,9 @@ namespace epseon::gpu::cpp {
             potential_source(clone_or_null(o.potential_source)),
             algorithm_config(clone_or_null(o.algorithm_config)),
             wavefunction_output(o.wavefunction_output),
-            rotational_states(o.rotational_states) {}
+            rotational_states(o.rotational_states),
+            shard_rank(o.shard_rank),
+            shard_world(o.shard_world) {}
         TaskConfigurator& operator=(const TaskConfigurator& o) {
             if (this != &o) {
                 hardware_config     = clone_or_null(o.hardware_config);
@@ -73,6 +83,8 @@ namespace epseon::gpu::cpp {
                 algorithm_config    = clone_or_null(o.algorithm_config);
                 wavefunction_output = o.wavefunction_output;
                 rotational_states   = o.rotational_states;
+                shard_rank          = o.shard_rank;
+                shard_world         = o.shard_world;
             }
             return *this;
         }
@@ -110,6 +122,15 @@ namespace epseon::gpu::cpp {
             return *this;
         }
         [[nodiscard]] const std::vector<uint32_t>& getRotationalStates() const { return rotational_states; }
+
+        TaskConfigurator& setEnergyShard(uint32_t rank, uint32_t world) {
+            if (world == 0 || rank >= world) throw std::runtime_error("energy shard: need rank < world");
+            shard_rank  = rank;
+            shard_world = world;
+            return *this;
+        }
+        [[nodiscard]] uint32_t getEnergyShardRank() const { return shard_rank; }
+        [[nodiscard]] uint32_t getEnergyShardWorld() const { return shard_world; }
 
         [[nodiscard]] bool isConfigured() const {
             return static_cast<bool>(hardware_config) && static_cast<bool>(potential_source) &&

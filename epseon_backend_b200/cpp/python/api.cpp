@@ -110,6 +110,10 @@ namespace epseon::gpu::python {
                      py::arg("tables"), py::arg("min_r"), py::arg("max_r"), py::return_value_policy::reference,
                      "Use curves held in memory: a float64 array [n_curves][point_count] of V(r_i) on the uniform grid "
                      "r_i = min_r + i (max_r - min_r)/(point_count - 1).")
+                .def("set_energy_shard", &C::set_energy_shard, py::arg("rank"), py::arg("world"),
+                     py::return_value_policy::reference,
+                     "Search only slice `rank` of `world` contiguous slices of the coarse energy grid (energy-range "
+                     "sharding of one problem over several devices); the union over the ranks equals the unsharded task.")
                 .def("set_potential_files", &C::set_potential_files, py::arg("file_names"), py::arg("point_count") = 0,
                      py::return_value_policy::reference,
                      "Use tabulated 'r V' text files (or NumPy .npy arrays of shape (n, 2)) as potential source; "

@@ -13,12 +13,17 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace eps;
@@ -62,7 +67,9 @@ struct eps_ctx {
     // resident potentials
     uint32_t                    nC = 0, N = 0;
     uint64_t                    slot = 0;  // doubles per curve
-    DevBuf<double>              d_F, d_V, d_scale, d_spl, d_Vraw, d_rot;
+    DevBuf<double>              d_F, d_A, d_V, d_scale, d_spl, d_Vraw, d_rot;
+    int                         opt_form  = 0;  // EPS_OPT_FORM: 0 = X form (4 operations), 1 = D form (accurate, 5 operations)
+    int                         form_resident = 0;  // form the resident tables were prepared for
     DevBuf<uint32_t>            d_J;
     DevBuf<PrepOut>             d_prep;
     DevBuf<PrepPart>            d_prep_parts;
@@ -78,6 +85,7 @@ struct eps_ctx {
     unsigned long long* d_steps = nullptr;
 
     // level-search state
+    uint32_t         last_total = 0, last_nC = 0;  // (curve, level) pairs / curves of the last solve (d_levels, d_widths, d_nbelow)
     DevBuf<double>   d_lo, d_hi, d_levels, d_widths;
     DevBuf<uint32_t> d_state, d_jstar, d_nbelow, d_nactive;
     uint32_t*        h_pinned = nullptr;  // small pinned scratch (readbacks)
@@ -127,7 +135,7 @@ struct eps_ctx {
 // curve descriptors, small bookkeeping).  SCRATCH: grow-only work areas that any later call
 // re-reserves on demand (eps_ctx_trim releases them).
 #define EPS_RESIDENT_BUFS(X) \
-    X(d_F) X(d_scale) X(d_prep) X(d_prep_parts) X(d_curves) X(d_J) X(d_rot) X(d_jobs) X(d_jobs_ref) X(d_Elo) X(d_Ehi) \
+    X(d_F) X(d_A) X(d_scale) X(d_prep) X(d_prep_parts) X(d_curves) X(d_J) X(d_rot) X(d_jobs) X(d_jobs_ref) X(d_Elo) X(d_Ehi) \
     X(d_lo) X(d_hi) X(d_levels) X(d_widths) X(d_state) X(d_jstar) X(d_nbelow) X(d_nactive) X(d_nflag)
 #define EPS_SCRATCH_BUFS(X) \
     X(d_V) X(d_Vraw) X(d_spl) X(d_E) X(d_mant) X(d_nodes) X(d_exp) \
@@ -192,7 +200,7 @@ struct SweepOut {  // device pointers of one sweep's results
     int32_t*  expo;
 };
 
-template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan>
+template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan, int kForm = 0>
 cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                                  const SweepOut& out, uint32_t n_seg, uint32_t tiles_per_seg, const SegOut& so,
                                  uint32_t pack_log2 = 0) {
@@ -203,33 +211,34 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
                             : pack_log2 ? ((n_jobs + (1u << pack_log2) - 1) >> pack_log2)
                                         : chunks * n_jobs * (kScan ? n_seg : 1u);
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
-    auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan>;
+    auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan, kForm>;
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
     if (configured_dev != ctx->dev) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()));
         if (e != cudaSuccess) return e;
         configured_dev = ctx->dev;
     }
+    ctx->stats.kernel_launches++;
     kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
-        ctx->d_F.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
+        kForm == 0 ? ctx->d_F.p : ctx->d_A.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
         kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2, ctx->d_stop);
     return cudaGetLastError();
 }
 
-template <int kEpt, int kWarps, int kStride>
+template <int kEpt, int kWarps, int kStride, int kForm>
 cudaError_t launch_sweep_t(eps_ctx* ctx, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out,
                            uint32_t pack_log2) {
     const SegOut none{};
-    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true, false>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2)
-                 : launch_sweep_variant<kEpt, kWarps, kStride, false, false>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2);
+    return tails ? launch_sweep_variant<kEpt, kWarps, kStride, true, false, kForm>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2)
+                 : launch_sweep_variant<kEpt, kWarps, kStride, false, false, kForm>(ctx, j, n, nE, E, out, 1, 0, none, pack_log2);
 }
 
-template <int kEpt, int kWarps>
+template <int kEpt, int kWarps, int kForm = 0>
 cudaError_t launch_sweep_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out,
                            uint32_t pack_log2) {
-    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32>(ctx, j, n, nE, E, tails, out, pack_log2);
-    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8>(ctx, j, n, nE, E, tails, out, pack_log2);
-    return launch_sweep_t<kEpt, kWarps, 1>(ctx, j, n, nE, E, tails, out, pack_log2);
+    if (stride == 32) return launch_sweep_t<kEpt, kWarps, 32, kForm>(ctx, j, n, nE, E, tails, out, pack_log2);
+    if (stride == 8) return launch_sweep_t<kEpt, kWarps, 8, kForm>(ctx, j, n, nE, E, tails, out, pack_log2);
+    return launch_sweep_t<kEpt, kWarps, 1, kForm>(ctx, j, n, nE, E, tails, out, pack_log2);
 }
 
 // CTA shape (energies per thread, consumer warps).  512 energies per CTA as 4 chains x 4 warps:
@@ -263,6 +272,11 @@ uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows, uint32_t per_cta = 512) 
 
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                               bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0, uint32_t pack_cta = 512) {
+    if (ctx->form_resident == 1) {  // D form: the two product shapes only (the EPS_FORCE_* tuning shapes are X-form)
+        if ((pack_log2 && pack_log2 != kFlatRows && pack_cta == 256) || (!pack_log2 && nE <= 256u))
+            return launch_sweep_s<2, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
+        return launch_sweep_s<4, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
+    }
     if (pack_log2 && pack_cta == 256) return launch_sweep_s<2, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     if (pack_log2) return launch_sweep_s<4, 4>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     const Shape sh = pick_shape(ctx, n_jobs, nE);
@@ -275,7 +289,7 @@ cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, 
 
 // Constant-bank sweep (numerov_cbank.cuh): one launch per chunk of kCbChunk steps, the chunk passed
 // by value through the kernel-parameter constant bank.
-template <int kEpt, int kThreads, int kStride, bool kTails>
+template <int kEpt, int kThreads, int kStride, bool kTails, int kForm = 0>
 cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                                  const SweepOut& out) {
     constexpr uint32_t per_cta = kThreads * kEpt;
@@ -299,21 +313,22 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
         cfg.attrs    = &attr;
         cfg.numAttrs = (ctx->cb_pdl >= 2 || (ctx->cb_pdl == 1 && grid >= 2ull * ctx->sm_count)) ? 1 : 0;
         const int pdl_late = ctx->cb_pdl > 2 ? ctx->cb_pdl - 2 : 0;  // trigger that many 128-step blocks before the chunk's end
-        cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails>, chunk, d_jobs,
+        cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails, kForm>, chunk, d_jobs,
                                            static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
                                            k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, pdl_late, st, out.nodes, kTails ? out.mant : nullptr,
                                            kTails ? out.expo : nullptr, ctx->d_steps, static_cast<const int*>(ctx->d_stop));
         if (e != cudaSuccess) return e;
         ctx->cbank_launches++;
+        ctx->stats.kernel_launches++;
     }
     return cudaSuccess;
 }
 
-template <int kEpt, int kThreads>
+template <int kEpt, int kThreads, int kForm = 0>
 cudaError_t launch_cbank_s(eps_ctx* ctx, int stride, const Job* j, uint32_t n, uint32_t nE, const double* E, bool tails, const SweepOut& out) {
-    if (stride == 32) return tails ? launch_cbank_variant<kEpt, kThreads, 32, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 32, false>(ctx, j, n, nE, E, out);
-    if (stride == 8) return tails ? launch_cbank_variant<kEpt, kThreads, 8, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 8, false>(ctx, j, n, nE, E, out);
-    return tails ? launch_cbank_variant<kEpt, kThreads, 1, true>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 1, false>(ctx, j, n, nE, E, out);
+    if (stride == 32) return tails ? launch_cbank_variant<kEpt, kThreads, 32, true, kForm>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 32, false, kForm>(ctx, j, n, nE, E, out);
+    if (stride == 8) return tails ? launch_cbank_variant<kEpt, kThreads, 8, true, kForm>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 8, false, kForm>(ctx, j, n, nE, E, out);
+    return tails ? launch_cbank_variant<kEpt, kThreads, 1, true, kForm>(ctx, j, n, nE, E, out) : launch_cbank_variant<kEpt, kThreads, 1, false, kForm>(ctx, j, n, nE, E, out);
 }
 
 // Host copy of the (single) curve's coefficient table: the constant-bank kernel takes its chunks by
@@ -322,7 +337,8 @@ int fetch_host_table(eps_ctx* ctx) {
     if (!ctx->h_F.empty()) return EPS_OK;
     const uint32_t n = ctx->curves[0].n_steps;
     ctx->h_F.resize(n);
-    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_F.data(), ctx->d_F.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_F.data(), ctx->form_resident == 1 ? ctx->d_A.p : ctx->d_F.p, n * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += n * sizeof(double);
     return EPS_OK;
@@ -338,7 +354,8 @@ int launch_cbank(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, 
     EPS_CUDA(ctx, ctx->d_cbnodes.reserve(n_out));
     EPS_CUDA(ctx, ctx->d_cbprev.reserve(n_out));
     cudaError_t e;
-    if (ctx->cb_ept == 4 && ctx->cb_threads == 128) e = launch_cbank_s<4, 128>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    if (ctx->form_resident == 1) e = launch_cbank_s<4, 128, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
+    else if (ctx->cb_ept == 4 && ctx->cb_threads == 128) e = launch_cbank_s<4, 128>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
     else if (ctx->cb_ept == 4) e = launch_cbank_s<4, 256>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
     else if (ctx->cb_threads == 128) e = launch_cbank_s<2, 128>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
     else e = launch_cbank_s<2, 256>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out);
@@ -393,14 +410,18 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
     EPS_CUDA(ctx, ctx->d_flagged.reserve(cap));
     const SegOut so{ctx->d_segXA.p, ctx->d_segSA.p, ctx->d_segXB.p, ctx->d_segSB.p, ctx->d_segeA.p, ctx->d_segeB.p, ctx->d_segnA.p};
     cudaError_t e;
-    if (stride == 32) e = launch_sweep_variant<2, 8, 32, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
-    else if (stride == 8) e = launch_sweep_variant<2, 8, 8, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
-    else e = launch_sweep_variant<2, 8, 1, false, true>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    const bool dform = ctx->form_resident == 1;
+    if (stride == 32) e = dform ? launch_sweep_variant<2, 8, 32, false, true, 1>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so)
+                                : launch_sweep_variant<2, 8, 32, false, true, 0>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    else if (stride == 8) e = dform ? launch_sweep_variant<2, 8, 8, false, true, 1>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so)
+                                    : launch_sweep_variant<2, 8, 8, false, true, 0>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
+    else e = dform ? launch_sweep_variant<2, 8, 1, false, true, 1>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so)
+                   : launch_sweep_variant<2, 8, 1, false, true, 0>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
     EPS_CUDA(ctx, e);
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nflag.p, 0, sizeof(uint32_t), ctx->stream));
     segment_combine_kernel<<<dim3(n_jobs, (nE + 127) / 128), 128, 0, ctx->stream>>>(
         so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
-        ctx->d_nflag.p, ctx->d_flagged.p, cap);
+        ctx->d_nflag.p, ctx->d_flagged.p, cap, dform ? 1.0 : -1.0);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
     ctx->scan_launches++;
@@ -536,6 +557,9 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
     invalidate_resident(ctx);
     EPS_CUDA(ctx, ctx->d_prep.reserve(n_curves));
     EPS_CUDA(ctx, ctx->d_F.reserve(n_f));
+    const int form = ctx->opt_form;
+    if (form == 1) EPS_CUDA(ctx, ctx->d_A.reserve(n_f));
+    double* d_A = form == 1 ? ctx->d_A.p : nullptr;
     EPS_CUDA(ctx, ctx->d_curves.reserve(n_curves));
     // few long curves: cut every curve into chunks (one CTA each) instead of one CTA per curve
     const uint32_t parts = (N >= 65536 && n_curves <= 64) ? std::min<uint32_t>(kPrepPartsMax, (N + 8191) / 8192) : 1;
@@ -545,11 +569,11 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
         prep_part_argmin_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, parts, ctx->d_prep_parts.p);
         prep_part_window_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, parts, kTMax, ctx->d_prep_parts.p);
         prep_part_finish_kernel<<<grid, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, parts, ctx->d_prep_parts.p,
-                                                                       ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+                                                                       ctx->d_F.p, d_A, ctx->d_curves.p, ctx->d_prep.p);
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches += 3;
     } else {
-        prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, ctx->d_curves.p, ctx->d_prep.p);
+        prep_curves_kernel<<<n_curves, kPrepThreads, 0, ctx->stream>>>(ctx->d_V.p, ctx->d_scale.p, N, slot, kTMax, ctx->d_F.p, d_A, ctx->d_curves.p, ctx->d_prep.p);
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches++;
     }
@@ -564,6 +588,7 @@ int prep_resident(eps_ctx* ctx, uint32_t n_curves, uint32_t n_points, ScaleOf sc
     std::vector<eps_curve_info> infos(n_curves);
     for (uint32_t c = 0; c < n_curves; c++) infos[c] = eps_curve_info{po[c].i0, po[c].n_steps, scale_of(c), po[c].v_min, po[c].v_last};
     ctx->nC     = n_curves;
+    ctx->form_resident = form;
     ctx->N      = N;
     ctx->slot   = slot;
     ctx->curves = std::move(infos);
@@ -927,7 +952,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
                uint32_t* n_below, uint32_t* n_first) {
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, ctx->nC > 0, EPS_ERR_STATE, "eps_set_potentials has not been called");
-    EPS_REQUIRE(ctx, p && g.A && g.B && levels, EPS_ERR_INVALID, "null argument");
+    EPS_REQUIRE(ctx, p && g.A && g.B, EPS_ERR_INVALID, "null argument");  // levels == NULL: results stay on the device
     EPS_REQUIRE(ctx, p->v_max >= p->v_min, EPS_ERR_INVALID, "v_max < v_min");
     EPS_REQUIRE(ctx, p->n_coarse >= 2 && p->refine_points >= 1, EPS_ERR_INVALID, "n_coarse >= 2 and refine_points >= 1 required");
     const uint32_t nC = ctx->nC, nlev = p->v_max - p->v_min + 1, M = p->refine_points;
@@ -1011,8 +1036,12 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     finalize_levels_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, total, ctx->d_levels.p, ctx->d_widths.p);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
-    EPS_CUDA(ctx, cudaMemcpyAsync(levels, ctx->d_levels.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += total * sizeof(double);
+    ctx->last_total = total;
+    ctx->last_nC    = nC;
+    if (levels) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(levels, ctx->d_levels.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += total * sizeof(double);
+    }
     if (widths) {
         EPS_CUDA(ctx, cudaMemcpyAsync(widths, ctx->d_widths.p, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += total * sizeof(double);
@@ -1215,6 +1244,10 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
             EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "cbank: 0 auto, 1 always, 2 never");
             ctx->opt_cbank = value;
             return EPS_OK;
+        case EPS_OPT_FORM:
+            EPS_REQUIRE(ctx, value == 0 || value == 1, EPS_ERR_INVALID, "form: 0 (X form, 4 operations) or 1 (D form, accurate, 5 operations)");
+            ctx->opt_form = static_cast<int>(value);  // takes effect at the next eps_set_potentials*
+            return EPS_OK;
         case EPS_OPT_PREP_PARTS:
             EPS_REQUIRE(ctx, value == 0 || value == 1, EPS_ERR_INVALID, "prep parts: 0 auto, 1 never");
             ctx->opt_prep_parts = value;
@@ -1266,6 +1299,7 @@ int eps_stats_get(eps_ctx* ctx, eps_stats* out) {
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats.grid_steps = steps;
     *out                  = ctx->stats;
+    out->kernel_launches += ctx->stats.other_launches;  // every kernel this library launched: sweeps (each chunk) + the rest
     return EPS_OK;
 }
 
@@ -1323,5 +1357,502 @@ int eps_fp64_probe(eps_ctx* ctx, double* tflops, float* ms_out) {
     if (ms_out) *ms_out = best;
     return EPS_OK;
 }
+
+}  // extern "C"
+
+// =====================================================================================================
+// Multi-device group: one process, one host thread and one eps_ctx per device.  The path
+// shards without any exchange during compute -- by potential curve or by energy range -- and only the
+// located levels travel: every device copies its level array into a gather buffer on the group's
+// first device with cudaMemcpyPeerAsync (NVLink / NVSwitch when peer access is available), device 0
+// waits on the peers' events and ONE device->host copy returns the lot; the per-level merge of an
+// energy-sharded search (each level is finite on exactly one device) runs on the host.
+// No torch, no NCCL: the payload is a few hundred bytes per device.
+// =====================================================================================================
+struct eps_group {
+    struct Worker {
+        eps_ctx*                ctx = nullptr;
+        std::thread             th;
+        std::mutex              m;
+        std::condition_variable cv;
+        std::function<int()>    job;
+        bool                    has_job = false, done = false, quit = false;
+        int                     rc = EPS_OK;
+        float                   ms = 0.f;
+        cudaEvent_t             posted = nullptr;  // levels of the last solve have landed in the gather buffer
+    };
+    std::vector<Worker*> w;
+    std::string          err;
+    int                  shard = EPS_SHARD_CURVES;
+    uint32_t             nC = 0, N = 0;          // whole job
+    std::vector<uint32_t> c0, cn;                 // curve block of every device (curve sharding)
+    double*              d_gather = nullptr;      // on device w[0]: [n_dev][2 * total + pad] levels + widths
+    size_t               gather_cap = 0;          // doubles per device slot
+    double*              h_gather = nullptr;      // pinned mirror
+    size_t               h_cap = 0;
+    float                last_ms = 0.f;
+};
+
+namespace {
+
+int gfail(eps_group* g, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (g) g->err = msg;
+    return code;
+}
+
+void worker_loop(eps_group::Worker* w) {
+    cudaSetDevice(w->ctx->dev);
+    for (;;) {
+        std::function<int()> job;
+        {
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+            if (w->quit) return;
+            job        = std::move(w->job);
+            w->has_job = false;
+        }
+        eps_ctx* ctx = w->ctx;
+        int      rc  = eps_timer_start(ctx);
+        if (rc == EPS_OK) rc = job();
+        float ms = 0.f;
+        if (rc == EPS_OK) rc = eps_timer_stop(ctx, &ms);
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            w->rc   = rc;
+            w->ms   = ms;
+            w->done = true;
+        }
+        w->cv.notify_all();
+    }
+}
+
+// Run job(rank) on every device concurrently; -> first failing status, group->last_ms = max over devices.
+int run_all(eps_group* g, const std::function<int(uint32_t)>& job) {
+    for (uint32_t r = 0; r < g->w.size(); r++) {
+        eps_group::Worker* w = g->w[r];
+        std::lock_guard<std::mutex> lk(w->m);
+        w->job     = [job, r] { return job(r); };
+        w->has_job = true;
+        w->done    = false;
+        w->cv.notify_all();
+    }
+    int   rc = EPS_OK;
+    float ms = 0.f;
+    for (uint32_t r = 0; r < g->w.size(); r++) {
+        eps_group::Worker* w = g->w[r];
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != EPS_OK && rc == EPS_OK) {
+            rc     = w->rc;
+            g->err = "device " + std::to_string(w->ctx->dev) + ": " + w->ctx->err;
+            g_last_error = g->err;
+        }
+        ms = std::max(ms, w->ms);
+    }
+    g->last_ms = ms;
+    return rc;
+}
+
+void shard_block(uint32_t n, uint32_t world, uint32_t rank, uint32_t& start, uint32_t& count) {
+    const uint32_t base = n / world, rem = n % world;  // contiguous blocks, the remainder to the first ranks
+    start = rank * base + std::min(rank, rem);
+    count = base + (rank < rem ? 1u : 0u);
+}
+
+}  // namespace
+
+extern "C" {
+
+int eps_group_create(const int* devices, uint32_t n_devices, eps_group** out) {
+    if (!out) return gfail(nullptr, EPS_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!devices || n_devices == 0 || n_devices > 64) return gfail(nullptr, EPS_ERR_INVALID, "need 1..64 devices");
+    eps_group* g = new (std::nothrow) eps_group();
+    if (!g) return gfail(nullptr, EPS_ERR_NOMEM, "out of host memory");
+    for (uint32_t r = 0; r < n_devices; r++) {
+        eps_ctx* ctx = nullptr;
+        int      rc  = eps_ctx_create(devices[r], &ctx);
+        if (rc != EPS_OK) {
+            const std::string m = g_last_error;
+            eps_group_destroy(g);
+            return gfail(nullptr, rc, m);
+        }
+        auto* w = new eps_group::Worker();
+        w->ctx  = ctx;
+        cudaSetDevice(ctx->dev);
+        cudaEventCreateWithFlags(&w->posted, cudaEventDisableTiming);
+        g->w.push_back(w);
+    }
+    // peer access towards the gather device (errors are not fatal: cudaMemcpyPeerAsync then stages through the host)
+    for (uint32_t r = 1; r < n_devices; r++) {
+        if (devices[r] == devices[0]) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[r], devices[0]) == cudaSuccess && can) {
+            cudaSetDevice(devices[r]);
+            cudaDeviceEnablePeerAccess(devices[0], 0);
+        }
+        cudaGetLastError();
+    }
+    for (auto* w : g->w) w->th = std::thread(worker_loop, w);
+    *out = g;
+    return EPS_OK;
+}
+
+int eps_group_destroy(eps_group* g) {
+    if (!g) return EPS_OK;
+    for (auto* w : g->w) {
+        if (w->th.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(w->m);
+                w->quit = true;
+            }
+            w->cv.notify_all();
+            w->th.join();
+        }
+        if (w->ctx) {
+            cudaSetDevice(w->ctx->dev);
+            if (w->posted) cudaEventDestroy(w->posted);
+            eps_ctx_destroy(w->ctx);
+        }
+        delete w;
+    }
+    if (!g->w.empty() || g->d_gather) {
+        if (g->d_gather) cudaFree(g->d_gather);
+        if (g->h_gather) cudaFreeHost(g->h_gather);
+    }
+    delete g;
+    return EPS_OK;
+}
+
+uint32_t    eps_group_size(const eps_group* g) { return g ? static_cast<uint32_t>(g->w.size()) : 0u; }
+eps_ctx*    eps_group_ctx(eps_group* g, uint32_t rank) { return (g && rank < g->w.size()) ? g->w[rank]->ctx : nullptr; }
+const char* eps_group_last_error(const eps_group* g) { return g ? g->err.c_str() : g_last_error.c_str(); }
+
+int eps_group_last_ms(eps_group* g, float* ms) {
+    if (!g || !ms) return gfail(g, EPS_ERR_INVALID, "null argument");
+    *ms = g->last_ms;
+    return EPS_OK;
+}
+
+int eps_group_set_option(eps_group* g, int option, int64_t value) {
+    if (!g) return gfail(nullptr, EPS_ERR_INVALID, "null group");
+    for (auto* w : g->w)
+        if (int rc = eps_set_option(w->ctx, option, value)) return gfail(g, rc, w->ctx->err);
+    return EPS_OK;
+}
+
+int eps_group_set_potentials(eps_group* g, const double* V, uint32_t n_curves, uint32_t n_points, const double* scale,
+                             int shard) {
+    if (!g || !V || !scale) return gfail(g, EPS_ERR_INVALID, "null argument");
+    if (shard != EPS_SHARD_CURVES && shard != EPS_SHARD_ENERGY) return gfail(g, EPS_ERR_INVALID, "shard: EPS_SHARD_CURVES or EPS_SHARD_ENERGY");
+    const uint32_t G = static_cast<uint32_t>(g->w.size());
+    if (shard == EPS_SHARD_CURVES && n_curves < G) return gfail(g, EPS_ERR_INVALID, "curve sharding needs at least one curve per device");
+    g->shard = shard;
+    g->nC    = 0;
+    g->c0.assign(G, 0);
+    g->cn.assign(G, n_curves);
+    if (shard == EPS_SHARD_CURVES)
+        for (uint32_t r = 0; r < G; r++) shard_block(n_curves, G, r, g->c0[r], g->cn[r]);
+    const int rc = run_all(g, [&](uint32_t r) {
+        return eps_set_potentials(g->w[r]->ctx, V + static_cast<size_t>(g->c0[r]) * n_points, g->cn[r], n_points, scale + g->c0[r]);
+    });
+    if (rc) return rc;
+    g->nC = n_curves;
+    g->N  = n_points;
+    return EPS_OK;
+}
+
+int eps_group_sweep_uniform(eps_group* g, const double* E_lo, const double* E_hi, uint64_t n_energies, uint32_t* nodes) {
+    if (!g || !E_lo || !E_hi) return gfail(g, EPS_ERR_INVALID, "null argument");
+    if (g->nC == 0) return gfail(g, EPS_ERR_STATE, "eps_group_set_potentials has not been called");
+    if (n_energies < 2 || n_energies >= (1ull << 32)) return gfail(g, EPS_ERR_INVALID, "bad energies");
+    const uint32_t G = static_cast<uint32_t>(g->w.size()), nC = g->nC, nE = static_cast<uint32_t>(n_energies);
+    if (g->shard == EPS_SHARD_CURVES)
+        return run_all(g, [&](uint32_t r) {
+            return eps_sweep_uniform(g->w[r]->ctx, E_lo + g->c0[r], E_hi + g->c0[r], nE,
+                                     nodes ? nodes + static_cast<size_t>(g->c0[r]) * nE : nullptr, nullptr, nullptr);
+        });
+    // energy range: every device sweeps a contiguous slice of the ONE global grid E_j = E_lo + j dE,
+    // expressed as (E0, dE, j0) so that the global energies are reproduced bit for bit
+    std::vector<double> dE(nC);
+    for (uint32_t c = 0; c < nC; c++) dE[c] = (E_hi[c] - E_lo[c]) / static_cast<double>(nE - 1);
+    std::vector<std::vector<uint32_t>> tmp(G);
+    const int rc = run_all(g, [&](uint32_t r) {
+        uint32_t j0, n;
+        shard_block(nE, G, r, j0, n);
+        if (n == 0) return static_cast<int>(EPS_OK);
+        uint32_t* dst = nullptr;
+        if (nodes) {
+            if (nC == 1) dst = nodes + j0;  // one curve: the slice is contiguous in the caller's array
+            else {
+                tmp[r].resize(static_cast<size_t>(nC) * n);
+                dst = tmp[r].data();
+            }
+        }
+        return eps_sweep_grid(g->w[r]->ctx, E_lo, dE.data(), j0, n, dst, nullptr, nullptr);
+    });
+    if (rc) return rc;
+    if (nodes && nC > 1)
+        for (uint32_t r = 0; r < G; r++) {
+            uint32_t j0, n;
+            shard_block(nE, G, r, j0, n);
+            for (uint32_t c = 0; c < nC && n; c++)
+                std::memcpy(nodes + static_cast<size_t>(c) * nE + j0, tmp[r].data() + static_cast<size_t>(c) * n, n * sizeof(uint32_t));
+        }
+    return EPS_OK;
+}
+
+int eps_group_solve_levels(eps_group* g, const eps_solve_params* p, const double* E_lo, const double* E_hi, double* levels,
+                           double* widths, uint32_t* n_below) {
+    if (!g || !p || !E_lo || !E_hi || !levels) return gfail(g, EPS_ERR_INVALID, "null argument");
+    if (g->nC == 0) return gfail(g, EPS_ERR_STATE, "eps_group_set_potentials has not been called");
+    if (p->v_max < p->v_min || p->n_coarse < 2) return gfail(g, EPS_ERR_INVALID, "v_max >= v_min and n_coarse >= 2 required");
+    const uint32_t G = static_cast<uint32_t>(g->w.size()), nC = g->nC, nlev = p->v_max - p->v_min + 1;
+    const bool     by_energy = g->shard == EPS_SHARD_ENERGY;
+    // gather buffer on device 0: per device [levels | widths] of its (curve, level) pairs
+    size_t slot = 0;
+    for (uint32_t r = 0; r < G; r++) slot = std::max(slot, 2 * static_cast<size_t>(g->cn[r]) * nlev);
+    cudaSetDevice(g->w[0]->ctx->dev);
+    if (slot > g->gather_cap) {
+        if (g->d_gather) cudaFree(g->d_gather);
+        if (g->h_gather) cudaFreeHost(g->h_gather);
+        g->d_gather = nullptr;
+        g->h_gather = nullptr;
+        g->gather_cap = 0;
+        if (cudaMalloc(reinterpret_cast<void**>(&g->d_gather), slot * G * sizeof(double)) != cudaSuccess ||
+            cudaMallocHost(reinterpret_cast<void**>(&g->h_gather), slot * G * sizeof(double)) != cudaSuccess)
+            return gfail(g, EPS_ERR_NOMEM, "gather buffer");
+        g->gather_cap = slot;
+    }
+    std::vector<double>   dE(nC);
+    std::vector<uint32_t> nl(static_cast<size_t>(G) * nC, 0u);
+    if (by_energy)
+        for (uint32_t c = 0; c < nC; c++) dE[c] = (E_hi[c] - E_lo[c]) / static_cast<double>(p->n_coarse - 1);
+    std::vector<uint8_t> active(G, 1);
+    const int dev0 = g->w[0]->ctx->dev;
+    int rc = run_all(g, [&](uint32_t r) {
+        eps_ctx* ctx = g->w[r]->ctx;
+        int      st;
+        if (by_energy) {
+            // the n_coarse - 1 grid intervals are split contiguously; a device owning intervals [a, b)
+            // sweeps the points a..b, i.e. shares point b with its right neighbour: every bracket of
+            // the global grid lies in exactly one slice
+            uint32_t a, cnt;
+            shard_block(p->n_coarse - 1, G, r, a, cnt);
+            if (cnt == 0) {
+                active[r] = 0;
+                return static_cast<int>(EPS_OK);
+            }
+            eps_solve_params q = *p;
+            q.n_coarse         = cnt + 1;
+            st = eps_solve_levels_grid(ctx, &q, E_lo, dE.data(), a, nullptr, nullptr, nl.data() + static_cast<size_t>(r) * nC, nullptr);
+        } else {
+            st = eps_solve_levels(ctx, p, E_lo + g->c0[r], E_hi + g->c0[r], nullptr, nullptr, n_below ? n_below + g->c0[r] : nullptr);
+        }
+        if (st) return st;
+        const size_t tot = static_cast<size_t>(g->cn[r]) * nlev;
+        double*      dst = g->d_gather + static_cast<size_t>(r) * g->gather_cap;
+        EPS_CUDA(ctx, cudaMemcpyPeerAsync(dst, dev0, ctx->d_levels.p, ctx->dev, tot * sizeof(double), ctx->stream));
+        EPS_CUDA(ctx, cudaMemcpyPeerAsync(dst + tot, dev0, ctx->d_widths.p, ctx->dev, tot * sizeof(double), ctx->stream));
+        EPS_CUDA(ctx, cudaEventRecord(g->w[r]->posted, ctx->stream));
+        return static_cast<int>(EPS_OK);
+    });
+    if (rc) return rc;
+    // device 0: wait for every peer's copy, then one device->host transfer
+    eps_ctx* c0 = g->w[0]->ctx;
+    cudaSetDevice(c0->dev);
+    for (uint32_t r = 0; r < G; r++)
+        if (active[r]) EPS_CUDA(c0, cudaStreamWaitEvent(c0->stream, g->w[r]->posted, 0));
+    EPS_CUDA(c0, cudaMemcpyAsync(g->h_gather, g->d_gather, g->gather_cap * G * sizeof(double), cudaMemcpyDeviceToHost, c0->stream));
+    EPS_CUDA(c0, cudaStreamSynchronize(c0->stream));
+    c0->stats.d2h_bytes += g->gather_cap * G * sizeof(double);
+    const double nan = std::nan("");
+    if (!by_energy) {
+        for (uint32_t r = 0; r < G; r++) {
+            const size_t tot = static_cast<size_t>(g->cn[r]) * nlev;
+            const double* src = g->h_gather + static_cast<size_t>(r) * g->gather_cap;
+            std::memcpy(levels + static_cast<size_t>(g->c0[r]) * nlev, src, tot * sizeof(double));
+            if (widths) std::memcpy(widths + static_cast<size_t>(g->c0[r]) * nlev, src + tot, tot * sizeof(double));
+        }
+        return EPS_OK;
+    }
+    const size_t tot = static_cast<size_t>(nC) * nlev;
+    for (size_t i = 0; i < tot; i++) {
+        levels[i] = nan;
+        if (widths) widths[i] = nan;
+    }
+    uint32_t last = 0;
+    for (uint32_t r = 0; r < G; r++) {
+        if (!active[r]) continue;
+        last = r;
+        const double* src = g->h_gather + static_cast<size_t>(r) * g->gather_cap;
+        for (size_t i = 0; i < tot; i++) {
+            if (src[i] != src[i]) continue;
+            if (levels[i] == levels[i]) return gfail(g, EPS_ERR_STATE, "a level was located by two devices: energy slices overlap");
+            levels[i] = src[i];
+            if (widths) widths[i] = src[tot + i];
+        }
+    }
+    if (n_below) std::memcpy(n_below, nl.data() + static_cast<size_t>(last) * nC, nC * sizeof(uint32_t));
+    return EPS_OK;
+}
+
+// =====================================================================================================
+// Cross-process mailbox (one process per GPU, e.g. under torchrun): rank 0 owns a device buffer of
+// `world` slots and exports its CUDA IPC handle (64 bytes, moved by whatever rendezvous channel the
+// launcher has); every rank copies its small result into its slot device-to-device (NVLink peer
+// write through the IPC mapping), followed in stream order by a sequence number; rank 0 polls the
+// sequence numbers and fetches all slots with one device->host copy.  Replaces an all-gather + two
+// staging copies + a stream sync through a framework by one peer write.
+// =====================================================================================================
+}  // extern "C"
+
+struct eps_mailbox {
+    eps_ctx*  ctx = nullptr;
+    uint32_t  world = 0, rank = 0;
+    size_t    slot_bytes = 0;   // per rank, multiple of 256
+    bool      owner = false;
+    char*     d_base = nullptr;  // [world][slot_bytes] data, then [world] uint32 sequence numbers (in rank 0's memory)
+    uint32_t* h_seq = nullptr;   // pinned ring of outgoing sequence numbers
+    uint32_t  ring = 0;
+    uint32_t* h_flags = nullptr; // pinned, owner: polled copy of the sequence numbers
+    char*     h_stage = nullptr; // pinned staging for host payloads
+};
+
+extern "C" {
+
+int eps_mailbox_create(eps_ctx* ctx, uint32_t world, size_t bytes_per_rank, eps_mailbox** out, unsigned char* handle64) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, out && handle64 && world >= 1 && bytes_per_rank >= 1, EPS_ERR_INVALID, "bad mailbox arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    auto* mb       = new (std::nothrow) eps_mailbox();
+    EPS_REQUIRE(ctx, mb, EPS_ERR_NOMEM, "out of host memory");
+    mb->ctx        = ctx;
+    mb->world      = world;
+    mb->rank       = 0;
+    mb->owner      = true;
+    mb->slot_bytes = (bytes_per_rank + 255) / 256 * 256;
+    const size_t total = mb->slot_bytes * world + 256 * ((world * sizeof(uint32_t) + 255) / 256);
+    cudaError_t  e     = cudaMalloc(reinterpret_cast<void**>(&mb->d_base), total);
+    if (e == cudaSuccess) e = cudaMemset(mb->d_base, 0, total);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, mb->d_base);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&mb->h_seq), 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&mb->h_flags), world * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&mb->h_stage), mb->slot_bytes);
+    if (e != cudaSuccess) {
+        eps_mailbox_destroy(mb);
+        return fail(ctx, EPS_ERR_CUDA, std::string("eps_mailbox_create: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle64, &h, 64);
+    *out = mb;
+    return EPS_OK;
+}
+
+int eps_mailbox_open(eps_ctx* ctx, const unsigned char* handle64, uint32_t world, uint32_t rank, size_t bytes_per_rank,
+                     eps_mailbox** out) {
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, out && handle64 && rank >= 1 && rank < world && bytes_per_rank >= 1, EPS_ERR_INVALID, "bad mailbox arguments");
+    auto* mb       = new (std::nothrow) eps_mailbox();
+    EPS_REQUIRE(ctx, mb, EPS_ERR_NOMEM, "out of host memory");
+    mb->ctx        = ctx;
+    mb->world      = world;
+    mb->rank       = rank;
+    mb->slot_bytes = (bytes_per_rank + 255) / 256 * 256;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(reinterpret_cast<void**>(&mb->d_base), h, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&mb->h_seq), 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&mb->h_stage), mb->slot_bytes);
+    if (e != cudaSuccess) {
+        const std::string m = std::string("eps_mailbox_open: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        eps_mailbox_destroy(mb);
+        return fail(ctx, EPS_ERR_CUDA, m);
+    }
+    *out = mb;
+    return EPS_OK;
+}
+
+int eps_mailbox_destroy(eps_mailbox* mb) {
+    if (!mb) return EPS_OK;
+    if (mb->ctx && cudaSetDevice(mb->ctx->dev) == cudaSuccess) {
+        if (mb->ctx->stream) cudaStreamSynchronize(mb->ctx->stream);
+        if (mb->d_base) {
+            if (mb->owner) cudaFree(mb->d_base);
+            else cudaIpcCloseMemHandle(mb->d_base);
+        }
+        if (mb->h_seq) cudaFreeHost(mb->h_seq);
+        if (mb->h_flags) cudaFreeHost(mb->h_flags);
+        if (mb->h_stage) cudaFreeHost(mb->h_stage);
+    }
+    delete mb;
+    return EPS_OK;
+}
+
+namespace {
+int mailbox_flag(eps_mailbox* mb, uint32_t seq) {  // sequence number after the payload, in stream order
+    eps_ctx* ctx = mb->ctx;
+    uint32_t* src = mb->h_seq + (mb->ring++ % 64);
+    *src          = seq;
+    uint32_t* flags = reinterpret_cast<uint32_t*>(mb->d_base + mb->slot_bytes * mb->world);
+    EPS_CUDA(ctx, cudaMemcpyAsync(flags + mb->rank, src, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return EPS_OK;
+}
+}  // namespace
+
+/* This rank's levels and widths of its last eps_solve_levels* (device resident), copied
+ * device-to-device into its slot: [levels (n) | widths (n)], n = curves x levels of the last solve. */
+int eps_mailbox_post_levels(eps_mailbox* mb, uint32_t seq) {
+    if (!mb) return fail(nullptr, EPS_ERR_INVALID, "null mailbox");
+    eps_ctx* ctx = mb->ctx;
+    if (int rc = bind(ctx)) return rc;
+    const size_t n = ctx->last_total;
+    EPS_REQUIRE(ctx, n > 0, EPS_ERR_STATE, "no level search has run on this context");
+    EPS_REQUIRE(ctx, 2 * n * sizeof(double) <= mb->slot_bytes, EPS_ERR_INVALID, "mailbox slot too small for the levels");
+    char* dst = mb->d_base + mb->slot_bytes * mb->rank;
+    EPS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_levels.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    EPS_CUDA(ctx, cudaMemcpyAsync(dst + n * sizeof(double), ctx->d_widths.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return mailbox_flag(mb, seq);
+}
+
+/* A small host payload (e.g. a checksum) into this rank's slot. */
+int eps_mailbox_post(eps_mailbox* mb, const void* src, size_t bytes, uint32_t seq) {
+    if (!mb) return fail(nullptr, EPS_ERR_INVALID, "null mailbox");
+    eps_ctx* ctx = mb->ctx;
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, src && bytes <= mb->slot_bytes, EPS_ERR_INVALID, "payload larger than the mailbox slot");
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer may still be in flight
+    std::memcpy(mb->h_stage, src, bytes);
+    EPS_CUDA(ctx, cudaMemcpyAsync(mb->d_base + mb->slot_bytes * mb->rank, mb->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return mailbox_flag(mb, seq);
+}
+
+/* Rank 0: wait until every rank's slot carries `seq`, then fetch all slots ([world][slot]; the slot
+ * stride is eps_mailbox_slot_bytes) with one device->host copy.  EPS_ERR_STATE after timeout_s. */
+int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout_s) {
+    if (!mb) return fail(nullptr, EPS_ERR_INVALID, "null mailbox");
+    eps_ctx* ctx = mb->ctx;
+    if (int rc = bind(ctx)) return rc;
+    EPS_REQUIRE(ctx, mb->owner && out, EPS_ERR_INVALID, "collect is for the mailbox's owner (rank 0)");
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(mb->d_base + mb->slot_bytes * mb->world);
+    const auto      t0    = std::chrono::steady_clock::now();
+    for (;;) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(mb->h_flags, flags, mb->world * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bool all = true;
+        for (uint32_t r = 0; r < mb->world; r++) all = all && mb->h_flags[r] == seq;
+        if (all) break;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+            return fail(ctx, EPS_ERR_STATE, "eps_mailbox_collect: timed out waiting for a rank");
+    }
+    EPS_CUDA(ctx, cudaMemcpyAsync(out, mb->d_base, mb->slot_bytes * mb->world, cudaMemcpyDeviceToHost, ctx->stream));
+    EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += mb->slot_bytes * mb->world;
+    return EPS_OK;
+}
+
+size_t eps_mailbox_slot_bytes(const eps_mailbox* mb) { return mb ? mb->slot_bytes : 0; }
 
 }  // extern "C"

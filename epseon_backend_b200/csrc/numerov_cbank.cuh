@@ -38,7 +38,7 @@ struct CbState {  // per-energy carry between chunk launches, [row * out_stride 
 // grid = n_jobs * chunks_per_job CTAs of kThreads threads, kEpt energies per thread.
 //   len    steps of this chunk (multiple of 128 except for the curve's last chunk)
 //   first  != 0: initialise the state instead of loading it;  last != 0: emit results.
-template <int kEpt, int kThreads, int kStride, bool kTails>
+template <int kEpt, int kThreads, int kStride, bool kTails, int kForm>
 __global__ void __launch_bounds__(kThreads)
 numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ jobs,
                      const uint32_t chunks_per_job, const double* __restrict__ Eexp,
@@ -78,9 +78,9 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
         double E;
         if (Eexp != nullptr) E = Eexp[job.e_off + j];
         else E = __dadd_rn(job.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(job.j0) + j), job.dE));
-        ep[i] = __ddiv_rn(__dmul_rn(scale, E), 12.0);
+        ep[i] = energy_const<kForm>(scale, E);
         if (first) {
-            c[i]       = Chain{1.0, 0.0};
+            c[i]       = kForm == 0 ? Chain{1.0, 0.0} : Chain{1.0, 1.0};
             expo[i]    = 0;
             n_nodes[i] = 0;
             prev[i]    = 0;
@@ -111,12 +111,12 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
                 nxt              = P.f2[(k >> 1) + p + 1];  // uniform index: LDCU into uniform registers
 #pragma unroll
                 for (int i = 0; i < kEpt; i++) {
-                    numerov_step(c[i], ff.x, ep[i]);
+                    step_form<kForm>(c[i], ff.x, ep[i]);
                     if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                 }
 #pragma unroll
                 for (int i = 0; i < kEpt; i++) {
-                    numerov_step(c[i], ff.y, ep[i]);
+                    step_form<kForm>(c[i], ff.y, ep[i]);
                     if (kStride == 1) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                 }
                 if (kStride == 8 && (p & 3) == 3) {
@@ -151,7 +151,7 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
 #pragma unroll
         for (int i = 0; i < kEpt; i++) {
             const uint32_t before = static_cast<uint32_t>(__double2hiint(c[i].X));
-            numerov_step(c[i], Fk, ep[i]);
+            step_form<kForm>(c[i], Fk, ep[i]);
             const uint32_t after = static_cast<uint32_t>(__double2hiint(c[i].X));
             n_nodes[i] += (before ^ after) >> 31;
             prev[i] = (kStride == 1) ? (after >> 31) : after;

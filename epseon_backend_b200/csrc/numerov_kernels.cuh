@@ -151,6 +151,34 @@ __device__ __forceinline__ void numerov_step(Chain& c, const double Fk, const do
     c.S = Sn;
 }
 
+// The ACCURATE recurrence, "D form" (spec DESIGN.md section 3.3; oracle sweep_block, form 1): the
+// chain carries Y_k (in Chain::X) and the scaled first difference D_{k-1} (in Chain::S); the table
+// holds A_k = 12 q_k and the per-energy constant is 12 e.  5 operations, 8 FLOP per step:
+//   T12 = A_k - 12e;  f = fma(-1/12, T12, 1);  t = T12 * Y;  D = fma(f, D, t);  Y' = fma(f, Y, D).
+// Carrying the difference keeps one step's rounding out of the SLOPE of the solution, which every
+// value-carrying form amplifies by 1/sqrt(12 T): eigenvalues agree with the binary128 solution of
+// the discrete problem to ~1e-14 instead of 1e-9 (tests/test_accuracy_floor.py).
+__device__ __forceinline__ void numerov_step_d(Chain& c, const double Ak, const double e12) {
+    const double T12 = __dsub_rn(Ak, e12);
+    const double t   = __dmul_rn(T12, c.X);
+    const double f   = __fma_rn(-(1.0 / 12.0), T12, 1.0);
+    c.S = __fma_rn(f, c.S, t);
+    c.X = __fma_rn(f, c.X, c.S);
+}
+
+template <int kForm>
+__device__ __forceinline__ void step_form(Chain& c, const double Tk, const double ec) {
+    if constexpr (kForm == 0) numerov_step(c, Tk, ec);
+    else numerov_step_d(c, Tk, ec);
+}
+
+// Per-energy constant of a form: e/12 = (s E)/12 (X form) or 12 e = 12 (s E) (D form).
+template <int kForm>
+__device__ __forceinline__ double energy_const(const double s, const double E) {
+    if constexpr (kForm == 0) return __ddiv_rn(__dmul_rn(s, E), 12.0);
+    else return __dmul_rn(12.0, __dmul_rn(s, E));
+}
+
 // Scale (X, S) by the power of two that brings |X| into [1,2); exact.
 __device__ __forceinline__ void renorm(Chain& c, int& expo) {
     const uint32_t ex = (static_cast<uint32_t>(__double2hiint(c.X)) >> 20) & 0x7ffu;
@@ -209,7 +237,7 @@ struct SegOut {
     uint32_t* nA;  // sign flips of X along column A
 };
 
-template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan>
+template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan, int kForm>
 __global__ void __launch_bounds__((kWarps + 1) * 32, (kEpt * kWarps >= 32) ? 1 : 2)
 numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
                      const Job* __restrict__ jobs, const uint32_t chunks_per_job,
@@ -309,8 +337,11 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         double E;
         if (Eexp != nullptr) E = Eexp[jb.e_off + j];
         else E = __dadd_rn(jb.E0, __dmul_rn(__ull2double_rn(static_cast<unsigned long long>(jb.j0) + j), jb.dE));
-        ep[i]      = __ddiv_rn(__dmul_rn(cv.s, E), 12.0);
-        c[i]       = kScan ? (i == 1 ? Chain{0.0, 1.0} : Chain{1.0, 1.0}) : Chain{1.0, 0.0};
+        ep[i]      = energy_const<kForm>(cv.s, E);
+        // start: psi = 0 one point to the left.  X form (X, S) = (1, 0); D form (Y, D) = (1, 1).
+        // Scan basis: "flat" / "unit slope" = (X, D) = (1, 0) / (0, 1), i.e. (X, S) = (1, 1) / (0, 1) in the X form.
+        if (kForm == 0) c[i] = kScan ? (i == 1 ? Chain{0.0, 1.0} : Chain{1.0, 1.0}) : Chain{1.0, 0.0};
+        else c[i] = kScan ? (i == 1 ? Chain{0.0, 1.0} : Chain{1.0, 0.0}) : Chain{1.0, 1.0};
         expo[i]    = 0;
         n_nodes[i] = 0;
         prev[i]    = 0;  // kStride==1: bit0 = sign of the last X; else: hi word of the last sampled X
@@ -338,20 +369,20 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                     if (kScan) {  // the two basis chains share fp: both steps of a chain back to back
 #pragma unroll              // (30 instead of 3 of the 83 three-register DFMAs then take fp from the reuse cache)
                         for (int i = 0; i < kEpt; i++) {
-                            numerov_step(c[i], ff.x, ep[0]);
+                            step_form<kForm>(c[i], ff.x, ep[0]);
                             if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
-                            numerov_step(c[i], ff.y, ep[0]);
+                            step_form<kForm>(c[i], ff.y, ep[0]);
                             if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                         }
                     } else {
 #pragma unroll
                         for (int i = kEpt - 1; i >= 0; i--) {
-                            numerov_step(c[i], ff.x, ep[i]);
+                            step_form<kForm>(c[i], ff.x, ep[i]);
                             if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                         }
 #pragma unroll
                         for (int i = 0; i < kEpt; i++) {
-                            numerov_step(c[i], ff.y, ep[i]);
+                            step_form<kForm>(c[i], ff.y, ep[i]);
                             if (kStride == 1 && i < kCnt) mask[i] = __funnelshift_l(static_cast<uint32_t>(__double2hiint(c[i].X)), mask[i], 1);
                         }
                     }
@@ -386,7 +417,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 #pragma unroll
             for (int i = 0; i < kEpt; i++) {
                 const uint32_t before = static_cast<uint32_t>(__double2hiint(c[i].X));
-                numerov_step(c[i], Fk, ep[kScan ? 0 : i]);
+                step_form<kForm>(c[i], Fk, ep[kScan ? 0 : i]);
                 const uint32_t after = static_cast<uint32_t>(__double2hiint(c[i].X));
                 n_nodes[i] += (before ^ after) >> 31;
                 prev[i] = (kStride == 1) ? (after >> 31) : after;
@@ -403,9 +434,9 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         if (j < job.nE) {
             const uint64_t o = (static_cast<uint64_t>(job_idx) * n_seg + seg) * out_stride + j;
             seg_out.XA[o] = c[0].X;
-            seg_out.SA[o] = __dsub_rn(c[0].S, c[0].X);
+            seg_out.SA[o] = kForm == 0 ? __dsub_rn(c[0].S, c[0].X) : c[0].S;  // D form: S already holds D
             seg_out.XB[o] = c[1].X;
-            seg_out.SB[o] = __dsub_rn(c[1].S, c[1].X);
+            seg_out.SB[o] = kForm == 0 ? __dsub_rn(c[1].S, c[1].X) : c[1].S;
             seg_out.eA[o] = expo[0];
             seg_out.eB[o] = expo[1];
             seg_out.nA[o] = n_nodes[0];
@@ -459,12 +490,12 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
                                        uint32_t n_seg, uint64_t out_stride,
                                        uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                                        int32_t* __restrict__ exp_out, uint32_t* __restrict__ n_flagged,
-                                       uint2* __restrict__ flagged, uint32_t flagged_cap) {
+                                       uint2* __restrict__ flagged, uint32_t flagged_cap, const double D_start) {
     const uint32_t row = blockIdx.x;  // rows on grid.x (up to 2^31 - 1 of them), energy blocks on grid.y
     const uint32_t j   = blockIdx.y * blockDim.x + threadIdx.x;
     if (row >= n_jobs || j >= jobs[row].nE) return;
     constexpr double kEta = 5.820766091346741e-11;  // 2^-34
-    double   X = 1.0, D = -1.0, rho = 0.0;
+    double   X = 1.0, D = D_start, rho = 0.0;  // start state in (X, D): X form (1, S - X = -1), D form (1, 1)
     int      ex = 0;
     uint32_t nodes = 0;
     for (uint32_t sgm = 0; sgm < n_seg; sgm++) {
@@ -823,7 +854,7 @@ constexpr int kPrepThreads = 512;
 
 __global__ void __launch_bounds__(kPrepThreads)
 prep_curves_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint64_t slot,
-                   double t_max, double* __restrict__ F, CurveDev* __restrict__ curves,
+                   double t_max, double* __restrict__ F, double* __restrict__ A, CurveDev* __restrict__ curves,
                    PrepOut* __restrict__ out) {
     __shared__ double   red_q[kPrepThreads / 32];
     __shared__ uint32_t red_i[kPrepThreads / 32];
@@ -915,6 +946,10 @@ prep_curves_kernel(const double* __restrict__ V, const double* __restrict__ scal
     double* dst = F + static_cast<uint64_t>(c) * slot;
     for (uint64_t k = tid; k < slot; k += kPrepThreads)
         dst[k] = (k < n) ? __ddiv_rn(__dsub_rn(1.0, __dmul_rn(s, v[i0 + k])), 12.0) : 1.0 / 12.0;
+    if (A != nullptr) {  // D-form table A_k = 12 q_k in the same slot layout (pad 0)
+        double* dsa = A + static_cast<uint64_t>(c) * slot;
+        for (uint64_t k = tid; k < slot; k += kPrepThreads) dsa[k] = (k < n) ? __dmul_rn(12.0, __dmul_rn(s, v[i0 + k])) : 0.0;
+    }
     if (tid == 0) {
         const double vm = (m != kNone) ? v[m] : __longlong_as_double(0x7ff8000000000000LL);  // no finite value at all
         curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, vm};
@@ -1057,7 +1092,7 @@ prep_part_window_kernel(const double* __restrict__ V, const double* __restrict__
 __global__ void __launch_bounds__(kPrepThreads)
 prep_part_finish_kernel(const double* __restrict__ V, const double* __restrict__ scale, uint32_t N, uint64_t slot,
                         uint32_t parts, const PrepPart* __restrict__ pp_all, double* __restrict__ F,
-                        CurveDev* __restrict__ curves, PrepOut* __restrict__ out) {
+                        double* __restrict__ A, CurveDev* __restrict__ curves, PrepOut* __restrict__ out) {
     const uint32_t  c = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
     const double*   v  = V + static_cast<uint64_t>(c) * N;
     const double    s  = scale[c];
@@ -1079,6 +1114,10 @@ prep_part_finish_kernel(const double* __restrict__ V, const double* __restrict__
     double*        dst = F + static_cast<uint64_t>(c) * slot;
     for (uint64_t k = k_lo + tid; k < k_hi; k += kPrepThreads)
         dst[k] = (k < n) ? __ddiv_rn(__dsub_rn(1.0, __dmul_rn(s, v[i0 + k])), 12.0) : 1.0 / 12.0;
+    if (A != nullptr) {
+        double* dsa = A + static_cast<uint64_t>(c) * slot;
+        for (uint64_t k = k_lo + tid; k < k_hi; k += kPrepThreads) dsa[k] = (k < n) ? __dmul_rn(12.0, __dmul_rn(s, v[i0 + k])) : 0.0;
+    }
     if (part == 0 && tid == 0) {
         const double vm = (m != kNone) ? v[m] : __longlong_as_double(0x7ff8000000000000LL);
         curves[c] = CurveDev{static_cast<uint64_t>(c) * slot, n, i0, s, vm};

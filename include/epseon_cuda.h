@@ -102,6 +102,8 @@ typedef struct eps_stats {
     uint64_t grid_steps;       /* grid-steps x trial-energies executed by sweeps   */
     double   sweep_ms;         /* summed CUDA-event time of the sweep launches     */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kernel_launches;  /* every kernel launched: each sweep kernel (a constant-bank sweep
+                                  is one launch per 3968-step chunk) + other_launches          */
 } eps_stats;
 
 /* ---- devices and contexts (replaces ComputeContext::getPhysicalDevicesInfo /
@@ -215,9 +217,16 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   the launch qualifies, 2 = never.  EPS_OPT_CBANK_SHAPE, EPS_OPT_CBANK_PDL: tuning knobs.
  * EPS_OPT_PREP_PARTS: eps_set_potentials* prepares few long curves (<= 64 curves of >= 65 536
  *   points) with every curve cut into chunks over many CTAs; 0 = automatic, 1 = never (one CTA
- *   per curve).  Identical results. */
+ *   per curve).  Identical results.
+ * EPS_OPT_FORM: the recurrence every later eps_set_potentials* prepares its tables for, and every
+ *   sweep on them then runs.  0 (default) = X form: 4 FP64 operations per
+ *   grid step, eigenvalue rounding-noise floor ~1e-9 relative at 2e5 grid points and ~2e-8 at 1e6.
+ *   1 = D form ("accurate"): the chain carries the first difference, 5 operations per step,
+ *   eigenvalues within ~1e-14 of the binary128 solution of the discrete problem at every grid size
+ *   (tests/test_accuracy_floor.py).  Node counts and levels of each form are bit-identical to the
+ *   oracle's same form; the two forms agree with each other to the X form's noise floor. */
 enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5,
-       EPS_OPT_PREP_PARTS = 6 };
+       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7 };
 enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2, EPS_CNT_CBANK_LAUNCHES = 3 };
 int eps_set_option(eps_ctx* ctx, int option, int64_t value);
 int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);
@@ -241,6 +250,51 @@ int eps_wavefunctions(eps_ctx* ctx, const double* E, uint32_t n_levels, const do
  * with a loose tolerance.  dE[n_curves][n_levels] (host). */
 int eps_level_corrections(eps_ctx* ctx, const double* E, uint32_t n_levels, const double* grid_step,
                           double* dE);
+
+/* ---- several devices in ONE process ("one process, G host threads, one eps_ctx per
+ * device"; the reference gives one device per task, device_interface.hpp:22 -- additive).  A group
+ * owns one context and one host thread per device.  The path shards without any exchange during
+ * compute; only the located levels are gathered: every device writes them into a buffer on the
+ * group's first device with cudaMemcpyPeerAsync (NVLink when peer access exists), one
+ * device->host copy returns them.
+ *   EPS_SHARD_CURVES: contiguous blocks of curves per device.
+ *   EPS_SHARD_ENERGY: every device holds all curves and works on a contiguous slice of the ONE
+ *     global energy grid (slices of neighbours share one grid point), so sweeps and level searches
+ *     return exactly the bits of a single-device call.
+ * Arrays are host pointers for the WHOLE job ([n_curves] / [n_curves][n]).  eps_group_ctx lends a
+ * device's context (options, counters, stats); eps_group_last_ms = max over the devices of the
+ * CUDA-event time of the last group call. */
+typedef struct eps_group eps_group;
+enum { EPS_SHARD_CURVES = 0, EPS_SHARD_ENERGY = 1 };
+int         eps_group_create(const int* devices, uint32_t n_devices, eps_group** out);
+int         eps_group_destroy(eps_group* g);
+uint32_t    eps_group_size(const eps_group* g);
+eps_ctx*    eps_group_ctx(eps_group* g, uint32_t rank);
+const char* eps_group_last_error(const eps_group* g);
+int         eps_group_last_ms(eps_group* g, float* ms);
+int         eps_group_set_option(eps_group* g, int option, int64_t value);
+int         eps_group_set_potentials(eps_group* g, const double* V, uint32_t n_curves, uint32_t n_points,
+                                     const double* scale, int shard);
+int         eps_group_sweep_uniform(eps_group* g, const double* E_lo, const double* E_hi, uint64_t n_energies,
+                                    uint32_t* nodes);
+int         eps_group_solve_levels(eps_group* g, const eps_solve_params* p, const double* E_lo, const double* E_hi,
+                                   double* levels, double* widths, uint32_t* n_below);
+
+/* ---- one process per device (e.g. under torchrun): a mailbox in rank 0's device memory, shared
+ * through a CUDA IPC handle (64 bytes; the caller moves it between the processes).  Every rank
+ * writes its small result into its slot device-to-device (a peer write over NVLink) followed by a
+ * sequence number in stream order; rank 0 waits for all sequence numbers and fetches every slot
+ * with one device->host copy.  Slot layout of eps_mailbox_post_levels: [levels | widths] of the
+ * rank's last level search. */
+typedef struct eps_mailbox eps_mailbox;
+int    eps_mailbox_create(eps_ctx* ctx, uint32_t world, size_t bytes_per_rank, eps_mailbox** out, unsigned char* handle64);
+int    eps_mailbox_open(eps_ctx* ctx, const unsigned char* handle64, uint32_t world, uint32_t rank, size_t bytes_per_rank,
+                        eps_mailbox** out);
+int    eps_mailbox_destroy(eps_mailbox* mb);
+int    eps_mailbox_post_levels(eps_mailbox* mb, uint32_t seq);
+int    eps_mailbox_post(eps_mailbox* mb, const void* src, size_t bytes, uint32_t seq);
+int    eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout_s);
+size_t eps_mailbox_slot_bytes(const eps_mailbox* mb);
 
 /* ---- page-locked host buffers (optional) ---------------------------------
  * Every entry point accepts ANY host pointer.  Tables and result arrays that live in memory

@@ -140,8 +140,16 @@ double orc_scale(double m0, double m1, double h) {
  * F_k = (1 - q_{i0+k}) / 12,  k = 0 .. n_steps-1  (so f_k/12 = F_k + e/12).
  * F must hold N doubles.  Returns 0, or -1 when the table is unusable
  * (non-finite values, or fewer than 2 steps). */
+int orc_prep_form(const double* V, uint32_t N, double s, int form, double* F, uint32_t* i0_out,
+                  uint32_t* n_steps_out, double* vmin_out);
 int orc_prep(const double* V, uint32_t N, double s, double* F, uint32_t* i0_out,
              uint32_t* n_steps_out, double* vmin_out) {
+    return orc_prep_form(V, N, s, 0, F, i0_out, n_steps_out, vmin_out);
+}
+
+/* form 0: F_k = (1 - q_k)/12 (X form).  form 1: A_k = 12 q_k (D form). */
+int orc_prep_form(const double* V, uint32_t N, double s, int form, double* F, uint32_t* i0_out,
+                  uint32_t* n_steps_out, double* vmin_out) {
     if (N < 3) return -1;
     uint32_t m = 0;
     for (uint32_t i = 0; i < N; i++) {
@@ -162,7 +170,7 @@ int orc_prep(const double* V, uint32_t N, double s, double* F, uint32_t* i0_out,
     const uint32_t n = iend - i0;
     for (uint32_t k = 0; k < n; k++) {
         const double q = s * V[i0 + k];
-        F[k]           = (1.0 - q) / 12.0;
+        F[k]           = form == 0 ? (1.0 - q) / 12.0 : 12.0 * q;
     }
     *i0_out      = i0;
     *n_steps_out = n;
@@ -193,32 +201,64 @@ static inline void renorm(double* X, double* S, int32_t* expo) {
  *     S_k  = fp * X_k                      (1 mul)
  * X_k has the sign of psi_k while every f_j > 0; node = sign-bit flip between
  * consecutive X.  Start: X = 1, S = 0 (psi = 0 one point to the left). */
-static void sweep_block(const double* F, uint32_t n_steps, double s, const double* E, int nb,
+/* The ACCURATE recurrence, "D form" (form 1) -- 5 operations per step:
+ * with Pi_k = prod_{j<k} f_j,  Y_k = f_k psi_k Pi_k  and  D_k = Y_{k+1} - f_k Y_k  (the scaled
+ * first difference), the same textbook recurrence reads
+ *     T12 = A_k - 12 e                      (1 add;  A_k = 12 q_k,  12 T_k = 12 (q_k - e))
+ *     f   = fma(-1/12, T12, 1)              (1 fma)
+ *     t   = T12 * Y_k                       (1 mul)
+ *     D_k = fma(f, D_{k-1}, t)              (1 fma)
+ *     Y'  = fma(f, Y_k, D_k)                (1 fma)
+ * Start Y = 1, D = 1 (psi = 0 one point to the left).  Carrying the first difference instead of
+ * the previous value keeps the rounding of one step from entering the SLOPE of the solution, which
+ * in any value-carrying form (X, Y) is amplified by 1/sqrt(12 T) ~ 10^2..10^3 on fine grids:
+ * measured eigenvalue noise (vs binary128, tests/test_accuracy_floor.py) falls from 2e-9 (C5) /
+ * 2e-8 (C3) to ~1e-11.  Y_k has the sign of psi_k while every f_j > 0. */
+static void sweep_block(const double* F, uint32_t n_steps, double s, const double* E, int nb, int form,
                         uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
     double   ep[ORC_EB], X[ORC_EB], S[ORC_EB];
     int64_t  cnt[ORC_EB];
     int32_t  ex[ORC_EB];
     for (int b = 0; b < ORC_EB; b++) {
         const double Eb = E[b < nb ? b : nb - 1];
-        ep[b]  = (s * Eb) / 12.0;
+        ep[b]  = form == 0 ? (s * Eb) / 12.0 : 12.0 * (s * Eb);
         X[b]   = 1.0;
-        S[b]   = 0.0;
+        S[b]   = form == 0 ? 0.0 : 1.0;
         cnt[b] = 0;
         ex[b]  = 0;
     }
-    for (uint32_t k = 0; k < n_steps; k++) {
-        const double Fk = F[k];
+    if (form == 0) {
+        for (uint32_t k = 0; k < n_steps; k++) {
+            const double Fk = F[k];
 #pragma omp simd
-        for (int b = 0; b < ORC_EB; b++) {
-            const double fp = Fk + ep[b];
-            const double Q  = fma(10.0, X[b], S[b]);
-            const double Xn = fma(-fp, Q, X[b]);
-            S[b]            = fp * X[b];
-            cnt[b] += (int64_t)((d2u(Xn) ^ d2u(X[b])) >> 63);
-            X[b] = Xn;
+            for (int b = 0; b < ORC_EB; b++) {
+                const double fp = Fk + ep[b];
+                const double Q  = fma(10.0, X[b], S[b]);
+                const double Xn = fma(-fp, Q, X[b]);
+                S[b]            = fp * X[b];
+                cnt[b] += (int64_t)((d2u(Xn) ^ d2u(X[b])) >> 63);
+                X[b] = Xn;
+            }
+            if (((k + 1) % ORC_RENORM_PERIOD) == 0)
+                for (int b = 0; b < ORC_EB; b++) renorm(&X[b], &S[b], &ex[b]);
         }
-        if (((k + 1) % ORC_RENORM_PERIOD) == 0)
-            for (int b = 0; b < ORC_EB; b++) renorm(&X[b], &S[b], &ex[b]);
+    } else {
+        const double nC = -(1.0 / 12.0);
+        for (uint32_t k = 0; k < n_steps; k++) {
+            const double Ak = F[k];
+#pragma omp simd
+            for (int b = 0; b < ORC_EB; b++) {
+                const double T12 = Ak - ep[b];
+                const double f   = fma(nC, T12, 1.0);
+                const double t   = T12 * X[b];
+                S[b]             = fma(f, S[b], t);
+                const double Yn  = fma(f, X[b], S[b]);
+                cnt[b] += (int64_t)((d2u(Yn) ^ d2u(X[b])) >> 63);
+                X[b] = Yn;
+            }
+            if (((k + 1) % ORC_RENORM_PERIOD) == 0)
+                for (int b = 0; b < ORC_EB; b++) renorm(&X[b], &S[b], &ex[b]);
+        }
     }
     for (int b = 0; b < nb; b++) {
         renorm(&X[b], &S[b], &ex[b]);
@@ -229,22 +269,34 @@ static void sweep_block(const double* F, uint32_t n_steps, double s, const doubl
 }
 
 /* Sweep explicit energies E[0..nE). Any output pointer may be NULL. */
+void orc_sweep_form(const double* F, uint32_t n_steps, double s, int form, const double* E, uint64_t nE,
+                    uint32_t* nodes, double* tail_mant, int32_t* tail_exp);
 void orc_sweep(const double* F, uint32_t n_steps, double s, const double* E, uint64_t nE,
                uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
+    orc_sweep_form(F, n_steps, s, 0, E, nE, nodes, tail_mant, tail_exp);
+}
+void orc_sweep_form(const double* F, uint32_t n_steps, double s, int form, const double* E, uint64_t nE,
+                    uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
     const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
 #pragma omp parallel for schedule(static)
     for (int64_t blk = 0; blk < nblk; blk++) {
         const uint64_t o  = (uint64_t)blk * ORC_EB;
         const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
-        sweep_block(F, n_steps, s, E + o, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+        sweep_block(F, n_steps, s, E + o, nb, form, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
                     tail_exp ? tail_exp + o : 0);
     }
 }
 
 /* Uniform grid E_j = E0 + j*dE, j = j0 .. j0+nE-1 (one multiply, one add). */
+void orc_sweep_uniform_form(const double* F, uint32_t n_steps, double s, int form, double E0, double dE,
+                            uint64_t j0, uint64_t nE, uint32_t* nodes, double* tail_mant, int32_t* tail_exp);
 void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, double dE,
                        uint64_t j0, uint64_t nE, uint32_t* nodes, double* tail_mant,
                        int32_t* tail_exp) {
+    orc_sweep_uniform_form(F, n_steps, s, 0, E0, dE, j0, nE, nodes, tail_mant, tail_exp);
+}
+void orc_sweep_uniform_form(const double* F, uint32_t n_steps, double s, int form, double E0, double dE,
+                            uint64_t j0, uint64_t nE, uint32_t* nodes, double* tail_mant, int32_t* tail_exp) {
     const int64_t nblk = (int64_t)((nE + ORC_EB - 1) / ORC_EB);
 #pragma omp parallel for schedule(static)
     for (int64_t blk = 0; blk < nblk; blk++) {
@@ -252,7 +304,7 @@ void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, d
         const int      nb = (int)((nE - o) < ORC_EB ? (nE - o) : ORC_EB);
         double         Eb[ORC_EB];
         for (int b = 0; b < nb; b++) Eb[b] = E0 + (double)(j0 + o + (uint64_t)b) * dE;
-        sweep_block(F, n_steps, s, Eb, nb, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
+        sweep_block(F, n_steps, s, Eb, nb, form, nodes ? nodes + o : 0, tail_mant ? tail_mant + o : 0,
                     tail_exp ? tail_exp + o : 0);
     }
 }
@@ -270,10 +322,21 @@ void orc_sweep_uniform(const double* F, uint32_t n_steps, double s, double E0, d
  *   result:  0.5*(lo+hi).
  * All decisions are integer comparisons of node counts.  Returns the number of
  * refinement rounds used; *steps_done gets grid-steps x energies executed. */
+int orc_solve_levels_grid_form(const double* F, uint32_t n_steps, double s, int form, double E0, double dE, uint64_t j0,
+                               uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
+                               uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
+                               uint32_t* n_first, uint64_t* steps_done);
 int orc_solve_levels_grid(const double* F, uint32_t n_steps, double s, double E0, double dE, uint64_t j0,
                           uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
-                     uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
+                          uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
                           uint32_t* n_first, uint64_t* steps_done) {
+    return orc_solve_levels_grid_form(F, n_steps, s, 0, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol, max_rounds, levels,
+                                      widths, n_below_hi, n_first, steps_done);
+}
+int orc_solve_levels_grid_form(const double* F, uint32_t n_steps, double s, int form, double E0, double dE, uint64_t j0,
+                               uint32_t n_coarse, uint32_t vmin, uint32_t vmax, uint32_t M, double rel_tol,
+                               uint32_t max_rounds, double* levels, double* widths, uint32_t* n_below_hi,
+                               uint32_t* n_first, uint64_t* steps_done) {
     const uint32_t nlev  = vmax - vmin + 1;
     uint64_t       steps = 0;
     uint32_t*      nodes = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n_coarse > M ? n_coarse : M));
@@ -281,7 +344,7 @@ int orc_solve_levels_grid(const double* F, uint32_t n_steps, double s, double E0
     double*        hi    = (double*)malloc(sizeof(double) * nlev);
     uint8_t*       act   = (uint8_t*)malloc(nlev);
 
-    orc_sweep_uniform(F, n_steps, s, E0, dE, j0, n_coarse, nodes, 0, 0);
+    orc_sweep_uniform_form(F, n_steps, s, form, E0, dE, j0, n_coarse, nodes, 0, 0);
     steps += (uint64_t)n_steps * n_coarse;
     if (n_below_hi) *n_below_hi = nodes[n_coarse - 1];
     if (n_first) *n_first = nodes[0];
@@ -312,7 +375,7 @@ int orc_solve_levels_grid(const double* F, uint32_t n_steps, double s, double E0
             const uint32_t v    = vmin + l;
             const double   step = (hi[l] - lo[l]) / (double)(M + 1);
             /* points m = 1..M are j = 1..M of the grid E0=lo, dE=step */
-            orc_sweep_uniform(F, n_steps, s, lo[l], step, 1, M, nodes, 0, 0);
+            orc_sweep_uniform_form(F, n_steps, s, form, lo[l], step, 1, M, nodes, 0, 0);
             steps += (uint64_t)n_steps * M;
             uint32_t m = 1;
             while (m <= M && nodes[m - 1] <= v) m++;

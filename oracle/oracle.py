@@ -32,9 +32,10 @@ _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 def build_oracle(force: bool = False) -> None:
     """Compile the oracle with gcc (a few seconds)."""
-    src = _HERE / "numerov_oracle.c"
-    libs = [_BUILD / "liboracle.so", _BUILD / "liboracle_omp.so"]
-    if not force and all(p.exists() and p.stat().st_mtime >= src.stat().st_mtime for p in libs):
+    srcs = [_HERE / "numerov_oracle.c", _HERE / "numerov_quad.c", _HERE / "Makefile"]
+    libs = [_BUILD / "liboracle.so", _BUILD / "liboracle_omp.so", _BUILD / "libquad.so"]
+    newest = max(p.stat().st_mtime for p in srcs)
+    if not force and all(p.exists() and p.stat().st_mtime >= newest for p in libs):
         return
     subprocess.run(["make", "-s", "-C", str(_HERE), f"OUT={_BUILD}"] + (["-B"] if force else []),
                    check=True)
@@ -54,8 +55,11 @@ class Oracle:
     host threads); used for the timed CPU baseline.
     """
 
-    def __init__(self, omp: bool = False, threads: int | None = None):
+    def __init__(self, omp: bool = False, threads: int | None = None, form: int = 0):
+        """form 0: the 4-operation X form (default); form 1: the accurate 5-operation D form.  The
+        table returned by prep() and taken by the sweeps is the one of that form."""
         build_oracle()
+        self.form = int(form)
         self.lib = C.CDLL(str(_BUILD / ("liboracle_omp.so" if omp else "liboracle.so")))
         L = self.lib
         if omp and threads:
@@ -65,20 +69,20 @@ class Oracle:
         L.orc_scale.argtypes = [C.c_double] * 3
         L.orc_morse_tabulate.argtypes = [C.c_double] * 5 + [C.c_uint32, _f64p]
         L.orc_lj_tabulate.argtypes = [C.c_double] * 4 + [C.c_uint32, _f64p]
-        L.orc_prep.restype = C.c_int
-        L.orc_prep.argtypes = [_f64p, C.c_uint32, C.c_double, _f64p, C.POINTER(C.c_uint32),
-                               C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
-        L.orc_sweep.argtypes = [_f64p, C.c_uint32, C.c_double, _f64p, C.c_uint64,
-                                C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_sweep_uniform.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double,
-                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_prep_form.restype = C.c_int
+        L.orc_prep_form.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_int, _f64p, C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+        L.orc_sweep_form.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_int, _f64p, C.c_uint64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sweep_uniform_form.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_int, C.c_double, C.c_double,
+                                             C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_solve_levels.restype = C.c_int
         L.orc_solve_levels.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                        C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64)]
-        L.orc_solve_levels_grid.restype = C.c_int
-        L.orc_solve_levels_grid.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint64,
+        L.orc_solve_levels_grid_form.restype = C.c_int
+        L.orc_solve_levels_grid_form.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_int, C.c_double, C.c_double, C.c_uint64,
                                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                             C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
@@ -119,7 +123,7 @@ class Oracle:
         V = np.ascontiguousarray(V, dtype=np.float64)
         AB = np.empty(V.size, dtype=np.float64)
         i0, n, vmin = C.c_uint32(), C.c_uint32(), C.c_double()
-        rc = self.lib.orc_prep(V, V.size, s, AB, C.byref(i0), C.byref(n), C.byref(vmin))
+        rc = self.lib.orc_prep_form(V, V.size, s, self.form, AB, C.byref(i0), C.byref(n), C.byref(vmin))
         if rc != 0:
             raise ValueError("orc_prep: unusable potential table")
         return AB[: n.value].copy(), i0.value, n.value, vmin.value
@@ -130,7 +134,7 @@ class Oracle:
         nodes = np.empty(E.size, dtype=np.uint32)
         mant = np.empty(E.size, dtype=np.float64) if tails else None
         expo = np.empty(E.size, dtype=np.int32) if tails else None
-        self.lib.orc_sweep(AB, n_steps, s, E, E.size, _opt(nodes, np.uint32),
+        self.lib.orc_sweep_form(AB, n_steps, s, self.form, E, E.size, _opt(nodes, np.uint32),
                            _opt(mant, np.float64), _opt(expo, np.int32))
         return nodes, mant, expo
 
@@ -139,7 +143,7 @@ class Oracle:
         nodes = np.empty(nE, dtype=np.uint32)
         mant = np.empty(nE, dtype=np.float64) if tails else None
         expo = np.empty(nE, dtype=np.int32) if tails else None
-        self.lib.orc_sweep_uniform(AB, n_steps, s, E0, dE, j0, nE, _opt(nodes, np.uint32),
+        self.lib.orc_sweep_uniform_form(AB, n_steps, s, self.form, E0, dE, j0, nE, _opt(nodes, np.uint32),
                                    _opt(mant, np.float64), _opt(expo, np.int32))
         return nodes, mant, expo
 
@@ -151,9 +155,10 @@ class Oracle:
         levels = np.empty(nlev, dtype=np.float64)
         widths = np.empty(nlev, dtype=np.float64)
         nb, st = C.c_uint32(), C.c_uint64()
-        rounds = self.lib.orc_solve_levels(AB, n_steps, s, E_lo, E_hi, n_coarse, vmin, vmax, M,
-                                           rel_tol, max_rounds, levels, widths, C.byref(nb),
-                                           C.byref(st))
+        dE = (E_hi - E_lo) / float(n_coarse - 1)  # orc_solve_levels: uniform grid, j0 = 0
+        rounds = self.lib.orc_solve_levels_grid_form(AB, n_steps, s, self.form, E_lo, dE, 0, n_coarse, vmin, vmax, M,
+                                                     rel_tol, max_rounds, levels, widths, C.byref(nb), None,
+                                                     C.byref(st))
         return levels, widths, nb.value, rounds, st.value
 
     def solve_levels_grid(self, AB, s, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol=1e-12, max_rounds=8):
@@ -162,7 +167,7 @@ class Oracle:
         levels = np.empty(nlev, dtype=np.float64)
         widths = np.empty(nlev, dtype=np.float64)
         nb, nf, st = C.c_uint32(), C.c_uint32(), C.c_uint64()
-        rounds = self.lib.orc_solve_levels_grid(AB, AB.size, s, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol,
+        rounds = self.lib.orc_solve_levels_grid_form(AB, AB.size, s, self.form, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol,
                                                 max_rounds, levels, widths, C.byref(nb), C.byref(nf), C.byref(st))
         return levels, widths, nb.value, nf.value, rounds, st.value
 
@@ -185,3 +190,33 @@ class Oracle:
         if self.lib.orc_spline_resample(r, V, r.size, float(rmin), float(rmax), N, out) != 0:
             raise ValueError("orc_spline_resample: bad knots")
         return out
+
+
+class QuadReference:
+    """Independent binary128 solution of the discrete Numerov eigenproblem (oracle/numerov_quad.c):
+    textbook recurrence with a division per step, bisection on the node count to 2^-100."""
+
+    def __init__(self):
+        build_oracle()
+        self.lib = C.CDLL(str(_BUILD / "libquad.so"))
+        L = self.lib
+        L.quad_node_count.restype = C.c_uint32
+        L.quad_node_count.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double]
+        L.quad_levels.restype = None
+        L.quad_levels.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, _f64p, _f64p, _f64p]
+
+    def set_table_kind(self, kind: int) -> None:
+        """0: table F_k = (1 - q_k)/12 (X form, default); 1: table A_k = 12 q_k (D form)."""
+        self.lib.quad_set_table_kind(C.c_int(kind))
+
+    def node_count(self, F, s, E) -> int:
+        return int(self.lib.quad_node_count(np.ascontiguousarray(F), F.size, float(s), float(E)))
+
+    def levels(self, F, s, v_min, v_max, brackets):
+        """brackets[nlev, 2] = (E_lo, E_hi) per level -> (E as double, remainder): E = hi + lo to ~1e-30."""
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        br = np.ascontiguousarray(brackets, dtype=np.float64).reshape(-1)
+        n = v_max - v_min + 1
+        hi, lo = np.empty(n), np.empty(n)
+        self.lib.quad_levels(F, F.size, float(s), v_min, v_max, br, hi, lo)
+        return hi, lo

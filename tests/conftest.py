@@ -21,6 +21,15 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def oracle_d():
+    """The oracle's statement of the accurate D form (EPS_OPT_FORM = 1): what the drop-in
+    VibwaAlgorithm<FP>::run uses."""
+    from oracle import Oracle
+
+    return Oracle(form=1)
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     """One C-ABI context on cuda:0; fails loudly (no fallback) when the library or GPU is missing."""
     import __graft_entry__ as ge

@@ -16,6 +16,23 @@ from oracle import Oracle  # noqa: E402
 from tests import workloads as W  # noqa: E402
 
 
+class GlooComm:
+    """The `comm` protocol of epseon_backend_b200.multi (world, rank, gather) over torch.distributed /
+    gloo -- test plumbing; the product's carriers are eps_group_* and eps_mailbox_* (CUDA)."""
+
+    def __init__(self):
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+
+    def gather(self, arr):
+        import torch
+
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t)
+        return [o.numpy().view(a.dtype).reshape(a.shape) for o in outs]
+
+
 class OracleSolver:
     """cabi.Context look-alike over the oracle (tests only)."""
 
@@ -41,11 +58,12 @@ class OracleSolver:
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    comm = GlooComm()
     # --- energy-range sharding of one solve == single-process solve, bit for bit
     w = W.c4(nC=3, N=3000, nE=257)
     solver = OracleSolver(w["V"], w["s"])
     for n_coarse in (257, 64, 2 * world, 3):
-        lev, wid, nb = multi.solve_levels_energy_sharded(solver, dist, w["E_lo"], w["E_hi"], n_coarse, 0, 9, 32, 1e-12, 10)
+        lev, wid, nb = multi.solve_levels_energy_sharded(solver, comm, w["E_lo"], w["E_hi"], n_coarse, 0, 9, 32, 1e-12, 10)
         for c in range(3):
             ref = solver.orc.solve_levels(solver.F[c], w["s"], w["E_lo"][c], w["E_hi"][c], n_coarse, 0, 9, 32, 1e-12, 10)
             assert np.array_equal(lev[c].view(np.uint64), ref[0].view(np.uint64)), (rank, n_coarse, c, lev[c], ref[0])
@@ -60,7 +78,7 @@ def main():
     lev, *_ = mine.solve_levels_grid(lo, dE, 0, 128, 0, 5, 32, 1e-12, 10)
     pad = np.full((4, 6), np.nan)  # equal shapes for the gather (7 curves over 2 ranks: 4 + 3)
     pad[: lev.shape[0]] = lev
-    parts = multi.all_gather_array(dist, pad)
+    parts = comm.gather(pad)
     full = np.concatenate([parts[r][: (multi.curve_shard(7, world, r).stop - multi.curve_shard(7, world, r).start)]
                            for r in range(world)])
     whole = OracleSolver(w["V"], w["s"])

@@ -196,7 +196,7 @@ class TestEpseonComputeContext:
 
 # ----------------------------------------------------------------------------- GPU (results: additive API)
 @pytest.mark.gpu
-def test_levels_of_reference_fixture(gpu_mod, oracle):
+def test_levels_of_reference_fixture(gpu_mod, oracle, oracle_d):
     """submit_task on the reference's fixture curve (two identical Sr2-like Morse curves, N = 16500):
     levels equal the oracle's bits (float64) and the analytic Morse spectrum."""
     interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
@@ -216,8 +216,8 @@ def test_levels_of_reference_fixture(gpu_mod, oracle):
     N = 16500
     V = oracle.morse(5500.0, 0.6, 10.0, 0.0, 10.0, N)
     s = oracle.scale(87.62, 87.62, W.grid_h(0.0, 10.0, N))
-    F, _, _, vmin = oracle.prep(V, s)
-    lev_o, *_ = oracle.solve_levels(F, s, vmin, V[-1] - 0.1, 1024, 0, 13, 256, 1e-12, 16)
+    F, _, _, vmin = oracle_d.prep(V, s)
+    lev_o, *_ = oracle_d.solve_levels(F, s, vmin, V[-1] - 0.1, 1024, 0, 13, 256, 1e-12, 16)
     assert np.array_equal(levels[0].view(np.uint64), lev_o.view(np.uint64))
 
 
@@ -282,7 +282,7 @@ def test_wavefunctions_through_python_api(gpu_mod, oracle):
 
 
 @pytest.mark.gpu
-def test_rotational_states_through_python_api(gpu_mod, oracle):
+def test_rotational_states_through_python_api(gpu_mod, oracle, oracle_d):
     """Additive surface: set_rotational_states([J...]) -> rows [curve][J]; levels carry
     the bits of the oracle run on orc_centrifugal's table."""
     interface = gpu_mod.EpseonComputeContext.create().get_device_interface(0)
@@ -305,13 +305,13 @@ def test_rotational_states_through_python_api(gpu_mod, oracle):
     s = oracle.scale(87.62, 87.62, h)
     for k, J in enumerate((0, 2, 10)):
         VJ = oracle.centrifugal(V, s, 0.0, h, J)
-        F, _, _, vmin = oracle.prep(VJ, s)
-        lev_o, *_ = oracle.solve_levels(F, s, vmin, VJ[-1] - 0.1, 1024, 0, 3, 256, 1e-12, 16)
+        F, _, _, vmin = oracle_d.prep(VJ, s)
+        lev_o, *_ = oracle_d.solve_levels(F, s, vmin, VJ[-1] - 0.1, 1024, 0, 3, 256, 1e-12, 16)
         assert np.array_equal(levels[k].view(np.uint64), lev_o.view(np.uint64)), J
 
 
 @pytest.mark.gpu
-def test_potential_tables_through_python_api(gpu_mod, oracle):
+def test_potential_tables_through_python_api(gpu_mod, oracle, oracle_d):
     """Additive surface: curves handed over as a numpy array [curve][point]; float64 levels carry the
     bits of the oracle run on the same tables (Morse + Lennard-Jones in one batch, as in config 4)."""
     N, rmin, rmax = 12000, 0.4, 10.0
@@ -333,8 +333,8 @@ def test_potential_tables_through_python_api(gpu_mod, oracle):
     levels = np.array(handle.get_levels())
     s = oracle.scale(20.0, 20.0, W.grid_h(rmin, rmax, N))
     for c in range(2):
-        F, _, _, vmin = oracle.prep(V[c], s)
-        ref, *_ = oracle.solve_levels(F, s, vmin, V[c][-1] - 1.0, 1024, 0, 6, 256, 1e-12, 16)
+        F, _, _, vmin = oracle_d.prep(V[c], s)
+        ref, *_ = oracle_d.solve_levels(F, s, vmin, V[c][-1] - 1.0, 1024, 0, 6, 256, 1e-12, 16)
         assert np.array_equal(levels[c].view(np.uint64), ref.view(np.uint64)), c
 
 
@@ -368,7 +368,7 @@ def test_example_script_runs():
 
 
 @pytest.mark.gpu
-def test_batch_task_uses_fewer_points_per_round(gpu_mod, oracle):
+def test_batch_task_uses_fewer_points_per_round(gpu_mod, oracle, oracle_d):
     """Hundreds of curves in one task: the search runs with fewer points per level per round
     (get_search_parameters), and the levels still carry the oracle's bits for those parameters."""
     N, nC = 3000, 640
@@ -391,8 +391,8 @@ def test_batch_task_uses_fewer_points_per_round(gpu_mod, oracle):
     s = oracle.scale(20.0, 20.0, W.grid_h(0.4, 10.0, N))
     for c in (0, 1, 317, 639):
         V = oracle.morse(float(De[c]), 2.2, 1.6, 0.4, 10.0, N)
-        F, _, _, vmin = oracle.prep(V, s)
-        ref, *_ = oracle.solve_levels(F, s, vmin, V[-1] - 1.0, n_coarse, 0, 7, M, tol, rounds)
+        F, _, _, vmin = oracle_d.prep(V, s)
+        ref, *_ = oracle_d.solve_levels(F, s, vmin, V[-1] - 1.0, n_coarse, 0, 7, M, tol, rounds)
         assert np.array_equal(levels[c].view(np.uint64), ref.view(np.uint64)), c
     # a small task keeps the 256-point rounds
     small = interface.submit_task(_configure_task(gpu_mod, interface.get_task_configurator("float64"), max_level=3))

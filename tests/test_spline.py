@@ -63,7 +63,7 @@ def test_gpu_spline_rejects_bad_knots(gpu_ctx):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["dat", "npy"])
-def test_file_loader_resamples_non_uniform_table(tmp_path, oracle, fmt):
+def test_file_loader_resamples_non_uniform_table(tmp_path, oracle, fmt, oracle_d):
     """PotentialFileLoader made real for ab initio tables: a 64-knot non-uniform 'r V' file (text, or
     a NumPy .npy array of shape (n, 2)), resampled by the C++ loader to 20 001 points, solved through
     the Python API == the oracle on the oracle's own resampling of the same knots."""
@@ -91,6 +91,6 @@ def test_file_loader_resamples_non_uniform_table(tmp_path, oracle, fmt):
     levels = np.array(handle.get_levels())[0]
     V = oracle.spline_resample(rk, Vk, rk[0], rk[-1], N)
     s = oracle.scale(W.H2["m0"], W.H2["m1"], (rk[-1] - rk[0]) / (N - 1))
-    F, _, _, vmin = oracle.prep(V, s)
-    ref, *_ = oracle.solve_levels(F, s, vmin, V[-1] - 1.0, 1024, 0, 9, 256, 1e-12, 16)
+    F, _, _, vmin = oracle_d.prep(V, s)
+    ref, *_ = oracle_d.solve_levels(F, s, vmin, V[-1] - 1.0, 1024, 0, 9, 256, 1e-12, 16)
     assert np.array_equal(levels.view(np.uint64), ref.view(np.uint64))
