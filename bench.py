@@ -56,7 +56,10 @@ from tests import workloads as W  # noqa: E402
 
 METRIC = "numerov_grid_steps_x_trial_energies_per_s"
 _REAL_STDOUT = 1  # fd of the run's own stdout (main() moves fd 1 to stderr)
-FLOP_PER_STEP = 6  # executed by the 4-instruction X form: 1 DADD + 1 DMUL + 2 DFMA
+FLOP_PER_STEP = {0: 6, 1: 8}  # executed per grid step x energy: X form 1 DADD + 1 DMUL + 2 DFMA; D form 1 DADD + 1 DMUL + 3 DFMA
+INSTR_PER_STEP = {0: 4, 1: 5}
+FORM_NAME = {0: "X form (4 FP64 operations per step; eigenvalue noise floor 1e-9 .. 2e-8 on 2e5 .. 1e6-point grids)",
+             1: "D form, accurate (5 FP64 operations per step; eigenvalues within 1e-13 of the binary128 discrete problem)"}
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 SUB_STEPS = 10  # timed steps of a sub-record (min with --steps)
 
@@ -461,9 +464,18 @@ def timed_run(wl: Workload, comm: Comm, step_fn, k: int):
 
 
 def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmup: int, fp64_peak: float,
-            cpu_seconds: float) -> dict | None:
+            cpu_seconds: float, form: int = 0) -> dict | None:
     """One record (headline or sub-record): resident rate, e2e rate, roofline of the dominant kernel,
-    clocks, CPU oracle beside it, parity flags.  Returned on rank 0 only."""
+    clocks, CPU oracle beside it, parity flags.  Returned on rank 0 only.  form: the recurrence
+    (EPS_OPT_FORM) the tables are prepared for and the sweeps run."""
+    ctx.set_option(ctx.OPT_FORM, form)
+    try:
+        return _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form)
+    finally:
+        ctx.set_option(ctx.OPT_FORM, 0)
+
+
+def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form):
     wl = Workload(name, ctx, comm)
     for _ in range(warmup):
         comm.gather(wl.digest(wl.resident()))
@@ -502,7 +514,7 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
         rng = np.random.default_rng(5000 + comm.rank)
         idx = np.unique(np.concatenate([[0, wl.per - 1], rng.integers(0, wl.per, C5["check_sample"] - 2)]))
         E = wl.w["E_lo"] + (wl.j0 + idx).astype(np.float64) * wl.dE  # the device's operations: mul, add
-        orc1 = Oracle(omp=True, threads=max(1, host_threads() // comm.world))
+        orc1 = Oracle(omp=True, threads=max(1, host_threads() // comm.world), form=form)
         F, *_ = orc1.prep(wl.w["V"], wl.s)
         n_cpu, _, _ = orc1.sweep(F, wl.s, E, tails=False)
         same = bool(np.array_equal(n_cpu, res2[0][0][idx]))
@@ -510,7 +522,8 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
     if comm.rank != 0:
         return None
 
-    frac = FLOP_PER_STEP * sweep_rate / 1e12 / fp64_peak
+    flop = FLOP_PER_STEP[form]
+    frac = flop * sweep_rate / 1e12 / fp64_peak
     rec = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": comm.world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_res / steps, "higher_is_better": True,
@@ -520,18 +533,18 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
                 "h2d_bytes_per_step": int(st2.h2d_bytes // steps), "d2h_bytes_per_step": int(st2.d2h_bytes // steps)},
         "gpu_launches": launches,
         "roofline": {
-            "bound": "fp64", "kernel": KERNELS[name],
-            "achieved": FLOP_PER_STEP * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
+            "bound": "fp64", "kernel": KERNELS[name] + (", D form" if form else ""),
+            "achieved": flop * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
             "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "peak_nominal": NOMINAL_FP64_TFLOPS,
-            "frac_of_nominal": FLOP_PER_STEP * sweep_rate / 1e12 / NOMINAL_FP64_TFLOPS,
-            "flop_per_step": FLOP_PER_STEP, "steps_per_s_kernel": sweep_rate,
-            "fp64_instr_per_step": 4, "sweep_launches": int(st.sweep_launches),
+            "frac_of_nominal": flop * sweep_rate / 1e12 / NOMINAL_FP64_TFLOPS,
+            "flop_per_step": flop, "steps_per_s_kernel": sweep_rate,
+            "fp64_instr_per_step": INSTR_PER_STEP[form], "sweep_launches": int(st.sweep_launches),
             "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
-            **kernel_traffic(name),
+            **kernel_traffic(name if form == 0 else name + "_dform"),
             "algorithmic_bytes_per_launch": 8 * int(wl.n_steps) * int(ctx.n_curves),
         },
-        "clocks": clocks,
+        "clocks": clocks, "recurrence": FORM_NAME[form],
     }
     if name == "c2":
         exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
@@ -545,7 +558,7 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
     if cpu_seconds > 0:
         from oracle import Oracle
 
-        orc = Oracle(omp=True, threads=host_threads())
+        orc = Oracle(omp=True, threads=host_threads(), form=form)
         one, sample = cpu_sample(name, orc)
         rate, secs, reps, first = cpu_timed(one, cpu_seconds)
         cb = {"value": rate, "unit": "steps/s", "cores": orc.threads, "kind": "port",
@@ -609,6 +622,14 @@ def main() -> None:
             rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, cpu_s / 2)
             if rec is not None:
                 subs[name] = rec
+        # the accurate recurrence on the same workloads (EPS_OPT_FORM = 1): what the drop-in
+        # VibwaAlgorithm<FP>::run uses; 5 instead of 4 FP64 operations per step
+        for name in ("c5", "c2", "c4", "c3"):
+            rec = measure(name, ctx, comm, sampler, min(args.steps, 5), 3, fp64_peak, 0.001 if cpu_s else 0.0, form=1)
+            if rec is not None:
+                keep = ("value", "ms_per_step", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
+                        "nodes_bit_identical_to_oracle_full_size_sample", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
+                (line if name == "c5" else subs[name])["accurate_mode"] = {k: rec[k] for k in keep if k in rec}
         if line is not None:
             line["sub_records"] = subs
             line["time_to_all_levels_ms"] = {"c2": subs["c2"]["time_to_all_levels_ms"], "c4": subs["c4"]["time_to_all_levels_ms"]}

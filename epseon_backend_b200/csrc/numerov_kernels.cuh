@@ -510,7 +510,11 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
         const int    fa = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
         const int    fb = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
                                             static_cast<uint32_t>(__double2hiint(XA))) >> 31);
-        const int    sg = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
+        // orientation: the sign of the discrete Wronskian of (A, v).  In the X form's coordinates D is
+        // MINUS the backward difference (D = S - X), in the D form's it is PLUS (D = Y_k - f Y_{k-1}),
+        // so the two forms need opposite signs; D_start = -1 / +1 carries exactly that.
+        const int    sg0 = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
+        const int    sg  = D_start < 0.0 ? sg0 : -sg0;
         nodes += so.nA[o] + static_cast<uint32_t>(sg * (fb - fa));
         const double magX = fabs(__dmul_rn(XA, X)) + fabs(pX), magD = fabs(__dmul_rn(DA, X)) + fabs(pD);
         const double cX = magX > 0.0 ? fabs(Xn) / magX : 1.0, cD = magD > 0.0 ? fabs(Dn) / magD : 1.0;
