@@ -341,7 +341,7 @@ class Comm:
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.dist = self.torch = None
-        self._bufs = {}
+        self.box = None
         if self.world > 1:
             import torch
             import torch.distributed as dist
@@ -364,31 +364,40 @@ class Comm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def attach(self, ctx):
+        """The result gather of the path: an eps_mailbox in rank 0's device memory (CUDA IPC + peer
+        writes over NVLink, epseon_backend_b200.multi.MailboxComm).  torch.distributed only moves the
+        64-byte IPC handle, once."""
+        if self.dist is None or self.box is not None:
+            return
+        from epseon_backend_b200 import multi
+
+        def exchange(payload: bytes):
+            out = [None] * self.world
+            self.dist.all_gather_object(out, payload)
+            return out
+
+        self.box = multi.MailboxComm(ctx, self.world, self.rank, exchange, max_bytes=1 << 20)
+
     def gather(self, arr: np.ndarray):
-        """Gather a small per-rank result to rank 0 (the only inter-GPU traffic of the path): pinned
-        staging, one all-gather over NCCL, one copy back."""
+        """A small host payload of every rank -> rank 0 (None elsewhere)."""
         if self.dist is None:
             return [arr]
-        torch, dist = self.torch, self.dist
-        arr = np.ascontiguousarray(arr)
-        key = (arr.shape, arr.dtype.str)
-        if key not in self._bufs:
-            h_in = torch.from_numpy(np.empty_like(arr)).pin_memory()
-            d_in = torch.empty_like(h_in, device="cuda")
-            d_out = torch.empty((self.world,) + tuple(arr.shape), dtype=h_in.dtype, device="cuda")
-            h_out = torch.empty(d_out.shape, dtype=h_in.dtype).pin_memory()
-            self._bufs[key] = (h_in, d_in, d_out, h_out)
-        h_in, d_in, d_out, h_out = self._bufs[key]
-        h_in.copy_(torch.from_numpy(arr))
-        d_in.copy_(h_in, non_blocking=True)
-        dist.all_gather_into_tensor(d_out, d_in)
-        h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return [h_out[r].numpy().copy() for r in range(self.world)] if self.rank == 0 else None
+        return self.box.gather(arr)
+
+    def gather_levels(self, res, n_curves: int, n_levels: int):
+        """The levels of every rank's last level search -> rank 0, device to device (one peer write per
+        rank, one D2H on rank 0); single process: the host arrays the solve returned."""
+        if self.dist is None:
+            return [res[0]]
+        parts = self.box.gather_levels(n_curves, n_levels)
+        return None if parts is None else [p[0] for p in parts]
 
     def close(self):
         if self.dist is not None:
             self.dist.barrier()
+            if self.box is not None:
+                self.box.close()
             self.dist.destroy_process_group()
 
 
@@ -415,13 +424,13 @@ class Workload:
             self.resident = lambda: ctx.solve_levels(E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
                                                      C2["rel_tol"], C2["max_rounds"])
             self.e2e_tail = self.resident
-            self.digest = lambda res: res[0][0]  # 17 level energies
+            self.gather = lambda res: comm.gather_levels(res, 1, C2["v_max"] + 1)  # 17 level energies per rank
         elif name == "c3":
             w = W.c3(C3["N"], C3["nE"])
             self.w, self.V, self.s, self.scaling = w, pinned(w["V"]), w["s"], "weak"
             self.resident = lambda: ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=False, tails=False)
             self.e2e_tail = lambda: ctx.sweep_uniform(w["E_lo"], w["E_hi"], C3["nE"], nodes=True, tails=False)
-            self.digest = lambda res: np.zeros(1)
+            self.gather = lambda res: comm.gather(np.zeros(1))  # completion only: replicas
         elif name == "c4":
             w = W.c4(C4["nC"], C4["N"], C4["n_coarse"])
             sl = multi.curve_shard(C4["nC"], world, rank)
@@ -430,7 +439,7 @@ class Workload:
             self.resident = lambda: ctx.solve_levels(E_lo4, E_hi4, C4["n_coarse"], 0, C4["v_max"], C4["refine_points"],
                                                      C4["rel_tol"], C4["max_rounds"])
             self.e2e_tail = self.resident
-            self.digest = lambda res: res[0]  # [curves of this rank][8] level energies
+            self.gather = lambda res: comm.gather_levels(res, sl.stop - sl.start, C4["v_max"] + 1)  # [curves of this rank][8]
         else:
             w = W.c5(C5["N"], C5["nE"])
             sl = multi.curve_shard(C5["nE"], world, rank)  # contiguous slice of the global energy grid
@@ -439,7 +448,7 @@ class Workload:
             self.w, self.V, self.s, self.scaling = w, pinned(w["V"]), w["s"], "strong"
             self.resident = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=False, tails=False)
             self.e2e_tail = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=True, tails=False)  # 4 B/energy D2H
-            self.digest = lambda res: np.zeros(1)
+            self.gather = lambda res: comm.gather(np.zeros(1))  # completion only: the node counts stay on the devices
         ctx.set_potentials(self.V, self.s)
         self.n_steps = ctx.curve_info(0).n_steps
 
@@ -457,7 +466,7 @@ def timed_run(wl: Workload, comm: Comm, step_fn, k: int):
         comm.barrier(ctx)
         ctx.timer_start()
         results = step_fn()
-        digest = comm.gather(wl.digest(results))
+        digest = wl.gather(results)
         ms.append(ctx.timer_stop())
     comm.barrier(ctx)
     return ms, results, digest
@@ -476,9 +485,10 @@ def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmu
 
 
 def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form):
+    comm.attach(ctx)
     wl = Workload(name, ctx, comm)
     for _ in range(warmup):
-        comm.gather(wl.digest(wl.resident()))
+        wl.gather(wl.resident())
     ctx.sync()
 
     # ---- timed: resident ----
@@ -548,8 +558,8 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     }
     if name == "c2":
         exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
-        rec["levels_found"] = int(np.sum(np.isfinite(digest[0])))
-        rec["max_rel_err_vs_analytic_rank0"] = float(np.max(np.abs(digest[0] - exact) / exact))
+        rec["levels_found"] = int(np.sum(np.isfinite(digest[0][0])))
+        rec["max_rel_err_vs_analytic_rank0"] = float(np.max(np.abs(digest[0][0] - exact) / exact))
     if name == "c3":
         rec["scan"] = {"launches": ctx.counter(ctx.CNT_SCAN_LAUNCHES), "flagged": ctx.counter(ctx.CNT_SCAN_FLAGGED)}
     if name == "c5":
@@ -564,7 +574,7 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         cb = {"value": rate, "unit": "steps/s", "cores": orc.threads, "kind": "port",
               "sample": f"{sample}, repeated {reps}x", "seconds": secs}
         if name == "c2":
-            cb["levels_bit_identical_to_gpu"] = bool(np.array_equal(first.view(np.uint64), digest[0].view(np.uint64)))
+            cb["levels_bit_identical_to_gpu"] = bool(np.array_equal(first.view(np.uint64), digest[0][0].view(np.uint64)))
         elif name == "c4":
             cb["levels_bit_identical_to_gpu"] = bool(np.array_equal(first.view(np.uint64),
                                                                     digest[0][: first.shape[0]].view(np.uint64)))

@@ -185,7 +185,8 @@ int eps_sweep_grid(eps_ctx* ctx, const double* E0, const double* dE, uint32_t j0
 /* ---- bracketing + k-section refinement of levels v_min..v_max of every
  * resident curve inside [E_lo[c], E_hi[c]].  Outputs (host):
  *   levels[n_curves][level_count]  (NaN where the level is not in range) --
- *     the reference's planned output buffer (algorithm_config.hpp:183-190);
+ *     the reference's planned output buffer (algorithm_config.hpp:183-190); may be NULL: the
+ *     results then stay on the device (for eps_mailbox_post_levels / eps_group_*);
  *   widths[n_curves][level_count]  final bracket widths (may be NULL);
  *   n_below[n_curves]              levels below E_hi[c]   (may be NULL). */
 int eps_solve_levels(eps_ctx* ctx, const eps_solve_params* p, const double* E_lo,
