@@ -56,7 +56,7 @@ class CurveInfo(C.Structure):
 
 class SolveParams(C.Structure):
     _fields_ = [("v_min", C.c_uint32), ("v_max", C.c_uint32), ("n_coarse", C.c_uint32),
-                ("refine_points", C.c_uint32), ("max_rounds", C.c_uint32), ("reserved", C.c_uint32),
+                ("refine_points", C.c_uint32), ("max_rounds", C.c_uint32), ("flags", C.c_uint32),
                 ("rel_tol", C.c_double)]
 
 
@@ -239,12 +239,14 @@ class Context:
                                          _ptr(x, np.int32)))
         return n, m, x
 
+    SOLVE_COOLEY, SOLVE_OPEN_TAIL = 1, 2
+
     def solve_levels_grid(self, E0, dE, j0: int, n_coarse: int, v_min: int, v_max: int, refine_points: int,
-                          rel_tol: float = 1e-12, max_rounds: int = 8):
+                          rel_tol: float = 1e-12, max_rounds: int = 8, flags: int = 0):
         """-> (levels[nC, nlev], widths[nC, nlev], n_last[nC], n_first[nC])"""
         a, b = _vec(E0, self.n_curves), _vec(dE, self.n_curves)
         nlev = v_max - v_min + 1
-        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, flags, rel_tol)
         levels = np.empty((self.n_curves, nlev), dtype=np.float64)
         widths = np.empty((self.n_curves, nlev), dtype=np.float64)
         nl = np.empty(self.n_curves, dtype=np.uint32)
@@ -256,11 +258,11 @@ class Context:
         return levels, widths, nl, nf
 
     def solve_levels(self, E_lo, E_hi, n_coarse: int, v_min: int, v_max: int, refine_points: int,
-                     rel_tol: float = 1e-12, max_rounds: int = 8):
-        """-> (levels[nC, nlev], widths[nC, nlev], n_below[nC])"""
+                     rel_tol: float = 1e-12, max_rounds: int = 8, flags: int = 0):
+        """-> (levels[nC, nlev], widths[nC, nlev], n_below[nC]); flags=SOLVE_COOLEY: matching iteration"""
         lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
         nlev = v_max - v_min + 1
-        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, flags, rel_tol)
         levels = np.empty((self.n_curves, nlev), dtype=np.float64)
         widths = np.empty((self.n_curves, nlev), dtype=np.float64)
         nb = np.empty(self.n_curves, dtype=np.uint32)
@@ -405,11 +407,11 @@ class Group:
         return n
 
     def solve_levels(self, E_lo, E_hi, n_coarse: int, v_min: int, v_max: int, refine_points: int,
-                     rel_tol: float = 1e-12, max_rounds: int = 8):
+                     rel_tol: float = 1e-12, max_rounds: int = 8, flags: int = 0):
         """-> (levels[nC, nlev], widths[nC, nlev], n_below[nC]) of the WHOLE job"""
         lo, hi = _vec(E_lo, self.n_curves), _vec(E_hi, self.n_curves)
         nlev = v_max - v_min + 1
-        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, 0, rel_tol)
+        p = SolveParams(v_min, v_max, n_coarse, refine_points, max_rounds, flags, rel_tol)
         levels = np.empty((self.n_curves, nlev), dtype=np.float64)
         widths = np.empty((self.n_curves, nlev), dtype=np.float64)
         nb = np.empty(self.n_curves, dtype=np.uint32)

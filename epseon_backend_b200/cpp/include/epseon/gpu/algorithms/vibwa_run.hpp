@@ -217,6 +217,10 @@ namespace epseon::gpu::cpp {
                 p.max_rounds    = 24;
             }
         }
+        if (configurator.getLevelSearch() != 0) { // Cooley iteration instead of k-section sweeps
+            p.flags      = EPS_SOLVE_COOLEY | (configurator.getLevelSearch() == 2 ? EPS_SOLVE_OPEN_TAIL : 0);
+            p.max_rounds = 40;
+        }
         handle->setSearchParameters(p.n_coarse, p.refine_points, p.max_rounds, p.rel_tol);
         std::vector<double>   lev(static_cast<size_t>(nC) * nlev);
         std::vector<uint32_t> below(nC);

@@ -135,6 +135,15 @@ namespace epseon::gpu::python {
         }
 
         // Additive: tabulated curves from "r V" text files.
+        // additive: "ksection" (default), "cooley", "cooley_open"
+        TaskConfigurator& set_level_search(const std::string& mode) {
+            if (mode == "ksection") configurator->setLevelSearch(0);
+            else if (mode == "cooley") configurator->setLevelSearch(1);
+            else if (mode == "cooley_open") configurator->setLevelSearch(2);
+            else throw std::runtime_error("level search mode must be 'ksection', 'cooley' or 'cooley_open'");
+            return *this;
+        }
+
         // additive: energy-range sharding of one problem over several devices (multi.py)
         TaskConfigurator& set_energy_shard(uint32_t rank, uint32_t world) {
             configurator->setEnergyShard(rank, world);

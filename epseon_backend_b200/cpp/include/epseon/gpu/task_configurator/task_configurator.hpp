@@ -32,6 +32,10 @@ namespace epseon::gpu::cpp {
         // slices of the coarse energy grid (energy-range sharding of ONE problem over several devices;
         // the reference gives one device per task, device_interface.hpp:22).  Default: the whole grid.
         uint32_t shard_rank = 0, shard_world = 1;
+        // additive: how located brackets are refined.  0 = k-section on node counts
+        // (default: bit-reproducible decisions), 1 = Cooley outward/inward matching iteration,
+        // 2 = Cooley with an open (decaying) tail for near-dissociation levels.
+        uint32_t level_search = 0;
 
         template <typename T>
         static std::shared_ptr<T> clone_or_null(const std::shared_ptr<T>& p) {
@@ -54,7 +58,8 @@ namespace epseon::gpu::cpp {
             wavefunction_output(o.wavefunction_output),
             rotational_states(std::move(o.rotational_states)),
             shard_rank(o.shard_rank),
-            shard_world(o.shard_world) {}
+            shard_world(o.shard_world),
+            level_search(o.level_search) {}
         TaskConfigurator& operator=(TaskConfigurator&& o) noexcept {
             if (this != &o) {
                 hardware_config     = std::move(o.hardware_config);
@@ -64,6 +69,7 @@ namespace epseon::gpu::cpp {
                 rotational_states   = std::move(o.rotational_states);
                 shard_rank          = o.shard_rank;
                 shard_world         = o.shard_world;
+                level_search        = o.level_search;
             }
             return *this;
         }
@@ -75,7 +81,8 @@ namespace epseon::gpu::cpp {
             wavefunction_output(o.wavefunction_output),
             rotational_states(o.rotational_states),
             shard_rank(o.shard_rank),
-            shard_world(o.shard_world) {}
+            shard_world(o.shard_world),
+            level_search(o.level_search) {}
         TaskConfigurator& operator=(const TaskConfigurator& o) {
             if (this != &o) {
                 hardware_config     = clone_or_null(o.hardware_config);
@@ -85,6 +92,7 @@ namespace epseon::gpu::cpp {
                 rotational_states   = o.rotational_states;
                 shard_rank          = o.shard_rank;
                 shard_world         = o.shard_world;
+                level_search        = o.level_search;
             }
             return *this;
         }
@@ -129,6 +137,12 @@ namespace epseon::gpu::cpp {
             shard_world = world;
             return *this;
         }
+        TaskConfigurator& setLevelSearch(uint32_t mode) {
+            if (mode > 2) throw std::runtime_error("level search: 0 (k-section), 1 (cooley) or 2 (cooley, open tail)");
+            level_search = mode;
+            return *this;
+        }
+        [[nodiscard]] uint32_t getLevelSearch() const { return level_search; }
         [[nodiscard]] uint32_t getEnergyShardRank() const { return shard_rank; }
         [[nodiscard]] uint32_t getEnergyShardWorld() const { return shard_world; }
 

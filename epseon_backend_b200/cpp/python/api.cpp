@@ -110,6 +110,10 @@ namespace epseon::gpu::python {
                      py::arg("tables"), py::arg("min_r"), py::arg("max_r"), py::return_value_policy::reference,
                      "Use curves held in memory: a float64 array [n_curves][point_count] of V(r_i) on the uniform grid "
                      "r_i = min_r + i (max_r - min_r)/(point_count - 1).")
+                .def("set_level_search", &C::set_level_search, py::arg("mode"), py::return_value_policy::reference,
+                     "How bracketed levels are refined: 'ksection' (default; sweeps of trial energies, decisions on node "
+                     "counts), 'cooley' (outward/inward matching iteration: 3-5 iterations per level), 'cooley_open' (the "
+                     "same with a decaying tail instead of a wall at max_r, for levels near dissociation).")
                 .def("set_energy_shard", &C::set_energy_shard, py::arg("rank"), py::arg("world"),
                      py::return_value_policy::reference,
                      "Search only slice `rank` of `world` contiguous slices of the coarse energy grid (energy-range "

@@ -10,6 +10,7 @@
 #include "../../include/epseon_cuda.h"
 #include "numerov_kernels.cuh"
 #include "numerov_cbank.cuh"
+#include "cooley_search.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -989,6 +990,20 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches += 2;
     }
+    // ---- Cooley (outward/inward matching) iteration instead of k-section sweeps ----
+    bool cooley = (p->flags & EPS_SOLVE_COOLEY) != 0;
+    if (cooley) {
+        EPS_REQUIRE(ctx, ctx->form_resident == 1, EPS_ERR_STATE, "EPS_SOLVE_COOLEY needs the accurate tables (EPS_OPT_FORM = 1 before eps_set_potentials)");
+        for (const auto& ci : ctx->curves) cooley = cooley && ci.n_steps >= 256u;  // short windows: k-section
+    }
+    if (cooley) {
+        cooley_search_kernel<<<total, kCooleyThreads, 0, ctx->stream>>>(ctx->d_A.p, ctx->d_curves.p, nlev, p->v_min, p->rel_tol,
+                                                                       std::max<uint32_t>(p->max_rounds, 1u), ctx->d_lo.p, ctx->d_hi.p,
+                                                                       ctx->d_state.p, ctx->d_levels.p, ctx->d_widths.p, nullptr,
+                                                                       ctx->d_steps, ctx->d_stop, (p->flags & EPS_SOLVE_OPEN_TAIL) ? 1 : 0);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches++;
+    }
     // ---- k-section refinement rounds ----
     // One curve resident: the active brackets are compacted into rows that are swept with the
     // flat-row mapping (full CTAs).  Several curves: dense rows [curve][level padded to the CTA
@@ -1004,7 +1019,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     const uint32_t n_dense   = nC * nlev_pad;
     EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_dense));
     EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_dense, total)));
-    for (uint32_t round = 0; round < p->max_rounds; round++) {
+    for (uint32_t round = 0; round < p->max_rounds && !cooley; round++) {
         if (flat) {
             compact_refine_jobs_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
                                                                   ctx->d_jobs_ref.p, ctx->d_nactive.p);
@@ -1033,9 +1048,11 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches += 2;
     }
-    finalize_levels_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, total, ctx->d_levels.p, ctx->d_widths.p);
-    EPS_CUDA(ctx, cudaGetLastError());
-    ctx->stats.other_launches++;
+    if (!cooley) {
+        finalize_levels_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, total, ctx->d_levels.p, ctx->d_widths.p);
+        EPS_CUDA(ctx, cudaGetLastError());
+        ctx->stats.other_launches++;
+    }
     ctx->last_total = total;
     ctx->last_nC    = nC;
     if (levels) {

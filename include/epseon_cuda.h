@@ -90,10 +90,30 @@ typedef struct eps_solve_params {
     uint32_t v_min, v_max;
     uint32_t n_coarse;       /* trial energies of the bracketing sweep (per curve)  */
     uint32_t refine_points;  /* interior trial energies per level per round (M)     */
-    uint32_t max_rounds;
-    uint32_t reserved;
+    uint32_t max_rounds;     /* k-section rounds / Cooley iterations per level      */
+    uint32_t flags;          /* EPS_SOLVE_* (0: k-section on node counts)           */
     double   rel_tol;        /* stop when hi-lo <= rel_tol*max(|lo|,|hi|)           */
 } eps_solve_params;
+
+/* eps_solve_params.flags.
+ * EPS_SOLVE_COOLEY: after the coarse sweep has bracketed the levels, refine every level with the
+ *   outward/inward matching (Cooley) iteration instead of k-section sweeps (spec
+ *   DESIGN.md section 3.9): march out from the left wall and in from the right wall to the outer
+ *   classical turning point, take the Rayleigh-quotient correction of section 3.8 as a Newton step,
+ *   keep a rigorous bracket from the node count of the full outward solution (a step that leaves it
+ *   is replaced by the midpoint), stop when |correction| <= rel_tol |E|.  One CTA per (curve, level)
+ *   iterates on the device; 3-5 iterations from a coarse bracket.  Needs the accurate tables
+ *   (EPS_OPT_FORM = 1) and windows of >= 256 steps (else the call uses k-section).  levels = E,
+ *   widths = |last correction|.  Agrees with the k-section result to the tolerance (a few 1e-14
+ *   measured), not bit for bit; bit-identical to the oracle's statement of the same iteration.
+ * EPS_SOLVE_OPEN_TAIL (with EPS_SOLVE_COOLEY): the inward branch starts on the DECAYING solution of
+ *   the recurrence (last coefficient frozen) instead of psi = 0 at the end of the table: the levels
+ *   of the unbounded problem.  For states near dissociation, whose tail still matters at r_max --
+ *   within VibwaAlgorithmConfig::min_distance_to_asymptote of the asymptote
+ *   (algorithm_config.hpp:81) -- the box pushes the level up (docs-example curve, v = 26:
+ *   +2.6e-6 relative); the open tail removes that.  Node counts are a property of the box problem, so
+ *   the bracket becomes a soft window [lo - (hi - lo), hi] around the box level. */
+enum { EPS_SOLVE_COOLEY = 1, EPS_SOLVE_OPEN_TAIL = 2 };
 
 /* Counters since the last eps_stats_reset(). */
 typedef struct eps_stats {

@@ -408,6 +408,220 @@ int orc_solve_levels(const double* F, uint32_t n_steps, double s, double E_lo, d
                                  levels, widths, n_below_hi, 0, steps_done);
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Outward/inward matching level search (Cooley; spec DESIGN.md section 3.9).  Mirrors
+ * csrc/cooley_search.cuh operation for operation: the window is cut into segments of
+ * L = max(64, ceil(n/256)) steps; pass 1 = two basis solutions per segment, a serial chain gives
+ * the true entry state of every segment, pass 2 re-marches every segment counting sign flips and
+ * accumulating the norm; the sums are added in segment order.  A is the D-form table (12 q_k).
+ * ------------------------------------------------------------------------------------------- */
+#define ORC_COOLEY_SEGS 256u
+#define ORC_COOLEY_MINSEG 64u
+typedef struct {
+    double  u, d;
+    int32_t e;
+} cst;
+
+static void c_renorm(cst* x, double* acc, double* psi_prev) {
+    uint32_t ex = (uint32_t)(d2u(x->u) >> 52) & 0x7ffu;
+    if (ex == 0) ex = (uint32_t)(d2u(x->d) >> 52) & 0x7ffu;
+    if (ex != 0 && ex != 1023u) {
+        const double sc = u2d((uint64_t)(2046u - ex) << 52);
+        x->u *= sc;
+        x->d *= sc;
+        x->e += (int32_t)ex - 1023;
+        if (acc) *acc = (*acc * sc) * sc;
+        if (psi_prev) *psi_prev = *psi_prev * sc;
+    }
+}
+static void c_coef(double Ak, double e12, double* g, double* r) {
+    const double T12 = Ak - e12;
+    const double f   = fma(-(1.0 / 12.0), T12, 1.0);
+    *r               = 1.0 / f;
+    *g               = T12 * *r;
+}
+static void c_step(cst* x, double g) {
+    x->d = fma(g, x->u, x->d);
+    x->u = x->u + x->d;
+}
+static void c_basis(const double* A, double e12, uint32_t k0, uint32_t k1, int dir, cst* a, cst* b) {
+    *a = (cst){1.0, 0.0, 0};
+    *b = (cst){0.0, 1.0, 0};
+    for (uint32_t i = 0; i < k1 - k0; i++) {
+        const uint32_t k = dir > 0 ? k0 + i : k1 - 1 - i;
+        double         g, r;
+        c_coef(A[k], e12, &g, &r);
+        c_step(a, g);
+        c_step(b, g);
+        if ((i & 127u) == 127u) {
+            c_renorm(a, 0, 0);
+            c_renorm(b, 0, 0);
+        }
+    }
+    c_renorm(a, 0, 0);
+    c_renorm(b, 0, 0);
+}
+static cst c_apply(const cst* a, const cst* b, const cst* x) {
+    int sh = b->e - a->e;
+    sh     = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+    const double bu = scalbn(b->u, sh), bd = scalbn(b->d, sh);
+    cst          y;
+    y.u = fma(a->u, x->u, bu * x->d);
+    y.d = fma(a->d, x->u, bd * x->d);
+    y.e = x->e + a->e;
+    c_renorm(&y, 0, 0);
+    return y;
+}
+static void c_remarch(const double* A, double e12, uint32_t k0, uint32_t k1, int dir, cst* x, double psi_prev,
+                      uint32_t* flips, double* acc_out) {
+    uint32_t fl  = 0;
+    double   acc = 0.0;
+    for (uint32_t i = 0; i < k1 - k0; i++) {
+        const uint32_t k = dir > 0 ? k0 + i : k1 - 1 - i;
+        double         g, r;
+        c_coef(A[k], e12, &g, &r);
+        const double psi = x->u * r;
+        acc              = fma(psi, fma(10.0, psi, 2.0 * psi_prev), acc);
+        psi_prev         = psi;
+        const uint64_t before = d2u(x->u);
+        c_step(x, g);
+        fl += (uint32_t)((before ^ d2u(x->u)) >> 63);
+        if ((i & 127u) == 127u) c_renorm(x, &acc, &psi_prev);
+    }
+    c_renorm(x, &acc, &psi_prev);
+    *flips   = fl;
+    *acc_out = acc;
+}
+
+/* One level: bracket [lo, hi] with nodes(lo) <= v < nodes(hi).  Returns the iterations used;
+ * *E_out the level, *width_out the magnitude of the last correction. */
+int orc_cooley_level(const double* A, uint32_t n, double s, uint32_t v, double lo, double hi, double rel_tol,
+                     uint32_t max_iter, int open_tail, double* E_out, double* width_out) {
+    const uint32_t L0 = (n + ORC_COOLEY_SEGS - 1) / ORC_COOLEY_SEGS;
+    const uint32_t L  = L0 > ORC_COOLEY_MINSEG ? L0 : ORC_COOLEY_MINSEG;
+    const uint32_t S  = (n + L - 1) / L;
+    cst      fa[ORC_COOLEY_SEGS], fb[ORC_COOLEY_SEGS], ba[ORC_COOLEY_SEGS], bb[ORC_COOLEY_SEGS];
+    cst      fend[ORC_COOLEY_SEGS], bend[ORC_COOLEY_SEGS];
+    double   accs[ORC_COOLEY_SEGS];
+    uint32_t flips[ORC_COOLEY_SEGS];
+    double   E = 0.5 * (lo + hi), last = NAN;
+    uint32_t it = 0;
+    if (open_tail) lo = lo - (hi - lo); /* soft window for the level of the unbounded problem */
+    for (; it < max_iter; it++) {
+        const double e12 = 12.0 * (s * E);
+        uint32_t     best = 0;
+        for (uint32_t k = 0; k < n; k++)
+            if (A[k] - e12 < 0.0) best = k + 1;
+        const uint32_t ktp = best ? best - 1 : 0;
+        uint32_t       sm  = ktp / L;
+        sm                 = sm < 1 ? 1 : sm;
+        const uint32_t smx = (n - 2) / L;
+        sm                 = sm > smx ? smx : sm;
+        const uint32_t m   = sm * L;
+        for (uint32_t t = 0; t < S; t++) {
+            const uint32_t k0 = t * L < n ? t * L : n, k1 = k0 + L < n ? k0 + L : n;
+            c_basis(A, e12, k0, k1, +1, &fa[t], &fb[t]);
+            if (t >= sm) c_basis(A, e12, t == sm ? m + 1 : k0, k1, -1, &ba[t], &bb[t]);
+        }
+        cst x = {1.0, 1.0, 0};
+        for (uint32_t t = 0; t < S; t++) {
+            const cst y = c_apply(&fa[t], &fb[t], &x);
+            fa[t]       = x;
+            x           = y;
+        }
+        double rho = 0.0;
+        if (open_tail) { /* decaying solution of the recurrence with the last coefficient frozen */
+            double gt, rt;
+            c_coef(A[n - 1], e12, &gt, &rt);
+            if (gt > 0.0) rho = fma(0.5, gt, 1.0) - sqrt(gt * fma(0.25, gt, 1.0));
+        }
+        cst z = {1.0, 1.0 - rho, 0};
+        for (uint32_t t = S; t-- > sm;) {
+            const cst y = c_apply(&ba[t], &bb[t], &z);
+            ba[t]       = z;
+            z           = y;
+        }
+        for (uint32_t t = 0; t < S; t++) {
+            const uint32_t k0 = t * L < n ? t * L : n, k1 = k0 + L < n ? k0 + L : n;
+            cst            xe = fa[t];
+            double         gp, rp, pp = 0.0, acc = 0.0, acc_in = 0.0;
+            uint32_t       fl = 0, fdummy;
+            if (k0 > 0) {
+                c_coef(A[k0 - 1], e12, &gp, &rp);
+                pp = (xe.u - xe.d) * rp;
+            }
+            c_remarch(A, e12, k0, k1, +1, &xe, pp, &fl, &acc);
+            flips[t] = fl;
+            fend[t]  = xe;
+            accs[t]  = acc;
+            if (t >= sm) {
+                cst    ze = ba[t];
+                double pq = 0.0;
+                if (k1 < n) {
+                    c_coef(A[k1], e12, &gp, &rp);
+                    pq = (ze.u - ze.d) * rp;
+                }
+                c_remarch(A, e12, t == sm ? m + 1 : k0, k1, -1, &ze, pq, &fdummy, &acc_in);
+                accs[t] = acc_in;
+                bend[t] = ze;
+            }
+        }
+        uint32_t nodes = 0;
+        for (uint32_t t = 0; t < S; t++) nodes += flips[t];
+        const cst xo = fend[sm - 1], xi = bend[sm];
+        double    gm, rm, gl, rl, gr, rr;
+        c_coef(A[m], e12, &gm, &rm);
+        c_coef(A[m - 1], e12, &gl, &rl);
+        c_coef(A[m + 1], e12, &gr, &rr);
+        const double a_out = xo.d / xo.u, b_in = xi.d / xi.u;
+        const double R     = (-a_out - b_in) - gm;
+        double       Nrm   = 0.0;
+        for (uint32_t t = 0; t < sm; t++) {
+            int sh = 2 * (fend[t].e - xo.e);
+            sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
+            Nrm    = Nrm + scalbn(accs[t], sh);
+        }
+        Nrm = Nrm / (xo.u * xo.u);
+        double Nin = 0.0;
+        for (uint32_t t = S; t-- > sm;) {
+            int sh = 2 * (bend[t].e - xi.e);
+            sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
+            Nin    = Nin + scalbn(accs[t], sh);
+        }
+        Nin = Nin / (xi.u * xi.u);
+        const double pm = rm, pl = (1.0 - a_out) * rl, pr = (1.0 - b_in) * rr;
+        const double Nm = fma(pm, fma(10.0, pm, 2.0 * (pl + pr)), 0.0);
+        const double N  = (Nrm + Nin) + Nm;
+        const double de = -((rm * R) / N);
+        double       dE = de / s;
+        if (!open_tail) {
+            if (nodes > v) hi = E;
+            else lo = E;
+        }
+        double En = E + dE;
+        int    done;
+        if (dE == dE && fabs(dE) <= rel_tol * fabs(E)) { /* converged: the correction is below the tolerance */
+            if (!(En >= lo && En <= hi)) En = E;
+            done = 1;
+        } else if (!(dE == dE) || !(En > lo && En < hi)) { /* NaN, or the step leaves the bracket: bisect */
+            En   = 0.5 * (lo + hi);
+            dE   = En - E;
+            done = (fabs(dE) <= rel_tol * fabs(En)) || !(En != E);
+        } else {
+            done = 0;
+        }
+        last = fabs(dE);
+        E    = En;
+        if (done) {
+            it++;
+            break;
+        }
+    }
+    *E_out = E;
+    if (width_out) *width_out = last;
+    return (int)it;
+}
+
 /* N7.  Normalised wavefunction of one level at energy E on the integration
  * window (psi[0..n_steps), psi_k = psi(r_{i0+k}); Dirichlet zeros at k = -1 and
  * k = n_steps).  DESIGN.md section 3.6:

@@ -86,6 +86,9 @@ class Oracle:
                                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                             C.c_uint32, _f64p, _f64p, C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.orc_cooley_level.restype = C.c_int
+        L.orc_cooley_level.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_uint32, C.c_double, C.c_double, C.c_double,
+                                       C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_spline_resample.restype = C.c_int
         L.orc_spline_resample.argtypes = [_f64p, _f64p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, _f64p]
         L.orc_centrifugal.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32, _f64p]
@@ -170,6 +173,31 @@ class Oracle:
         rounds = self.lib.orc_solve_levels_grid_form(AB, AB.size, s, self.form, E0, dE, j0, n_coarse, vmin, vmax, M, rel_tol,
                                                 max_rounds, levels, widths, C.byref(nb), C.byref(nf), C.byref(st))
         return levels, widths, nb.value, nf.value, rounds, st.value
+
+    def cooley_level(self, A, s, v, lo, hi, rel_tol=1e-12, max_iter=30, open_tail=False):
+        """Outward/inward matching search of level v inside the bracket [lo, hi] on the D-form table A
+        -> (E, |last correction|, iterations)."""
+        assert self.form == 1, "the Cooley search runs on the D-form table (Oracle(form=1))"
+        E, wd = C.c_double(), C.c_double()
+        it = self.lib.orc_cooley_level(np.ascontiguousarray(A), A.size, float(s), int(v), float(lo), float(hi),
+                                       float(rel_tol), int(max_iter), int(bool(open_tail)), C.byref(E), C.byref(wd))
+        return E.value, wd.value, int(it)
+
+    def solve_levels_cooley(self, A, s, E_lo, E_hi, n_coarse, vmin, vmax, rel_tol=1e-12, max_iter=30, open_tail=False):
+        """Coarse sweep + bracketing as solve_levels, then the Cooley search per level
+        -> (levels[nlev], widths[nlev], n_below_hi, iterations[nlev])."""
+        dE = (E_hi - E_lo) / float(n_coarse - 1)
+        nodes, _, _ = self.sweep_uniform(A, s, E_lo, dE, 0, n_coarse, tails=False)
+        nlev = vmax - vmin + 1
+        lev, wid, its = np.full(nlev, np.nan), np.full(nlev, np.nan), np.zeros(nlev, dtype=np.uint32)
+        for l in range(nlev):
+            v = vmin + l
+            if nodes[-1] <= v or nodes[0] > v:
+                continue
+            j = int(np.argmax(nodes > v))
+            lo, hi = E_lo + float(j - 1) * dE, E_lo + float(j) * dE
+            lev[l], wid[l], its[l] = self.cooley_level(A, s, v, lo, hi, rel_tol, max_iter, open_tail)
+        return lev, wid, int(nodes[-1]), its
 
     def wavefunction(self, AB, s, E, h):
         """-> (psi[n_steps] on the integration window, match index m or -1)"""
