@@ -407,8 +407,10 @@ class Comm:
 class Workload:
     """step_resident / step_e2e / digest of one BASELINE config on this rank's context."""
 
-    def __init__(self, name: str, ctx, comm: Comm):
+    def __init__(self, name: str, ctx, comm: Comm, cooley: bool = False):
         from epseon_backend_b200 import multi
+
+        fl, rounds = (ctx.SOLVE_COOLEY, 40) if cooley else (0, None)
 
         self.name, self.ctx, self.cfg = name, ctx, workload_config(name)
         world, rank = comm.world, comm.rank
@@ -422,7 +424,7 @@ class Workload:
             V, s, E_lo, E_hi, _ = rank_curve(rank)
             self.V, self.s, self.scaling = pinned(V), s, "weak"
             self.resident = lambda: ctx.solve_levels(E_lo, E_hi, C2["n_coarse"], 0, C2["v_max"], C2["refine_points"],
-                                                     C2["rel_tol"], C2["max_rounds"])
+                                                     C2["rel_tol"], rounds or C2["max_rounds"], flags=fl)
             self.e2e_tail = self.resident
             self.gather = lambda res: comm.gather_levels(res, 1, C2["v_max"] + 1)  # 17 level energies per rank
         elif name == "c3":
@@ -437,7 +439,7 @@ class Workload:
             E_lo4, E_hi4 = np.ascontiguousarray(w["E_lo"][sl]), np.ascontiguousarray(w["E_hi"][sl])
             self.V, self.s, self.scaling, self.curves = pinned(w["V"][sl]), w["s"], "strong", sl
             self.resident = lambda: ctx.solve_levels(E_lo4, E_hi4, C4["n_coarse"], 0, C4["v_max"], C4["refine_points"],
-                                                     C4["rel_tol"], C4["max_rounds"])
+                                                     C4["rel_tol"], rounds or C4["max_rounds"], flags=fl)
             self.e2e_tail = self.resident
             self.gather = lambda res: comm.gather_levels(res, sl.stop - sl.start, C4["v_max"] + 1)  # [curves of this rank][8]
         else:
@@ -473,20 +475,20 @@ def timed_run(wl: Workload, comm: Comm, step_fn, k: int):
 
 
 def measure(name: str, ctx, comm: Comm, sampler: ClockSampler, steps: int, warmup: int, fp64_peak: float,
-            cpu_seconds: float, form: int = 0) -> dict | None:
+            cpu_seconds: float, form: int = 0, cooley: bool = False) -> dict | None:
     """One record (headline or sub-record): resident rate, e2e rate, roofline of the dominant kernel,
     clocks, CPU oracle beside it, parity flags.  Returned on rank 0 only.  form: the recurrence
     (EPS_OPT_FORM) the tables are prepared for and the sweeps run."""
     ctx.set_option(ctx.OPT_FORM, form)
     try:
-        return _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form)
+        return _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form, cooley)
     finally:
         ctx.set_option(ctx.OPT_FORM, 0)
 
 
-def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form):
+def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, form, cooley):
     comm.attach(ctx)
-    wl = Workload(name, ctx, comm)
+    wl = Workload(name, ctx, comm, cooley)
     for _ in range(warmup):
         wl.gather(wl.resident())
     ctx.sync()
@@ -565,6 +567,17 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     if name == "c5":
         rec["nodes_bit_identical_to_oracle_full_size_sample"] = c5_same
         rec["full_size_sample"] = f"{C5['check_sample']} seeded energies of every rank's slice of the 2^24 (incl. both slice ends)"
+    if cooley:
+        rec["level_search"] = ("Cooley outward/inward matching iteration after the coarse sweep (EPS_SOLVE_COOLEY), one CTA per "
+                               "(curve, level), no host round trips; tolerance-checked against the k-section levels")
+        ctx.set_potentials(wl.V, wl.s)
+        P = C2 if name == "c2" else C4
+        lo_hi = (rank_curve(0)[2:4] if name == "c2" else
+                 (np.ascontiguousarray(W.c4(64, C4["N"], C4["n_coarse"])["E_lo"]), None))
+        if name == "c2":
+            ref = ctx.solve_levels(lo_hi[0], lo_hi[1], P["n_coarse"], 0, P["v_max"], P["refine_points"], 1e-13, 12)[0]
+            rec["max_rel_diff_vs_ksection"] = float(np.nanmax(np.abs(digest[0] - ref) / np.abs(ref)))
+        cpu_seconds = 0
     if cpu_seconds > 0:
         from oracle import Oracle
 
@@ -640,6 +653,13 @@ def main() -> None:
                 keep = ("value", "ms_per_step", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
                         "nodes_bit_identical_to_oracle_full_size_sample", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 (line if name == "c5" else subs[name])["accurate_mode"] = {k: rec[k] for k in keep if k in rec}
+        # ... and the Cooley level search on the accurate tables: time to all levels without refinement sweeps
+        for name in ("c2", "c4"):
+            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, 0.0, form=1, cooley=True)
+            if rec is not None:
+                keep = ("value", "ms_per_step", "time_to_all_levels_ms", "e2e", "gpu_launches", "level_search",
+                        "max_rel_diff_vs_ksection", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
+                subs[name]["cooley_mode"] = {k: rec[k] for k in keep if k in rec}
         if line is not None:
             line["sub_records"] = subs
             line["time_to_all_levels_ms"] = {"c2": subs["c2"]["time_to_all_levels_ms"], "c4": subs["c4"]["time_to_all_levels_ms"]}

@@ -28,7 +28,7 @@ SYMBOLS = [
     "eps_group_create", "eps_group_destroy", "eps_group_size", "eps_group_ctx", "eps_group_last_error", "eps_group_last_ms",
     "eps_group_set_option", "eps_group_set_potentials", "eps_group_sweep_uniform", "eps_group_solve_levels",
     "eps_mailbox_create", "eps_mailbox_open", "eps_mailbox_destroy", "eps_mailbox_post_levels", "eps_mailbox_post",
-    "eps_mailbox_collect", "eps_mailbox_slot_bytes",
+    "eps_mailbox_collect", "eps_mailbox_slot_bytes", "eps_cooley_segment_length",
 ]
 
 
@@ -112,6 +112,12 @@ def device_props(dev: int) -> DeviceProps:
     if rc != EPS_OK:
         raise EpsError(rc, (load().eps_last_error(None) or b"").decode())
     return p
+
+
+def cooley_segment_length(n_steps: int, n_items: int) -> int:
+    lib = load()
+    lib.eps_cooley_segment_length.restype = C.c_uint32
+    return int(lib.eps_cooley_segment_length(C.c_uint32(n_steps), C.c_uint64(n_items)))
 
 
 def _vec(x, n):

@@ -27,8 +27,27 @@
 
 namespace eps {
 
-constexpr int      kCooleyThreads = 256;  // segments per (curve, level)
+constexpr int      kCooleyThreads = 256;  // most segments (= threads) per (curve, level)
 constexpr uint32_t kCooleyMinSeg  = 64;   // shortest segment (steps)
+
+// Segment length for a window of n steps.  Two regimes (measured, profiles/r2_cooley.md):
+//   few (curve, level) items  -- latency-bound: as many segments as there are threads,
+//                                L = ceil(n / kCooleyThreads);
+//   many items (a batch)      -- throughput-bound: the marches cost ~4 L steps per thread, the serial
+//                                chain of thread 0 ~2 n/L matrix applications and a barrier each:
+//                                L ~ sqrt(2.5 n) balances them (fewer, longer segments).
+// At least kCooleyMinSeg steps per segment.  Integer arithmetic: the oracle is handed the same L.
+__host__ __device__ inline uint32_t cooley_segment_length(uint32_t n, uint64_t n_items) {
+    const uint32_t by_threads = (n + kCooleyThreads - 1) / kCooleyThreads;
+    uint32_t       L          = by_threads;
+    if (n_items >= 1024) {
+        uint32_t r = 1;
+        while (static_cast<uint64_t>(r) * r * 2u < 5ull * n) r++;  // r = ceil(sqrt(2.5 n))
+        r = (r + 7u) & ~7u;
+        L = r > by_threads ? r : by_threads;
+    }
+    return L > kCooleyMinSeg ? L : kCooleyMinSeg;
+}
 
 struct CSt {  // value = (u, d) * 2^e
     double u, d;
@@ -62,19 +81,41 @@ __device__ __forceinline__ void cooley_step(CSt& x, const double g) {
     x.u = __dadd_rn(x.u, x.d);
 }
 
+// The coefficients g_k, r_k do not depend on the solution: they are computed kCoefBlock at a time
+// (independent divisions pipeline), and only the two-operation step stays on the dependent chain.
+constexpr int kCoefBlock = 8;
+
+// x * 2^sh, |sh| <= 2000, in one or two exact-power-of-two multiplications (deterministic; the oracle
+// does the same).
+__device__ __forceinline__ double cooley_pow2mul(double x, int sh) {
+    sh = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
+    const int h1 = sh / 2, h2 = sh - h1;
+    x = __dmul_rn(x, __hiloint2double((1023 + h1) << 20, 0));
+    return __dmul_rn(x, __hiloint2double((1023 + h2) << 20, 0));
+}
+
 // Pass 1: transfer matrix of steps k = k0 .. k1-1 taken in direction dir (+1: k0 upwards; -1: from
 // k1-1 downwards), as two basis solutions alpha = (1,0), beta = (0,1).
 __device__ __forceinline__ void cooley_basis(const double* __restrict__ A, const double e12, uint32_t k0, uint32_t k1, int dir,
                                              CSt& a, CSt& b) {
     a = CSt{1.0, 0.0, 0};
     b = CSt{0.0, 1.0, 0};
-    for (uint32_t i = 0; i < k1 - k0; i++) {
-        const uint32_t k = dir > 0 ? k0 + i : k1 - 1 - i;
-        double         g, r;
-        cooley_coef(A[k], e12, g, r);
-        cooley_step(a, g);
-        cooley_step(b, g);
-        if ((i & 127u) == 127u) {
+    const uint32_t len = k1 - k0;
+    for (uint32_t i0 = 0; i0 < len; i0 += kCoefBlock) {
+        double g[kCoefBlock];
+#pragma unroll
+        for (int j = 0; j < kCoefBlock; j++) {
+            const uint32_t i = min(i0 + j, len - 1);
+            double         r;
+            cooley_coef(A[dir > 0 ? k0 + i : k1 - 1 - i], e12, g[j], r);
+        }
+#pragma unroll
+        for (int j = 0; j < kCoefBlock; j++)
+            if (i0 + j < len) {
+                cooley_step(a, g[j]);
+                cooley_step(b, g[j]);
+            }
+        if (((i0 + kCoefBlock) & 127u) == 0u && i0 + kCoefBlock <= len) {
             cooley_renorm(a, nullptr, nullptr);
             cooley_renorm(b, nullptr, nullptr);
         }
@@ -88,7 +129,8 @@ __device__ __forceinline__ CSt cooley_apply(const CSt& a, const CSt& b, const CS
     // value = x.u * a + x.d * b, columns scaled by 2^a.e / 2^b.e: bring b to a's exponent
     int sh = b.e - a.e;
     sh     = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
-    const double bu = scalbn(b.u, sh), bd = scalbn(b.d, sh);
+    const double sc = __hiloint2double((1023 + sh) << 20, 0);  // 2^sh, exact
+    const double bu = __dmul_rn(b.u, sc), bd = __dmul_rn(b.d, sc);
     CSt          y;
     y.u = __fma_rn(a.u, x.u, __dmul_rn(bu, x.d));
     y.d = __fma_rn(a.d, x.u, __dmul_rn(bd, x.d));
@@ -104,24 +146,32 @@ __device__ __forceinline__ void cooley_remarch(const double* __restrict__ A, con
                                                CSt& x, double psi_prev, uint32_t& flips, double& acc) {
     flips = 0;
     acc   = 0.0;
-    for (uint32_t i = 0; i < k1 - k0; i++) {
-        const uint32_t k = dir > 0 ? k0 + i : k1 - 1 - i;
-        double         g, r;
-        cooley_coef(A[k], e12, g, r);
-        const double psi = __dmul_rn(x.u, r);
-        acc              = __fma_rn(psi, __fma_rn(10.0, psi, __dmul_rn(2.0, psi_prev)), acc);
-        psi_prev         = psi;
-        const uint32_t before = static_cast<uint32_t>(__double2hiint(x.u));
-        cooley_step(x, g);
-        flips += (before ^ static_cast<uint32_t>(__double2hiint(x.u))) >> 31;
-        if ((i & 127u) == 127u) cooley_renorm(x, &acc, &psi_prev);
+    const uint32_t len = k1 - k0;
+    for (uint32_t i0 = 0; i0 < len; i0 += kCoefBlock) {
+        double g[kCoefBlock], r[kCoefBlock];
+#pragma unroll
+        for (int j = 0; j < kCoefBlock; j++) {
+            const uint32_t i = min(i0 + j, len - 1);
+            cooley_coef(A[dir > 0 ? k0 + i : k1 - 1 - i], e12, g[j], r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kCoefBlock; j++)
+            if (i0 + j < len) {
+                const double psi = __dmul_rn(x.u, r[j]);
+                acc              = __fma_rn(psi, __fma_rn(10.0, psi, __dmul_rn(2.0, psi_prev)), acc);
+                psi_prev         = psi;
+                const uint32_t before = static_cast<uint32_t>(__double2hiint(x.u));
+                cooley_step(x, g[j]);
+                flips += (before ^ static_cast<uint32_t>(__double2hiint(x.u))) >> 31;
+            }
+        if (((i0 + kCoefBlock) & 127u) == 0u && i0 + kCoefBlock <= len) cooley_renorm(x, &acc, &psi_prev);
     }
     cooley_renorm(x, &acc, &psi_prev);
 }
 
 // state: 1 = active bracket [lo, hi] from the coarse sweep; on return levels[idx] = E (NaN for
 // absent levels), widths[idx] = |last correction|, state 2, iters[idx] = iterations used.
-__global__ void __launch_bounds__(kCooleyThreads)
+__global__ void __launch_bounds__(kCooleyThreads, 2)
 cooley_search_kernel(const double* __restrict__ Atab, const CurveDev* __restrict__ curves, uint32_t n_lev, uint32_t v_min,
                      double rel_tol, uint32_t max_iter, double* __restrict__ lo_g, double* __restrict__ hi_g,
                      uint32_t* __restrict__ state, double* __restrict__ levels, double* __restrict__ widths,
@@ -149,7 +199,7 @@ cooley_search_kernel(const double* __restrict__ Atab, const CurveDev* __restrict
     const uint32_t v  = v_min + idx % n_lev;
     const uint32_t n  = cv.n_steps;
     const double*  A  = Atab + cv.f_off;
-    const uint32_t L  = max(kCooleyMinSeg, (n + kCooleyThreads - 1) / kCooleyThreads);
+    const uint32_t L  = cooley_segment_length(n, gridDim.x);
     const uint32_t S  = (n + L - 1) / L;  // segments in use (<= kCooleyThreads)
     const uint32_t k0 = min(n, tid * L), k1 = min(n, k0 + L);
     double         lo = lo_g[idx], hi = hi_g[idx];
@@ -178,7 +228,7 @@ cooley_search_kernel(const double* __restrict__ Atab, const CurveDev* __restrict
         __syncthreads();
         if (tid == 0) {
             uint32_t b = 0;
-            for (int w = 0; w < kCooleyThreads / 32; w++) b = max(b, red[w]);
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) b = max(b, red[w]);
             const uint32_t ktp = b ? b - 1 : 0;
             uint32_t       sm  = ktp / L;
             sm                 = sm < 1 ? 1 : sm;
@@ -269,16 +319,12 @@ cooley_search_kernel(const double* __restrict__ Atab, const CurveDev* __restrict
             const double R     = __dsub_rn(__dsub_rn(-a_out, b_in), gm);  // (u_{m+1} - 2 u_m + u_{m-1}) / u_m - g_m
             double       Nrm   = 0.0;
             for (uint32_t s = 0; s < sm; s++) {  // outward segments: units of their end scale -> units of u_m
-                int sh = 2 * (fa[s].e - xo.e);
-                sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
-                Nrm    = __dadd_rn(Nrm, scalbn(acc_s[s], sh));
+                Nrm = __dadd_rn(Nrm, cooley_pow2mul(acc_s[s], 2 * (fa[s].e - xo.e)));
             }
             Nrm = __ddiv_rn(Nrm, __dmul_rn(xo.u, xo.u));
             double Nin = 0.0;
             for (uint32_t s = S; s-- > sm;) {
-                int sh = 2 * (ba[s].e - xi.e);
-                sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
-                Nin    = __dadd_rn(Nin, scalbn(acc_s[s], sh));
+                Nin = __dadd_rn(Nin, cooley_pow2mul(acc_s[s], 2 * (ba[s].e - xi.e)));
             }
             Nin = __ddiv_rn(Nin, __dmul_rn(xi.u, xi.u));
             // the point m itself and its two cross terms: psi_m = r_m, psi_{m-1} = (1 - a_out) r_{m-1}, psi_{m+1} = (1 - b_in) r_{m+1}

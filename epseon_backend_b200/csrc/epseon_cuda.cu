@@ -997,7 +997,14 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         for (const auto& ci : ctx->curves) cooley = cooley && ci.n_steps >= 256u;  // short windows: k-section
     }
     if (cooley) {
-        cooley_search_kernel<<<total, kCooleyThreads, 0, ctx->stream>>>(ctx->d_A.p, ctx->d_curves.p, nlev, p->v_min, p->rel_tol,
+        // one thread per segment of the longest window, rounded up to whole warps
+        uint32_t seg_max = 1;
+        for (const auto& ci : ctx->curves) {
+            const uint32_t L = cooley_segment_length(ci.n_steps, total);
+            seg_max          = std::max(seg_max, (ci.n_steps + L - 1) / L);
+        }
+        const uint32_t threads = std::min<uint32_t>(kCooleyThreads, (seg_max + 31u) / 32u * 32u);
+        cooley_search_kernel<<<total, threads, 0, ctx->stream>>>(ctx->d_A.p, ctx->d_curves.p, nlev, p->v_min, p->rel_tol,
                                                                        std::max<uint32_t>(p->max_rounds, 1u), ctx->d_lo.p, ctx->d_hi.p,
                                                                        ctx->d_state.p, ctx->d_levels.p, ctx->d_widths.p, nullptr,
                                                                        ctx->d_steps, ctx->d_stop, (p->flags & EPS_SOLVE_OPEN_TAIL) ? 1 : 0);
@@ -1871,5 +1878,7 @@ int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout
 }
 
 size_t eps_mailbox_slot_bytes(const eps_mailbox* mb) { return mb ? mb->slot_bytes : 0; }
+
+uint32_t eps_cooley_segment_length(uint32_t n_steps, uint64_t n_items) { return cooley_segment_length(n_steps, n_items); }
 
 }  // extern "C"

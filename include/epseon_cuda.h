@@ -114,6 +114,10 @@ typedef struct eps_solve_params {
  *   +2.6e-6 relative); the open tail removes that.  Node counts are a property of the box problem, so
  *   the bracket becomes a soft window [lo - (hi - lo), hi] around the box level. */
 enum { EPS_SOLVE_COOLEY = 1, EPS_SOLVE_OPEN_TAIL = 2 };
+/* Grid steps per segment of the Cooley kernel for windows of n_steps steps when n_items (curve, level)
+ * pairs are searched in one call (one thread per segment; the summation order, hence the result's
+ * last bits, depend on it: the oracle is handed the same number). */
+uint32_t eps_cooley_segment_length(uint32_t n_steps, uint64_t n_items);
 
 /* Counters since the last eps_stats_reset(). */
 typedef struct eps_stats {

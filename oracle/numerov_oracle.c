@@ -464,13 +464,20 @@ static void c_basis(const double* A, double e12, uint32_t k0, uint32_t k1, int d
 static cst c_apply(const cst* a, const cst* b, const cst* x) {
     int sh = b->e - a->e;
     sh     = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
-    const double bu = scalbn(b->u, sh), bd = scalbn(b->d, sh);
+    const double sc = u2d((uint64_t)(1023 + sh) << 52); /* 2^sh, exact */
+    const double bu = b->u * sc, bd = b->d * sc;
     cst          y;
     y.u = fma(a->u, x->u, bu * x->d);
     y.d = fma(a->d, x->u, bd * x->d);
     y.e = x->e + a->e;
     c_renorm(&y, 0, 0);
     return y;
+}
+static double c_pow2mul(double x, int sh) {
+    sh = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
+    const int h1 = sh / 2, h2 = sh - h1;
+    x = x * u2d((uint64_t)(1023 + h1) << 52);
+    return x * u2d((uint64_t)(1023 + h2) << 52);
 }
 static void c_remarch(const double* A, double e12, uint32_t k0, uint32_t k1, int dir, cst* x, double psi_prev,
                       uint32_t* flips, double* acc_out) {
@@ -496,9 +503,11 @@ static void c_remarch(const double* A, double e12, uint32_t k0, uint32_t k1, int
 /* One level: bracket [lo, hi] with nodes(lo) <= v < nodes(hi).  Returns the iterations used;
  * *E_out the level, *width_out the magnitude of the last correction. */
 int orc_cooley_level(const double* A, uint32_t n, double s, uint32_t v, double lo, double hi, double rel_tol,
-                     uint32_t max_iter, int open_tail, double* E_out, double* width_out) {
+                     uint32_t max_iter, int open_tail, uint32_t seg_len, double* E_out, double* width_out) {
+    /* seg_len: the segment length the device chose (eps_cooley_segment_length); 0 = the few-item rule */
     const uint32_t L0 = (n + ORC_COOLEY_SEGS - 1) / ORC_COOLEY_SEGS;
-    const uint32_t L  = L0 > ORC_COOLEY_MINSEG ? L0 : ORC_COOLEY_MINSEG;
+    uint32_t       L  = seg_len ? seg_len : L0;
+    L                 = L > ORC_COOLEY_MINSEG ? L : ORC_COOLEY_MINSEG;
     const uint32_t S  = (n + L - 1) / L;
     cst      fa[ORC_COOLEY_SEGS], fb[ORC_COOLEY_SEGS], ba[ORC_COOLEY_SEGS], bb[ORC_COOLEY_SEGS];
     cst      fend[ORC_COOLEY_SEGS], bend[ORC_COOLEY_SEGS];
@@ -577,16 +586,12 @@ int orc_cooley_level(const double* A, uint32_t n, double s, uint32_t v, double l
         const double R     = (-a_out - b_in) - gm;
         double       Nrm   = 0.0;
         for (uint32_t t = 0; t < sm; t++) {
-            int sh = 2 * (fend[t].e - xo.e);
-            sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
-            Nrm    = Nrm + scalbn(accs[t], sh);
+            Nrm = Nrm + c_pow2mul(accs[t], 2 * (fend[t].e - xo.e));
         }
         Nrm = Nrm / (xo.u * xo.u);
         double Nin = 0.0;
         for (uint32_t t = S; t-- > sm;) {
-            int sh = 2 * (bend[t].e - xi.e);
-            sh     = sh > 2000 ? 2000 : (sh < -2000 ? -2000 : sh);
-            Nin    = Nin + scalbn(accs[t], sh);
+            Nin = Nin + c_pow2mul(accs[t], 2 * (bend[t].e - xi.e));
         }
         Nin = Nin / (xi.u * xi.u);
         const double pm = rm, pl = (1.0 - a_out) * rl, pr = (1.0 - b_in) * rr;

@@ -88,7 +88,7 @@ class Oracle:
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.orc_cooley_level.restype = C.c_int
         L.orc_cooley_level.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_uint32, C.c_double, C.c_double, C.c_double,
-                                       C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+                                       C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_spline_resample.restype = C.c_int
         L.orc_spline_resample.argtypes = [_f64p, _f64p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, _f64p]
         L.orc_centrifugal.argtypes = [_f64p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32, _f64p]
@@ -174,16 +174,17 @@ class Oracle:
                                                 max_rounds, levels, widths, C.byref(nb), C.byref(nf), C.byref(st))
         return levels, widths, nb.value, nf.value, rounds, st.value
 
-    def cooley_level(self, A, s, v, lo, hi, rel_tol=1e-12, max_iter=30, open_tail=False):
+    def cooley_level(self, A, s, v, lo, hi, rel_tol=1e-12, max_iter=30, open_tail=False, seg_len=0):
         """Outward/inward matching search of level v inside the bracket [lo, hi] on the D-form table A
         -> (E, |last correction|, iterations)."""
         assert self.form == 1, "the Cooley search runs on the D-form table (Oracle(form=1))"
         E, wd = C.c_double(), C.c_double()
         it = self.lib.orc_cooley_level(np.ascontiguousarray(A), A.size, float(s), int(v), float(lo), float(hi),
-                                       float(rel_tol), int(max_iter), int(bool(open_tail)), C.byref(E), C.byref(wd))
+                                       float(rel_tol), int(max_iter), int(bool(open_tail)), int(seg_len), C.byref(E), C.byref(wd))
         return E.value, wd.value, int(it)
 
-    def solve_levels_cooley(self, A, s, E_lo, E_hi, n_coarse, vmin, vmax, rel_tol=1e-12, max_iter=30, open_tail=False):
+    def solve_levels_cooley(self, A, s, E_lo, E_hi, n_coarse, vmin, vmax, rel_tol=1e-12, max_iter=30, open_tail=False,
+                            seg_len=0):
         """Coarse sweep + bracketing as solve_levels, then the Cooley search per level
         -> (levels[nlev], widths[nlev], n_below_hi, iterations[nlev])."""
         dE = (E_hi - E_lo) / float(n_coarse - 1)
@@ -196,7 +197,7 @@ class Oracle:
                 continue
             j = int(np.argmax(nodes > v))
             lo, hi = E_lo + float(j - 1) * dE, E_lo + float(j) * dE
-            lev[l], wid[l], its[l] = self.cooley_level(A, s, v, lo, hi, rel_tol, max_iter, open_tail)
+            lev[l], wid[l], its[l] = self.cooley_level(A, s, v, lo, hi, rel_tol, max_iter, open_tail, seg_len)
         return lev, wid, int(nodes[-1]), its
 
     def wavefunction(self, AB, s, E, h):

@@ -94,9 +94,16 @@ def test_cuda_cooley_batch_and_open_tail(oracle_d, ctx):
     lev, wid, nb = ctx.solve_levels(w["E_lo"], w["E_hi"], 512, 0, 7, 1, 1e-12, 40, flags=ctx.SOLVE_COOLEY)
     ref, _, nb_ref = ctx.solve_levels(w["E_lo"], w["E_hi"], 512, 0, 7, 64, 1e-13, 14)
     assert np.array_equal(nb, nb_ref) and np.max(np.abs(lev - ref) / ref) < 2e-13
-    for c in (0, 17, 39):
+    from epseon_backend_b200 import cabi
+
+    w = W.c4(nC=160, N=6000, nE=512)  # 1280 (curve, level) items: the batch rule for the segment length
+    ctx.set_potentials(w["V"], w["s"])
+    lev, wid, nb = ctx.solve_levels(w["E_lo"], w["E_hi"], 512, 0, 7, 1, 1e-12, 40, flags=ctx.SOLVE_COOLEY)
+    for c in (0, 17, 159):
         A, *_ = oracle_d.prep(w["V"][c], w["s"])
-        lev_o, *_ = oracle_d.solve_levels_cooley(A, w["s"], w["E_lo"][c], w["E_hi"][c], 512, 0, 7, 1e-12, 40)
+        L = cabi.cooley_segment_length(A.size, 160 * 8)
+        assert L > cabi.cooley_segment_length(A.size, 8)
+        lev_o, *_ = oracle_d.solve_levels_cooley(A, w["s"], w["E_lo"][c], w["E_hi"][c], 512, 0, 7, 1e-12, 40, seg_len=L)
         assert _same_bits(lev[c], lev_o)
     V, s, De, exact = _docs_example()
     A, *_ = oracle_d.prep(V, s)
