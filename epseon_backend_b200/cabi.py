@@ -454,10 +454,11 @@ class Mailbox:
         a = np.ascontiguousarray(payload)
         self.ctx._ck(self.ctx.lib.eps_mailbox_post(self.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes), C.c_uint32(seq)))
 
-    def collect(self, seq: int, timeout_s: float = 60.0) -> np.ndarray:
-        """Rank 0: -> uint8 array [world, slot_bytes] once every rank has posted `seq`."""
-        out = np.empty((self.world, self.slot), dtype=np.uint8)
-        self.ctx._ck(self.ctx.lib.eps_mailbox_collect(self.h, C.c_uint32(seq), out.ctypes.data_as(C.c_void_p), C.c_double(timeout_s)))
+    def collect(self, seq: int, nbytes: int, timeout_s: float = 60.0) -> np.ndarray:
+        """Rank 0: -> uint8 array [world, nbytes] (the head of every slot) once every rank has posted `seq`."""
+        out = np.empty((self.world, nbytes), dtype=np.uint8)
+        self.ctx._ck(self.ctx.lib.eps_mailbox_collect(self.h, C.c_uint32(seq), out.ctypes.data_as(C.c_void_p),
+                                                      C.c_size_t(nbytes), C.c_double(timeout_s)))
         return out
 
     def close(self):

@@ -1757,7 +1757,7 @@ int eps_mailbox_create(eps_ctx* ctx, uint32_t world, size_t bytes_per_rank, eps_
     mb->rank       = 0;
     mb->owner      = true;
     mb->slot_bytes = (bytes_per_rank + 255) / 256 * 256;
-    const size_t total = mb->slot_bytes * world + 256 * ((world * sizeof(uint32_t) + 255) / 256);
+    const size_t total = mb->slot_bytes * world + 256 * (((world + 1) * sizeof(uint32_t) + 255) / 256);  // slots, flags, ack
     cudaError_t  e     = cudaMalloc(reinterpret_cast<void**>(&mb->d_base), total);
     if (e == cudaSuccess) e = cudaMemset(mb->d_base, 0, total);
     cudaIpcMemHandle_t h;
@@ -1816,9 +1816,26 @@ int eps_mailbox_destroy(eps_mailbox* mb) {
 }
 
 namespace {
+// Flow control: a rank may not overwrite its slot before rank 0 has fetched the previous payload.
+// Rank 0 acknowledges every collect by writing the sequence number behind the flags; a sender polls
+// that word (one small peer read, normally satisfied at once) before posting seq > ack + 1.
+int mailbox_wait_ack(eps_mailbox* mb, uint32_t seq) {
+    if (mb->owner || seq <= 1) return EPS_OK;
+    eps_ctx*        ctx = mb->ctx;
+    const uint32_t* ack = reinterpret_cast<const uint32_t*>(mb->d_base + mb->slot_bytes * mb->world) + mb->world;
+    const auto      t0  = std::chrono::steady_clock::now();
+    for (;;) {
+        EPS_CUDA(ctx, cudaMemcpyAsync(mb->h_seq + 63, ack, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (static_cast<int32_t>(mb->h_seq[63] - (seq - 1)) >= 0) return EPS_OK;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+            return fail(ctx, EPS_ERR_STATE, "eps_mailbox_post: rank 0 never collected the previous payload");
+    }
+}
+
 int mailbox_flag(eps_mailbox* mb, uint32_t seq) {  // sequence number after the payload, in stream order
     eps_ctx* ctx = mb->ctx;
-    uint32_t* src = mb->h_seq + (mb->ring++ % 64);
+    uint32_t* src = mb->h_seq + (mb->ring++ % 62);  // (slots 62 / 63: acknowledgement out / in)
     *src          = seq;
     uint32_t* flags = reinterpret_cast<uint32_t*>(mb->d_base + mb->slot_bytes * mb->world);
     EPS_CUDA(ctx, cudaMemcpyAsync(flags + mb->rank, src, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1835,6 +1852,7 @@ int eps_mailbox_post_levels(eps_mailbox* mb, uint32_t seq) {
     const size_t n = ctx->last_total;
     EPS_REQUIRE(ctx, n > 0, EPS_ERR_STATE, "no level search has run on this context");
     EPS_REQUIRE(ctx, 2 * n * sizeof(double) <= mb->slot_bytes, EPS_ERR_INVALID, "mailbox slot too small for the levels");
+    if (int rc = mailbox_wait_ack(mb, seq)) return rc;
     char* dst = mb->d_base + mb->slot_bytes * mb->rank;
     EPS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_levels.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     EPS_CUDA(ctx, cudaMemcpyAsync(dst + n * sizeof(double), ctx->d_widths.p, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1847,19 +1865,22 @@ int eps_mailbox_post(eps_mailbox* mb, const void* src, size_t bytes, uint32_t se
     eps_ctx* ctx = mb->ctx;
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, src && bytes <= mb->slot_bytes, EPS_ERR_INVALID, "payload larger than the mailbox slot");
+    if (int rc = mailbox_wait_ack(mb, seq)) return rc;
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer may still be in flight
     std::memcpy(mb->h_stage, src, bytes);
     EPS_CUDA(ctx, cudaMemcpyAsync(mb->d_base + mb->slot_bytes * mb->rank, mb->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return mailbox_flag(mb, seq);
 }
 
-/* Rank 0: wait until every rank's slot carries `seq`, then fetch all slots ([world][slot]; the slot
- * stride is eps_mailbox_slot_bytes) with one device->host copy.  EPS_ERR_STATE after timeout_s. */
-int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout_s) {
+/* Rank 0: wait until every rank's slot carries `seq`, then fetch the first bytes_per_rank bytes of
+ * every slot (out: [world][bytes_per_rank]) with one strided device->host copy, and acknowledge.
+ * EPS_ERR_STATE after timeout_s. */
+int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, size_t bytes_per_rank, double timeout_s) {
     if (!mb) return fail(nullptr, EPS_ERR_INVALID, "null mailbox");
     eps_ctx* ctx = mb->ctx;
     if (int rc = bind(ctx)) return rc;
     EPS_REQUIRE(ctx, mb->owner && out, EPS_ERR_INVALID, "collect is for the mailbox's owner (rank 0)");
+    EPS_REQUIRE(ctx, bytes_per_rank >= 1 && bytes_per_rank <= mb->slot_bytes, EPS_ERR_INVALID, "bytes_per_rank exceeds the slot");
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(mb->d_base + mb->slot_bytes * mb->world);
     const auto      t0    = std::chrono::steady_clock::now();
     for (;;) {
@@ -1871,9 +1892,13 @@ int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
             return fail(ctx, EPS_ERR_STATE, "eps_mailbox_collect: timed out waiting for a rank");
     }
-    EPS_CUDA(ctx, cudaMemcpyAsync(out, mb->d_base, mb->slot_bytes * mb->world, cudaMemcpyDeviceToHost, ctx->stream));
+    // the first bytes_per_rank bytes of every slot, packed [world][bytes_per_rank], in one strided copy
+    EPS_CUDA(ctx, cudaMemcpy2DAsync(out, bytes_per_rank, mb->d_base, mb->slot_bytes, bytes_per_rank, mb->world,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    mb->h_seq[62] = seq;  // acknowledge: the senders may post again
+    EPS_CUDA(ctx, cudaMemcpyAsync(const_cast<uint32_t*>(flags) + mb->world, mb->h_seq + 62, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->stats.d2h_bytes += mb->slot_bytes * mb->world;
+    ctx->stats.d2h_bytes += bytes_per_rank * mb->world;
     return EPS_OK;
 }
 

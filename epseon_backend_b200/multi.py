@@ -97,8 +97,8 @@ class MailboxComm:
         self.box.post(a, self.seq)
         if self.rank != 0:
             return None
-        raw = self.box.collect(self.seq)
-        return [raw[r, : a.nbytes].view(a.dtype).reshape(a.shape).copy() for r in range(self.world)]
+        raw = self.box.collect(self.seq, a.nbytes)
+        return [raw[r].view(a.dtype).reshape(a.shape).copy() for r in range(self.world)]
 
     def gather_levels(self, n_curves: int, n_levels: int):
         """The levels / widths of every rank's last ``solve_levels*``, device to device (no host
@@ -107,11 +107,11 @@ class MailboxComm:
         self.box.post_levels(self.seq)
         if self.rank != 0:
             return None
-        raw = self.box.collect(self.seq)
         n = n_curves * n_levels
+        raw = self.box.collect(self.seq, 16 * n)
         out = []
         for r in range(self.world):
-            d = raw[r, : 16 * n].view(np.float64)
+            d = raw[r].view(np.float64)
             out.append((d[:n].reshape(n_curves, n_levels).copy(), d[n:].reshape(n_curves, n_levels).copy()))
         return out
 

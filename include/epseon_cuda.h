@@ -308,8 +308,9 @@ int         eps_group_solve_levels(eps_group* g, const eps_solve_params* p, cons
 /* ---- one process per device (e.g. under torchrun): a mailbox in rank 0's device memory, shared
  * through a CUDA IPC handle (64 bytes; the caller moves it between the processes).  Every rank
  * writes its small result into its slot device-to-device (a peer write over NVLink) followed by a
- * sequence number in stream order; rank 0 waits for all sequence numbers and fetches every slot
- * with one device->host copy.  Slot layout of eps_mailbox_post_levels: [levels | widths] of the
+ * sequence number in stream order; rank 0 waits for all sequence numbers, fetches the first
+ * bytes_per_rank bytes of every slot with one strided device->host copy (out: [world][bytes_per_rank])
+ * and acknowledges, which lets the senders post again (one payload in flight per rank).  Slot layout of eps_mailbox_post_levels: [levels | widths] of the
  * rank's last level search. */
 typedef struct eps_mailbox eps_mailbox;
 int    eps_mailbox_create(eps_ctx* ctx, uint32_t world, size_t bytes_per_rank, eps_mailbox** out, unsigned char* handle64);
@@ -318,7 +319,7 @@ int    eps_mailbox_open(eps_ctx* ctx, const unsigned char* handle64, uint32_t wo
 int    eps_mailbox_destroy(eps_mailbox* mb);
 int    eps_mailbox_post_levels(eps_mailbox* mb, uint32_t seq);
 int    eps_mailbox_post(eps_mailbox* mb, const void* src, size_t bytes, uint32_t seq);
-int    eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, double timeout_s);
+int    eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, size_t bytes_per_rank, double timeout_s);
 size_t eps_mailbox_slot_bytes(const eps_mailbox* mb);
 
 /* ---- page-locked host buffers (optional) ---------------------------------
