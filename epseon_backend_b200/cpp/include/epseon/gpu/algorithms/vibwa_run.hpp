@@ -203,6 +203,13 @@ namespace epseon::gpu::cpp {
         p.refine_points = 256;
         p.max_rounds    = 16;
         p.rel_tol       = std::is_same_v<FP, float> ? 1e-8 : 1e-12;
+        // One curve, a large coarse grid: the sweep costs whole waves of 512-energy CTAs, so the grid is
+        // rounded up to the next full wave (65 536 -> 148 x 512 = 75 776 on a B200): finer brackets for
+        // the same sweep time (profiles/r1g_ncu.md: 128 and 148 CTAs take the same 1.87 ms).
+        if (nC == 1 && p.n_coarse >= 32768u) {
+            const uint32_t wave = static_cast<uint32_t>(detail::sm_count_of(guard.device)) * 512u;
+            p.n_coarse          = (p.n_coarse + wave - 1) / wave * wave;
+        }
         const uint32_t        nlev = p.v_max - p.v_min + 1;
         // A handful of curves: a refinement round is latency-bound, so many points per round (few
         // rounds) win.  Hundreds of curves: rounds are throughput-bound and k-section with fewer

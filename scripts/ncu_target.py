@@ -1,18 +1,56 @@
-"""Short workload for ncu captures: C2 set-up, a few sweeps, one full level solve."""
+"""Short workload for ncu captures: one BASELINE workload's resident step, a few times.
+
+    python scripts/ncu_target.py c2|c3|c4|c5|cooley [form] [reps]
+
+c2: 65 536-energy coarse sweep + refinement of 17 levels (TMA ring kernel, flat rows);
+c3: 4096 energies x 1M grid (scan path); c4: 4096 curves x (1024 coarse + packed refinement rows);
+c5: 2^22 energies x 200k grid (constant-bank kernel; a quarter of C5, same CTA count per SM wave);
+cooley: C2 and a 512-curve batch through EPS_SOLVE_COOLEY.  form = 0 (X form) / 1 (D form).
+"""
 import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+import numpy as np  # noqa: E402
+
 from epseon_backend_b200 import cabi  # noqa: E402
 from tests import workloads as W  # noqa: E402
 
-nE = int(sys.argv[1]) if len(sys.argv) > 1 else 75776
+which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+form = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 ctx = cabi.Context(0)
-w = W.c2()
-ctx.set_potentials(w["V"], w["s"])
-for _ in range(3):
-    ctx.sweep_uniform(w["E_lo"], w["E_hi"], nE, nodes=False, tails=False)
+ctx.set_option(ctx.OPT_FORM, form)
+if which == "c2":
+    w = W.c2()
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 65536, 0, 16, 4457, 1e-10, 8)
+elif which == "c3":
+    w = W.c3()
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.sweep_uniform(w["E_lo"], w["E_hi"], 4096, nodes=False, tails=False)
+elif which == "c4":
+    w = W.c4()
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, 7, 32, 1e-10, 8)
+elif which == "c5":
+    w = W.c5(nE=1 << 22)
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.sweep_uniform(w["E_lo"], w["E_hi"], 1 << 22, nodes=False, tails=False)
+elif which == "cooley":
+    ctx.set_option(ctx.OPT_FORM, 1)
+    w = W.c2()
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 65536, 0, 16, 1, 1e-10, 40, flags=ctx.SOLVE_COOLEY)
+    w = W.c4(512, 10_000, 1024)
+    ctx.set_potentials(w["V"], w["s"])
+    for _ in range(reps):
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, 7, 1, 1e-10, 40, flags=ctx.SOLVE_COOLEY)
 ctx.sync()
-if "solve" in sys.argv:
-    ctx.solve_levels(w["E_lo"], w["E_hi"], 65536, 0, 16, 4352, 1e-10, 8)
+print("ncu_target done", which, form)

@@ -1,7 +1,8 @@
 """Small pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
 TMA sweep (tails, packed + flat refinement rows), scan path + fix-up, constant-bank chunks,
-device prep, centrifugal expansion, spline evaluation, wavefunctions.  Sizes are tiny: the
-sanitizer slows kernels 10-100x."""
+device prep, centrifugal expansion, spline evaluation, wavefunctions; round 2: the D form on every
+route, the Cooley search kernel (box and open tail), a two-context group with its peer copies, the
+stop flag.  Sizes are tiny: the sanitizer slows kernels 10-100x."""
 import sys
 from pathlib import Path
 
@@ -35,5 +36,31 @@ with cabi.Context(0) as ctx:
     ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 0)
     rk = np.concatenate([np.linspace(0.4, 4.0, 40), np.linspace(4.5, 9.0, 8)])
     ctx.spline_resample(rk, W.morse(5500.0, 2.2, 1.6, 0.4, 9.0, 2)[0] + 5500.0 * (1 - np.exp(-1.6 * (rk - 2.2))) ** 2, 0.4, 9.0, 3000)
+    # ---- round 2: accurate recurrence (D form) on every route + Cooley search + cancellation flag
+    ctx.set_option(ctx.OPT_FORM, 1)
+    ctx.set_potentials(V, s)
+    ctx.sweep_uniform(lo, hi, 700)
+    ctx.solve_levels(lo, hi, 512, 0, 5, 64, 1e-10, 6)
+    ctx.solve_levels(lo, hi, 512, 0, 5, 1, 1e-12, 30, flags=ctx.SOLVE_COOLEY)
+    ctx.solve_levels(lo, hi, 512, 0, 5, 1, 1e-12, 30, flags=ctx.SOLVE_COOLEY | ctx.SOLVE_OPEN_TAIL)
+    ctx.set_potentials(V[0], s)
+    ctx.set_option(ctx.OPT_CBANK, 1)
+    ctx.sweep_uniform(lo[0], hi[0], 1500)
+    ctx.set_option(ctx.OPT_CBANK, 2)
+    ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 3)
+    ctx.solve_levels(lo[0], hi[0], 256, 0, 3, 32, 1e-10, 6)
+    ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 0)
+    ctx.request_stop()
+    try:
+        ctx.sweep_uniform(lo[0], hi[0], 600)
+    except cabi.EpsError as e:
+        assert e.code == cabi.EPS_ERR_CANCELLED
+    ctx.reset_stop()
     ctx.sync()
+with cabi.Group([0, 0]) as g:                                          # two contexts, host threads, peer copies
+    g.set_potentials(V, s, cabi.SHARD_CURVES)
+    g.solve_levels(lo, hi, 256, 0, 3, 32, 1e-10, 6)
+    g.set_potentials(V[0], s, cabi.SHARD_ENERGY)
+    g.solve_levels(lo[0], hi[0], 257, 0, 3, 32, 1e-10, 6)
+    g.sweep_uniform(lo[0], hi[0], 500)
 print("sanitize_target done")

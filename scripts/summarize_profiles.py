@@ -15,7 +15,9 @@ from __future__ import annotations
 import argparse
 import collections
 import csv
+import hashlib
 import io
+import json
 import shutil
 import subprocess
 from pathlib import Path
@@ -119,18 +121,58 @@ def ncu_md(tag: str, rep: Path) -> None:
     (PROF / f"{tag}_ncu.md").write_text("\n".join(out) + "\n")
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def csrc_digest() -> str:
+    """Same digest as bench.py: ties a DRAM-traffic figure to the kernel sources it was captured on."""
+    h = hashlib.sha256()
+    for p in sorted((ROOT / "epseon_backend_b200" / "csrc").glob("*.cu*")):
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def traffic_json(tag: str, rep: Path, name: str, kernel: str, per_step: int) -> None:
+    """profiles/traffic.json[name] = dram__bytes_read + dram__bytes_write per launch of the captured
+    launches whose kernel name contains `kernel` (x per_step launches when a bench "launch" is
+    several kernel launches, e.g. the 51 chunks of a constant-bank sweep)."""
+    raw = _ncu(rep, "raw")
+    hdr, units, data = raw[0], raw[1], raw[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    tot, n, names = 0.0, 0, set()
+    for r in data:
+        if kernel not in r[ix["Kernel Name"]]:
+            continue
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[ix[k]].replace(",", "")) * UNIT[units[ix[k]]]
+        n += 1
+        names.add(r[ix["Kernel Name"]].split("(")[0])
+    if n == 0:
+        raise SystemExit(f"no captured launch matches {kernel!r}")
+    path = PROF / "traffic.json"
+    cur = json.loads(path.read_text()) if path.exists() else {}
+    cur[name] = {"dram_bytes_per_launch": int(round(tot / n * per_step)), "launches_captured": n, "kernel_launches_per_bench_launch": per_step,
+                 "kernel": sorted(names)[0], "source": f"profiles/{tag}_ncu.md ({rep.name}, ncu --set full)", "csrc_digest": csrc_digest()}
+    path.write_text(json.dumps(cur, indent=1, sort_keys=True) + "\n")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
     ap.add_argument("--launches", type=Path)
     ap.add_argument("--rep", type=Path)
     ap.add_argument("--copy", type=Path, nargs="*", default=[])
+    ap.add_argument("--traffic", help="workload key of profiles/traffic.json to (re)write from --rep, e.g. c2 or c5_dform")
+    ap.add_argument("--kernel", default="numerov_sweep_kernel", help="kernel-name substring for --traffic")
+    ap.add_argument("--per-step", type=int, default=1, help="kernel launches per bench launch (51 for the c5 chunks)")
     a = ap.parse_args()
     PROF.mkdir(exist_ok=True)
     if a.launches:
         launches_md(a.tag, a.launches)
     if a.rep:
         ncu_md(a.tag, a.rep)
+        if a.traffic:
+            traffic_json(a.tag, a.rep, a.traffic, a.kernel, a.per_step)
     for f in a.copy:
         shutil.copy(f, PROF / f.name)
 
