@@ -69,6 +69,7 @@ struct eps_ctx {
     uint32_t                    nC = 0, N = 0;
     uint64_t                    slot = 0;  // doubles per curve
     DevBuf<double>              d_F, d_A, d_V, d_scale, d_spl, d_Vraw, d_rot;
+    int                         opt_pack128 = 0;  // EPS_OPT_PACK128: 0 auto, 1 always (when rows fit), 2 never
     int                         opt_form  = 0;  // EPS_OPT_FORM: 0 = X form (4 operations), 1 = D form (accurate, 5 operations)
     int                         form_resident = 0;  // form the resident tables were prepared for
     DevBuf<uint32_t>            d_J;
@@ -193,7 +194,7 @@ int fold_events(eps_ctx* ctx) {
     return EPS_OK;
 }
 
-size_t sweep_smem_bytes() { return sizeof(double) * kTile * kStages + 2 * kStages * sizeof(uint64_t); }
+size_t sweep_smem_bytes(int stages) { return sizeof(double) * kTile * stages + 2 * stages * sizeof(uint64_t); }
 
 struct SweepOut {  // device pointers of one sweep's results
     uint32_t* nodes;
@@ -213,14 +214,15 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
                                         : chunks * n_jobs * (kScan ? n_seg : 1u);
     if (grid == 0 || grid >= (1ull << 31)) return cudaErrorInvalidConfiguration;
     auto kern = numerov_sweep_kernel<kEpt, kWarps, kStride, kTails, kScan, kForm>;
+    const size_t smem = sweep_smem_bytes(sweep_stages<kEpt, kWarps>());
     static thread_local int configured_dev = -1;  // opt in to > 48 KiB dynamic smem once per device
     if (configured_dev != ctx->dev) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sweep_smem_bytes()));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         configured_dev = ctx->dev;
     }
     ctx->stats.kernel_launches++;
-    kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, sweep_smem_bytes(), ctx->stream>>>(
+    kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, smem, ctx->stream>>>(
         kForm == 0 ? ctx->d_F.p : ctx->d_A.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
         kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2, ctx->d_stop);
     return cudaGetLastError();
@@ -273,6 +275,9 @@ uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows, uint32_t per_cta = 512) 
 
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                               bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0, uint32_t pack_cta = 512) {
+    if (pack_log2 && pack_log2 != kFlatRows && pack_cta == 128)  // small packed CTAs (balance of small per-device batches)
+        return ctx->form_resident == 1 ? launch_sweep_s<1, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2)
+                                       : launch_sweep_s<1, 4, 0>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     if (ctx->form_resident == 1) {  // D form: the two product shapes only (the EPS_FORCE_* tuning shapes are X-form)
         if ((pack_log2 && pack_log2 != kFlatRows && pack_cta == 256) || (!pack_log2 && nE <= 256u))
             return launch_sweep_s<2, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
@@ -1020,7 +1025,25 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     // round (less total work for the same final width) pay off on many-curve batches.
     const bool     flat      = nC == 1 && !ctx->force_ept;
     const uint32_t rows512   = 1u << pack_log2_for(M, 512, 512);
-    const uint32_t pack_cta  = (!flat && M <= 128 && nlev <= rows512 / 2) ? 256u : 512u;
+    uint32_t       pack_cta  = (!flat && M <= 128 && nlev <= rows512 / 2) ? 256u : 512u;
+    // Balance of small per-device batches.  Equal CTAs over 148 SMs leave a tail: 512 curves in
+    // 256-energy CTAs (2 resident per SM) are 3.46 per SM -> two rounds of 2, i.e. 4 units of SM time
+    // for 3.46 of work.  128-energy CTAs (1 chain x 4 warps, 4 resident per SM: the same four chains
+    // per scheduler) halve the unit: 6.92 per SM -> a round of 4 and one of 3.  Cost model in units of
+    // (one chain per scheduler x the grid): full rounds cost `resident x chains`, the last one what is
+    // left; the smaller shape is taken when it saves more than 5 %.
+    if (pack_cta == 256 && M <= 64 && ctx->opt_pack128 != 2) {
+        const auto cost = [&](uint64_t ctas, uint32_t resident, uint32_t chains) {
+            const uint64_t per_round = static_cast<uint64_t>(ctx->sm_count) * resident;
+            const uint64_t rem       = ctas % per_round;
+            return static_cast<double>(ctas / per_round) * resident * chains +
+                   static_cast<double>((rem + ctx->sm_count - 1) / ctx->sm_count) * chains;
+        };
+        const uint32_t rows256 = 1u << pack_log2_for(M, 512, 256), rows128 = 1u << pack_log2_for(M, 512, 128);
+        const uint64_t c256 = static_cast<uint64_t>(nC) * ((nlev + rows256 - 1) / rows256);
+        const uint64_t c128 = static_cast<uint64_t>(nC) * ((nlev + rows128 - 1) / rows128);
+        if (ctx->opt_pack128 == 1 || cost(c128, 4, 1) < 0.95 * cost(c256, 2, 2)) pack_cta = 128u;
+    }
     const uint32_t pack_rows = flat ? kFlatRows : 1u << pack_log2_for(M, 512, pack_cta);
     const uint32_t nlev_pad  = flat ? nlev : (nlev + pack_rows - 1) / pack_rows * pack_rows;
     const uint32_t n_dense   = nC * nlev_pad;
@@ -1271,6 +1294,10 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
         case EPS_OPT_FORM:
             EPS_REQUIRE(ctx, value == 0 || value == 1, EPS_ERR_INVALID, "form: 0 (X form, 4 operations) or 1 (D form, accurate, 5 operations)");
             ctx->opt_form = static_cast<int>(value);  // takes effect at the next eps_set_potentials*
+            return EPS_OK;
+        case EPS_OPT_PACK128:
+            EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "pack128: 0 auto, 1 always, 2 never");
+            ctx->opt_pack128 = static_cast<int>(value);
             return EPS_OK;
         case EPS_OPT_PREP_PARTS:
             EPS_REQUIRE(ctx, value == 0 || value == 1, EPS_ERR_INVALID, "prep parts: 0 auto, 1 never");

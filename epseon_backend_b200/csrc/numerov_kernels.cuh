@@ -23,7 +23,18 @@
 namespace eps {
 
 constexpr int      kTile          = 2048;  // grid steps per shared-memory stage (16 KiB of F_k)
-constexpr int      kStages        = 4;     // TMA ring depth
+constexpr int      kStages        = 4;     // TMA ring depth of the big CTA shapes
+// Ring depth by CTA shape: the 128-energy CTA (1 chain x 4 warps) runs four to a SM, so two
+// stages (32 KiB) per CTA keep as much table in flight per SM as one 4-stage CTA does.
+template <int kEpt, int kWarps>
+__host__ __device__ constexpr int sweep_stages() {
+    return (kEpt * kWarps <= 4) ? 2 : kStages;
+}
+// Resident CTAs per SM the launch bounds ask for: 1 (512 energies), 2 (256), 4 (128).
+template <int kEpt, int kWarps>
+__host__ __device__ constexpr int sweep_min_ctas() {
+    return (kEpt * kWarps >= 32) ? 1 : ((kEpt * kWarps <= 4) ? 4 : 2);
+}
 constexpr uint32_t kProducerSuspendNs = 1000000;  // try_wait suspend-time hint of the TMA producer
 // CTA shape of the sweep: kWarps consumer warps (template parameter) + 1 TMA producer warp,
 // 32 * kWarps * kEpt trial energies per CTA.
@@ -238,7 +249,7 @@ struct SegOut {
 };
 
 template <int kEpt, int kWarps, int kStride, bool kTails, bool kScan, int kForm>
-__global__ void __launch_bounds__((kWarps + 1) * 32, (kEpt * kWarps >= 32) ? 1 : 2)
+__global__ void __launch_bounds__((kWarps + 1) * 32, sweep_min_ctas<kEpt, kWarps>())
 numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ curves,
                      const Job* __restrict__ jobs, const uint32_t chunks_per_job,
                      const double* __restrict__ Eexp, const uint64_t out_stride,
@@ -250,11 +261,12 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     static_assert(!kScan || (kEpt == 2 && !kTails), "scan mode: two basis chains per energy");
     constexpr uint32_t kPerCta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
     constexpr int      kCnt    = kScan ? 1 : kEpt;  // chains whose sign flips are counted
+    constexpr int      kSt     = sweep_stages<kEpt, kWarps>();  // ring depth of this shape
     if (*stop_flag != 0) return;  // eps_request_stop: queued sweeps drain without marching (uniform per CTA)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double*   ring  = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kStages);
-    uint64_t* empty = full + kStages;
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kTile * kSt);
+    uint64_t* empty = full + kSt;
 
     const uint32_t seg     = kScan ? blockIdx.x % n_seg : 0u;
     const uint32_t cta     = kScan ? blockIdx.x / n_seg : blockIdx.x;
@@ -289,7 +301,7 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < kSt; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kWarps);
         }
@@ -302,8 +314,8 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
         if (lane == 0) {
             const double* src = F + cv.f_off;
             for (uint32_t t = 0; t < n_tiles; t++) {
-                const uint32_t s = t % kStages;
-                if (t >= kStages) mbar_wait_backoff(&empty[s], ((t / kStages) - 1) & 1);
+                const uint32_t s = t % kSt;
+                if (t >= kSt) mbar_wait_backoff(&empty[s], ((t / kSt) - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], kTile * sizeof(double));
                 tma_bulk_g2s(ring + s * kTile, src + static_cast<uint64_t>(t_begin + t) * kTile,
                              kTile * sizeof(double), &full[s]);
@@ -348,8 +360,8 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     }
 
     for (uint32_t t = 0; t < n_tiles; t++) {
-        const uint32_t s = t % kStages;
-        mbar_wait(&full[s], (t / kStages) & 1);
+        const uint32_t s = t % kSt;
+        mbar_wait(&full[s], (t / kSt) & 1);
         const double* __restrict__ tile = ring + s * kTile;
         const uint32_t n_valid = min(static_cast<uint32_t>(kTile), n_steps - (t_begin + t) * kTile);
         const uint32_t n_full  = n_valid / kRenorm;

@@ -243,6 +243,10 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  * EPS_OPT_PREP_PARTS: eps_set_potentials* prepares few long curves (<= 64 curves of >= 65 536
  *   points) with every curve cut into chunks over many CTAs; 0 = automatic, 1 = never (one CTA
  *   per curve).  Identical results.
+ * EPS_OPT_PACK128: refinement rounds of many-curve batches with <= 64 points per level pack their rows
+ *   into 128-energy CTAs (four resident per SM) instead of 256-energy ones when that balances the
+ *   SMs better (a small per-device batch, e.g. 512 curves: 3.46 CTAs per SM); 0 = automatic,
+ *   1 = always, 2 = never.  Identical results.
  * EPS_OPT_FORM: the recurrence every later eps_set_potentials* prepares its tables for, and every
  *   sweep on them then runs.  0 (default) = X form: 4 FP64 operations per
  *   grid step, eigenvalue rounding-noise floor ~1e-9 relative at 2e5 grid points and ~2e-8 at 1e6.
@@ -251,7 +255,7 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   (tests/test_accuracy_floor.py).  Node counts and levels of each form are bit-identical to the
  *   oracle's same form; the two forms agree with each other to the X form's noise floor. */
 enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5,
-       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7 };
+       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7, EPS_OPT_PACK128 = 8 };
 enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2, EPS_CNT_CBANK_LAUNCHES = 3 };
 int eps_set_option(eps_ctx* ctx, int option, int64_t value);
 int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);

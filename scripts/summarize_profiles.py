@@ -162,11 +162,15 @@ def main() -> None:
     ap.add_argument("--launches", type=Path)
     ap.add_argument("--rep", type=Path)
     ap.add_argument("--copy", type=Path, nargs="*", default=[])
+    ap.add_argument("--out", type=Path, help="write into this directory instead of profiles/ (on the GPU box: gpurun_out/profiles)")
     ap.add_argument("--traffic", help="workload key of profiles/traffic.json to (re)write from --rep, e.g. c2 or c5_dform")
     ap.add_argument("--kernel", default="numerov_sweep_kernel", help="kernel-name substring for --traffic")
     ap.add_argument("--per-step", type=int, default=1, help="kernel launches per bench launch (51 for the c5 chunks)")
     a = ap.parse_args()
-    PROF.mkdir(exist_ok=True)
+    global PROF
+    if a.out:
+        PROF = a.out
+    PROF.mkdir(parents=True, exist_ok=True)
     if a.launches:
         launches_md(a.tag, a.launches)
     if a.rep:

@@ -1,5 +1,6 @@
 """The bench JSON contract (one line per run): keys the driver reads, checked on the committed lines
-of the last GPU runs (profiles/r1_bench_*.json) and on a live `--impl reference` run (CPU only)."""
+of the last GPU runs (profiles/r2_bench_n*.json: the default command at 1 / 2 / 4 / 8 GPUs) and on a
+live `--impl reference` run (CPU only)."""
 import json
 import subprocess
 import sys
@@ -10,7 +11,38 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 BASE = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
         "vs_baseline", "dtype", "data", "config", "e2e"}
-LINES = sorted((ROOT / "profiles").glob("r1_bench_c*.json"))
+LINES = sorted((ROOT / "profiles").glob("r2_bench_n*.json"))
+
+
+def _check_record(d, workload, full=True):
+    if full:
+        assert BASE <= d.keys(), BASE - d.keys()
+        assert d["metric"] == "numerov_grid_steps_x_trial_energies_per_s" and d["unit"] == "steps/s"
+        assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+        assert d["scaling"] == ("strong" if workload in ("c4", "c5") else "weak") and d["warmup"] >= 3
+        assert d["config"]["workload"].startswith(workload) and "model" not in d["config"]
+        c = d["clocks"]
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= c.keys()
+        assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= d["e2e"].keys()
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.001
+    assert d["gpu_launches"] > 0
+    if "roofline" in d:
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= r.keys()
+        assert r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 0.8
+        assert r["flop_per_step"] in (6, 8) and r["fp64_instr_per_step"] in (4, 5)
+        if r["traffic"] is not None:  # a committed capture on the current kernel sources
+            assert r["traffic"] >= 0.9 * r["algorithmic_bytes_per_launch"] or workload == "c5"
+    if "cpu_baseline" in d:
+        assert {"value", "unit", "cores", "kind", "sample"} <= d["cpu_baseline"].keys()
+        assert d["cpu_baseline"]["kind"] == "port"
+        for k in ("levels_bit_identical_to_gpu", "nodes_bit_identical_to_gpu"):
+            if k in d["cpu_baseline"]:
+                assert d["cpu_baseline"][k] is True
+    if "nodes_bit_identical_to_oracle_full_size_sample" in d:
+        assert d["nodes_bit_identical_to_oracle_full_size_sample"] is True
 
 
 @pytest.mark.parametrize("path", LINES, ids=lambda p: p.name)
@@ -18,26 +50,24 @@ def test_committed_bench_lines(path):
     text = path.read_text().strip()
     assert text.count("\n") == 0, "exactly one JSON line"
     d = json.loads(text)
-    assert BASE <= d.keys(), BASE - d.keys()
-    assert d["metric"] == "numerov_grid_steps_x_trial_energies_per_s" and d["unit"] == "steps/s"
-    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["scaling"] in ("weak", "strong") and d["warmup"] >= 3 and d["value"] > 0
-    assert d["config"]["workload"].startswith(path.name.split("_")[2][:2]) and "model" not in d["config"]
-    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= d["e2e"].keys()
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.001
-    assert d["gpu_launches"] > 0
-    r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= r.keys()
-    assert r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.2 < r["frac"] < 0.75
-    c = d["clocks"]
-    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= c.keys()
-    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
-    if "cpu_baseline" in d:
-        assert {"value", "unit", "cores", "kind", "sample"} <= d["cpu_baseline"].keys()
-        assert d["cpu_baseline"]["kind"] == "port"
-        for k in ("levels_bit_identical_to_gpu", "nodes_bit_identical_to_gpu"):
-            if k in d["cpu_baseline"]:
-                assert d["cpu_baseline"][k] is True
+    _check_record(d, "c5")  # headline: the north star's largest energy sweep, energy-range sharded
+    assert "nodes_bit_identical_to_oracle_full_size_sample" in d
+    assert d["measured_peaks"]["fp64_tflops"] > 30
+    subs = d["sub_records"]
+    assert set(subs) == {"c2", "c3", "c4"}  # every other BASELINE config rides in the same line
+    for name, rec in subs.items():
+        _check_record(rec, name)
+        _check_record(rec["accurate_mode"], name, full=False)
+    _check_record(d["accurate_mode"], "c5", full=False)
+    for name in ("c2", "c4"):
+        assert subs[name]["time_to_all_levels_ms"] == subs[name]["ms_per_step"]
+        assert subs[name]["cooley_mode"]["time_to_all_levels_ms"] > 0
+    assert subs["c2"]["cooley_mode"]["max_rel_diff_vs_ksection"] < 1e-12
+    assert subs["c2"]["levels_found"] == 17
+
+
+def test_there_are_committed_lines():
+    assert any(p.name == "r2_bench_n1.json" for p in LINES)
 
 
 def test_reference_arm_line_live():
@@ -56,3 +86,6 @@ def test_reference_arm_line_live():
 
     # the headline of both arms is the north star's largest energy sweep (BASELINE.json configs[4])
     assert d["config"] == bench.workload_config("c5") and d["metric"] == bench.METRIC and d["scaling"] == "strong"
+    committed = ROOT / "profiles" / "r2_bench_n1.json"
+    if committed.exists():
+        assert json.loads(committed.read_text())["config"] == d["config"]
