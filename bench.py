@@ -501,7 +501,8 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     t_wall1 = time.time()
     st = ctx.stats()
     clocks = sampler.window(t_wall0, t_wall1)
-    ms_res = float(np.sum(comm.reduce_vec(ms_rank, "max")))  # per step: max over ranks; summed over the K steps
+    ms_steps = comm.reduce_vec(ms_rank, "max")  # per step: max over ranks
+    ms_res = float(np.sum(ms_steps))            # ... summed over the K steps
     steps_rank = float(st.grid_steps)
     steps_all = float(comm.reduce_vec([steps_rank], "sum")[0])
     value = steps_all / (ms_res * 1e-3)
@@ -544,6 +545,7 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         "e2e": {"value": steps2 / (ms_e2e * 1e-3), "unit": "steps/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(st2.h2d_bytes // steps), "d2h_bytes_per_step": int(st2.d2h_bytes // steps)},
         "gpu_launches": launches,
+        "ms_steps_max_over_ranks": [round(float(x), 4) for x in ms_steps],
         "roofline": {
             "bound": "fp64", "kernel": KERNELS[name] + (", D form" if form else ""),
             "achieved": flop * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
@@ -554,7 +556,8 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
             "fp64_instr_per_step": INSTR_PER_STEP[form], "sweep_launches": int(st.sweep_launches),
             "avg_launch_ms": st.sweep_ms / max(1, st.sweep_launches),
             **kernel_traffic(name if form == 0 else name + "_dform"),
-            "algorithmic_bytes_per_launch": 8 * int(wl.n_steps) * int(ctx.n_curves),
+            # the table once + (c5) one u32 node count per trial energy written to device memory
+            "algorithmic_bytes_per_launch": 8 * int(wl.n_steps) * int(ctx.n_curves) + (4 * int(wl.per) if name == "c5" else 0),
         },
         "clocks": clocks, "recurrence": FORM_NAME[form],
     }
@@ -637,7 +640,10 @@ def main() -> None:
     sampler.start()
     fp64_peak, _ = ctx.fp64_probe()
     head = "c5" if args.workload == "all" else args.workload
-    cpu_s = 0.0 if args.no_cpu_baseline else 10.0
+    # the CPU oracle is timed beside the device on rank 0 at N = 1 only: under torchrun its 16 threads
+    # would share the host cores with the other ranks' launch threads (and stagger the ranks)
+    # (one oracle evaluation per record stays, for the parity flags)
+    cpu_s = 0.0 if args.no_cpu_baseline else (0.001 if comm.world > 1 else 10.0)
     line = measure(head, ctx, comm, sampler, args.steps, args.warmup, fp64_peak, cpu_s)
     if args.workload == "all":
         subs = {}

@@ -109,7 +109,7 @@ struct eps_ctx {
     DevBuf<int32_t>     d_cbexp;
     DevBuf<uint32_t>    d_cbnodes, d_cbprev;
     int64_t             opt_cbank = 0;  // 0 auto (large single-curve sweeps), 1 always when the launch qualifies, 2 never
-    int                 cb_ept = 4, cb_threads = 128, cb_pdl = 1;
+    int                 cb_ept = 4, cb_threads = 128, cb_pdl = 1, cb_group = 4;
     uint64_t            cbank_launches = 0;
 
     // wavefunction scratch
@@ -305,27 +305,42 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     const uint32_t n_steps = ctx->curves[0].n_steps;
     const CbState  st{ctx->d_cbX.p, ctx->d_cbS.p, ctx->d_cbexp.p, ctx->d_cbnodes.p, ctx->d_cbprev.p};
     static thread_local FChunk chunk;  // 31 KiB staging of the by-value parameter
-    for (uint32_t k0 = 0; k0 < n_steps; k0 += kCbChunk) {
-        const uint32_t len = std::min<uint32_t>(kCbChunk, n_steps - k0);
-        std::memcpy(&chunk, ctx->h_F.data() + k0, len * sizeof(double));
-        std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk + 2 - len) * sizeof(double));
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim  = dim3(static_cast<unsigned>(grid));
-        cfg.blockDim = dim3(kThreads);
-        cfg.stream   = ctx->stream;
-        cudaLaunchAttribute attr{};
-        attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs    = &attr;
-        cfg.numAttrs = (ctx->cb_pdl >= 2 || (ctx->cb_pdl == 1 && grid >= 2ull * ctx->sm_count)) ? 1 : 0;
-        const int pdl_late = ctx->cb_pdl > 2 ? ctx->cb_pdl - 2 : 0;  // trigger that many 128-step blocks before the chunk's end
-        cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails, kForm>, chunk, d_jobs,
-                                           static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
-                                           k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, pdl_late, st, out.nodes, kTails ? out.mant : nullptr,
-                                           kTails ? out.expo : nullptr, ctx->d_steps, static_cast<const int*>(ctx->d_stop));
-        if (e != cudaSuccess) return e;
-        ctx->cbank_launches++;
-        ctx->stats.kernel_launches++;
+    // Energy groups.  The per-energy state (X, S, exponent, node count, last sign: 28 B) is written by
+    // every chunk launch and read by the next.  With all 2^24 energies of C5 in every launch that is
+    // 470 MB out and 470 MB in per chunk -- 45 GB of HBM traffic per sweep for 1.6 MB of table.  Running
+    // the chunk launches group by group, a group being as many CTAs as keep its state (and the L2's
+    // other tenants) resident, leaves the state in L2: HBM then sees the table and the node counts.
+    // cb_group = CTAs per group in resident waves of the device (0: one group, the round-1 order).  Default 4
+    // (4736 CTAs, 68 MB of state on a B200): 754.8 ms against 753.8 ms ungrouped on C5, same node counts
+    // (profiles/r2_cbank_group.log); smaller groups pay more launch boundaries (1 wave: +1.9 %).
+    const int  resident_ctas = std::max(1, 2048 / kThreads > 8 ? 8 : 2048 / kThreads);  // 64 regs x 128 threads: 8 per SM
+    uint64_t   group         = grid;
+    if (ctx->cb_group > 0) group = std::min<uint64_t>(grid, static_cast<uint64_t>(ctx->cb_group) * resident_ctas * ctx->sm_count);
+    for (uint64_t g0 = 0; g0 < grid; g0 += group) {
+        const uint64_t g_ctas = std::min<uint64_t>(group, grid - g0);
+        for (uint32_t k0 = 0; k0 < n_steps; k0 += kCbChunk) {
+            const uint32_t len = std::min<uint32_t>(kCbChunk, n_steps - k0);
+            std::memcpy(&chunk, ctx->h_F.data() + k0, len * sizeof(double));
+            std::memset(reinterpret_cast<double*>(&chunk) + len, 0, (kCbChunk + 2 - len) * sizeof(double));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim  = dim3(static_cast<unsigned>(g_ctas));
+            cfg.blockDim = dim3(kThreads);
+            cfg.stream   = ctx->stream;
+            cudaLaunchAttribute attr{};
+            attr.id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr.val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs    = &attr;
+            cfg.numAttrs = (ctx->cb_pdl >= 2 || (ctx->cb_pdl == 1 && g_ctas >= 2ull * ctx->sm_count)) ? 1 : 0;
+            const int pdl_late = ctx->cb_pdl > 2 ? ctx->cb_pdl - 2 : 0;  // trigger that many 128-step blocks before the chunk's end
+            cudaError_t e = cudaLaunchKernelEx(&cfg, numerov_cbank_kernel<kEpt, kThreads, kStride, kTails, kForm>, chunk, d_jobs,
+                                               static_cast<uint32_t>(chunks), d_Eexp, static_cast<uint64_t>(nE), ctx->curves[0].scale, len,
+                                               k0 == 0 ? 1 : 0, k0 + len >= n_steps ? 1 : 0, pdl_late, static_cast<uint32_t>(g0), st,
+                                               out.nodes, kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps,
+                                               static_cast<const int*>(ctx->d_stop));
+            if (e != cudaSuccess) return e;
+            ctx->cbank_launches++;
+            ctx->stats.kernel_launches++;
+        }
     }
     return cudaSuccess;
 }
@@ -1305,6 +1320,9 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
             return EPS_OK;
         case EPS_OPT_CBANK_PDL:
             ctx->cb_pdl = value < 0 ? 0 : value > 18 ? 18 : static_cast<int>(value);
+            return EPS_OK;
+        case EPS_OPT_CBANK_GROUP:
+            ctx->cb_group = value < 0 ? 0 : value > 4096 ? 4096 : static_cast<int>(value);
             return EPS_OK;
         case EPS_OPT_CBANK_SHAPE:  // tuning: energies per thread * 1000 + threads per CTA
             EPS_REQUIRE(ctx, (value / 1000 == 2 || value / 1000 == 4) && (value % 1000 == 128 || value % 1000 == 256), EPS_ERR_INVALID,

@@ -35,7 +35,10 @@ struct CbState {  // per-energy carry between chunk launches, [row * out_stride 
     uint32_t* prev;
 };
 
-// grid = n_jobs * chunks_per_job CTAs of kThreads threads, kEpt energies per thread.
+// grid = n_jobs * chunks_per_job CTAs of kThreads threads, kEpt energies per thread -- or a GROUP of
+// them (cta_base .. cta_base + gridDim.x): the host may run all chunk launches of one group of
+// energies before the next group's, so that the group's carried state (28 B per energy) stays in L2
+// between launches instead of making a round trip through HBM per chunk (launch_cbank_variant).
 //   len    steps of this chunk (multiple of 128 except for the curve's last chunk)
 //   first  != 0: initialise the state instead of loading it;  last != 0: emit results.
 template <int kEpt, int kThreads, int kStride, bool kTails, int kForm>
@@ -43,7 +46,8 @@ __global__ void __launch_bounds__(kThreads)
 numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ jobs,
                      const uint32_t chunks_per_job, const double* __restrict__ Eexp,
                      const uint64_t out_stride, const double scale, const uint32_t len, const int first,
-                     const int last, const int pdl_late, const CbState st, uint32_t* __restrict__ nodes_out,
+                     const int last, const int pdl_late, const uint32_t cta_base, const CbState st,
+                     uint32_t* __restrict__ nodes_out,
                      double* __restrict__ mant_out, int32_t* __restrict__ exp_out,
                      unsigned long long* __restrict__ steps_done, const int* __restrict__ stop_flag) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
@@ -59,8 +63,9 @@ numerov_cbank_kernel(const __grid_constant__ FChunk P, const Job* __restrict__ j
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (pdl_late == 0) asm volatile("griddepcontrol.launch_dependents;");
     if (*stop_flag != 0) return;  // eps_request_stop: the remaining chunk launches of the sweep drain at once
-    const uint32_t job_idx = blockIdx.x / chunks_per_job;
-    const uint32_t chunk   = blockIdx.x - job_idx * chunks_per_job;
+    const uint32_t cta     = cta_base + blockIdx.x;  // the launch covers CTAs [cta_base, cta_base + gridDim.x) of the sweep
+    const uint32_t job_idx = cta / chunks_per_job;
+    const uint32_t chunk   = cta - job_idx * chunks_per_job;
     const Job      job     = jobs[job_idx];
     const uint32_t e_base  = chunk * kPerCta;
     if (e_base >= job.nE) return;

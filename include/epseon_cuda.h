@@ -240,6 +240,11 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   kernel-parameter constant bank (uniform-register operand, chunked launches) instead of the
  *   TMA / shared-memory ring; identical results.  0 = automatic (large sweeps), 1 = whenever
  *   the launch qualifies, 2 = never.  EPS_OPT_CBANK_SHAPE, EPS_OPT_CBANK_PDL: tuning knobs.
+ * EPS_OPT_CBANK_GROUP: the constant-bank sweep carries 28 B of state per energy from chunk launch to
+ *   chunk launch.  n > 0 runs all chunk launches of one group of n resident waves of CTAs before
+ *   the next group's, so that the group's state stays in L2 instead of crossing HBM once per chunk;
+ *   0 = one group (every launch covers all energies); default 4 (68 MB of state on a B200).
+ *   Identical results.
  * EPS_OPT_PREP_PARTS: eps_set_potentials* prepares few long curves (<= 64 curves of >= 65 536
  *   points) with every curve cut into chunks over many CTAs; 0 = automatic, 1 = never (one CTA
  *   per curve).  Identical results.
@@ -255,7 +260,7 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   (tests/test_accuracy_floor.py).  Node counts and levels of each form are bit-identical to the
  *   oracle's same form; the two forms agree with each other to the X form's noise floor. */
 enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5,
-       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7, EPS_OPT_PACK128 = 8 };
+       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7, EPS_OPT_PACK128 = 8, EPS_OPT_CBANK_GROUP = 9 };
 enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2, EPS_CNT_CBANK_LAUNCHES = 3 };
 int eps_set_option(eps_ctx* ctx, int option, int64_t value);
 int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);

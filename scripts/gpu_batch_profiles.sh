@@ -9,18 +9,18 @@ mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()"
 python bench.py > $O/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
 python bench.py --impl reference > $O/r2_bench_ref.json 2>> gpurun_out/r2_bench_n1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file /tmp/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_bench_all.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file /tmp/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_bench_all.log 2>&1
 python scripts/summarize_profiles.py r2_default --out $O --launches /tmp/r2_launches.csv
 cp profiles/traffic.json $O/traffic.json 2>/dev/null
-while read -r w f pat key per; do
-  ncu --set full --clock-control none --import-source on -k "regex:$pat" -c 4 -o /tmp/r2_${w}_f$f python scripts/ncu_target.py $w $f 1 > gpurun_out/r2_ncu_${w}_f$f.log 2>&1
+while read -r w f pat key per skip; do
+  ncu --set full --clock-control none --import-source on -k "regex:$pat" --launch-skip ${skip:-0} -c 4 -o /tmp/r2_${w}_f$f python scripts/ncu_target.py $w $f 1 > gpurun_out/r2_ncu_${w}_f$f.log 2>&1
   python scripts/summarize_profiles.py r2_${w}_f$f --out $O --rep /tmp/r2_${w}_f$f.ncu-rep --traffic $key --kernel ${pat%%|*} --per-step $per
   rm -f /tmp/r2_${w}_f$f.ncu-rep
 done <<SPECS
 c2 0 numerov_sweep c2 1
 c2 1 numerov_sweep c2_dform 1
-c5 0 numerov_cbank c5 51
-c5 1 numerov_cbank c5_dform 51
+c5 0 numerov_cbank c5 357 10
+c5 1 numerov_cbank c5_dform 357 10
 c3 0 numerov_sweep|segment_combine c3 1
 c3 1 numerov_sweep|segment_combine c3_dform 1
 c4 0 numerov_sweep c4 1

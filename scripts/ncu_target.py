@@ -4,7 +4,7 @@
 
 c2: 65 536-energy coarse sweep + refinement of 17 levels (TMA ring kernel, flat rows);
 c3: 4096 energies x 1M grid (scan path); c4: 4096 curves x (1024 coarse + packed refinement rows);
-c5: 2^22 energies x 200k grid (constant-bank kernel; a quarter of C5, same CTA count per SM wave);
+c5: 2^24 energies x 200k grid (constant-bank kernel, energy groups);
 cooley: C2 and a 512-curve batch through EPS_SOLVE_COOLEY.  form = 0 (X form) / 1 (D form).
 """
 import sys
@@ -38,10 +38,11 @@ elif which == "c4":
     for _ in range(reps):
         ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, 7, 32, 1e-10, 8)
 elif which == "c5":
-    w = W.c5(nE=1 << 22)
+    w = W.c5()  # the full 2^24 energies: the carried state's path through L2 / HBM depends on the size
     ctx.set_potentials(w["V"], w["s"])
     for _ in range(reps):
-        ctx.sweep_uniform(w["E_lo"], w["E_hi"], 1 << 22, nodes=False, tails=False)
+        ctx.sweep_uniform(w["E_lo"], w["E_hi"], 1 << 24, nodes=False, tails=False)
+    print("cbank launches per sweep", ctx.counter(ctx.CNT_CBANK_LAUNCHES) // reps)
 elif which == "cooley":
     ctx.set_option(ctx.OPT_FORM, 1)
     w = W.c2()
