@@ -311,7 +311,7 @@ class Context:
         return out
 
     OPT_SCAN_SEGMENTS, OPT_SCAN_EXACT, OPT_CBANK, OPT_CBANK_SHAPE, OPT_CBANK_PDL, OPT_PREP_PARTS, OPT_FORM, OPT_PACK128 = 1, 2, 3, 4, 5, 6, 7, 8
-    OPT_CBANK_GROUP = 9
+    OPT_CBANK_GROUP, OPT_SCAN_COMBINE = 9, 10
     CNT_SCAN_LAUNCHES, CNT_SCAN_FLAGGED, CNT_CBANK_LAUNCHES = 1, 2, 3
 
     def set_option(self, option: int, value: int) -> None:

@@ -101,6 +101,7 @@ struct eps_ctx {
     uint32_t         n_tiles_max  = 0;   // over the resident curves
     int64_t          opt_scan_segments = 0;  // 0 auto, 1 never, >= 2 forced segment count
     int64_t          opt_scan_exact    = 1;  // 1: eps_solve_levels also recomputes flagged energies sequentially
+    int              opt_scan_combine  = 0;  // 0 auto (prefix from kScanPrefixMin segments), 1 serial loop, 2 prefix always
     uint64_t         scan_launches = 0, scan_flagged = 0;
 
     // constant-bank sweep: host copy of the (single) curve's table + per-energy carry
@@ -400,7 +401,9 @@ bool use_cbank(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, uint32_t pack_r
 // run per SM.  The scan path executes 7 instead of 4 FP64 instructions per (energy, step) and
 // gains n_seg-fold parallelism.  Returns 1 for "sequential".
 constexpr uint32_t kScanMinTiles = 32;   // auto mode: grids of >= 65 536 steps only
-constexpr uint32_t kScanMaxSeg   = 64;
+constexpr uint32_t kScanMaxSeg   = 512;  // (64 while the combine was a serial loop only)
+constexpr uint32_t kScanPrefixMin = 8;   // segments from which the combine runs as a block-level prefix
+constexpr int      kScanLanes     = 16;  // segment lanes of segment_prefix_kernel
 uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool tails) {  // n_jobs: rows that carry energies
     const uint32_t n_tiles = ctx->n_tiles_max;
     if (ctx->opt_scan_segments == 1 || n_tiles < 2) return 1;
@@ -409,9 +412,28 @@ uint32_t pick_segments(const eps_ctx* ctx, uint32_t n_jobs, uint32_t nE, bool ta
     if (tails || n_tiles < kScanMinTiles) return 1;  // tails: only the sequential march reproduces the oracle's bits
     const uint64_t e_tot = static_cast<uint64_t>(n_jobs) * nE;
     if ((e_tot + 511) / 512 >= static_cast<uint64_t>(ctx->sm_count) / 2) return 1;
+    // Segment length t (whole tiles): the launch runs ceil(n_seg * ctas256 / slots) waves of t tiles on
+    // the 2 * SM-count resident 256-energy CTAs; a wave costs t tile-times plus a small fixed part
+    // (CTA prologue, measured ~0.03 tile).  One tile per segment often wins on granularity: C3's 489
+    // tiles x 16 CTAs are 26.4 -> 27 tile-times, 18 segments of 28 tiles are 28 (1.834 against 1.899 ms,
+    // profiles/r2_scan_few.log).  Ties go to the longer segment (less scratch, a shorter combine).
     const uint64_t ctas256 = static_cast<uint64_t>(n_jobs) * ((nE + 255) / 256);
-    const uint64_t s       = std::min<uint64_t>({2ull * ctx->sm_count / ctas256, n_tiles, kScanMaxSeg});
-    return s >= 3 ? static_cast<uint32_t>(s) : 1u;
+    const uint64_t slots   = 2ull * ctx->sm_count;
+    const uint64_t cap_mem = std::max<uint64_t>(3, (1ull << 30) / (44ull * std::max<uint64_t>(1, static_cast<uint64_t>(n_jobs) * nE)));
+    double   best_cost = 0.0;
+    uint32_t best_seg  = 1;
+    for (uint32_t t = 1; t <= n_tiles; t++) {
+        const uint64_t n_seg = (n_tiles + t - 1) / t;
+        if (n_seg < 3) break;
+        if (n_seg > kScanMaxSeg || n_seg > cap_mem) continue;
+        const uint64_t waves = (n_seg * ctas256 + slots - 1) / slots;
+        const double   cost  = static_cast<double>(waves) * (static_cast<double>(t) + 0.03);
+        if (best_seg == 1 || cost <= best_cost) {
+            best_cost = cost;
+            best_seg  = static_cast<uint32_t>(n_seg);
+        }
+    }
+    return best_seg;
 }
 
 int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp, bool tails,
@@ -440,9 +462,16 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
                    : launch_sweep_variant<2, 8, 1, false, true, 0>(ctx, d_jobs, n_jobs, nE, d_Eexp, out, n_seg, tiles_per_seg, so);
     EPS_CUDA(ctx, e);
     EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_nflag.p, 0, sizeof(uint32_t), ctx->stream));
-    segment_combine_kernel<<<dim3(n_jobs, (nE + 127) / 128), 128, 0, ctx->stream>>>(
-        so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
-        ctx->d_nflag.p, ctx->d_flagged.p, cap, dform ? 1.0 : -1.0);
+    // the chain of segment matrices: a serial loop per energy for a handful of segments, the block-level
+    // parallel prefix (16 segment lanes x 32 energies per CTA) from kScanPrefixMin segments on
+    if ((n_seg >= kScanPrefixMin || ctx->opt_scan_combine == 2) && ctx->opt_scan_combine != 1 && (nE + 31) / 32 <= 65535u)
+        segment_prefix_kernel<kScanLanes><<<dim3(n_jobs, (nE + 31) / 32), dim3(32, kScanLanes), 0, ctx->stream>>>(
+            so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
+            ctx->d_nflag.p, ctx->d_flagged.p, cap, dform ? 1.0 : -1.0);
+    else
+        segment_combine_kernel<<<dim3(n_jobs, (nE + 127) / 128), 128, 0, ctx->stream>>>(
+            so, d_jobs, n_jobs, n_seg, nE, out.nodes, tails ? out.mant : nullptr, tails ? out.expo : nullptr,
+            ctx->d_nflag.p, ctx->d_flagged.p, cap, dform ? 1.0 : -1.0);
     EPS_CUDA(ctx, cudaGetLastError());
     ctx->stats.other_launches++;
     ctx->scan_launches++;
@@ -1320,6 +1349,10 @@ int eps_set_option(eps_ctx* ctx, int option, int64_t value) {
             return EPS_OK;
         case EPS_OPT_CBANK_PDL:
             ctx->cb_pdl = value < 0 ? 0 : value > 18 ? 18 : static_cast<int>(value);
+            return EPS_OK;
+        case EPS_OPT_SCAN_COMBINE:
+            EPS_REQUIRE(ctx, value >= 0 && value <= 2, EPS_ERR_INVALID, "scan combine: 0 auto, 1 serial, 2 prefix");
+            ctx->opt_scan_combine = static_cast<int>(value);
             return EPS_OK;
         case EPS_OPT_CBANK_GROUP:
             ctx->cb_group = value < 0 ? 0 : value > 4096 ? 4096 : static_cast<int>(value);

@@ -498,6 +498,70 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
 // One thread per (row, energy); segments are a serial loop of n_seg 2x2 mat-vecs (n_seg <= 64:
 // a parallel prefix would save nothing next to the n_steps/n_seg marches it follows).
 // ---------------------------------------------------------------------------
+// State of one trial energy between segments: v = (X, D) 2^ex, the running node count and the guard.
+struct CombState {
+    double   X, D, rho;
+    int      ex;
+    uint32_t nodes;
+};
+
+// One segment applied to the state (the body both combine kernels share; operation order fixed).
+__device__ __forceinline__ void combine_segment(CombState& st, const SegOut& so, const uint64_t o, const bool last_seg,
+                                                const double D_start) {
+    constexpr double kEta = 5.820766091346741e-11;  // 2^-34
+    const double   XA = so.XA[o], DA = so.SA[o];
+    int            sh = so.eB[o] - so.eA[o];
+    sh                = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+    const double XB = scalbn(so.XB[o], sh), DB = scalbn(so.SB[o], sh);
+    const double X = st.X, D = st.D;
+    const double pX = __dmul_rn(XB, D), pD = __dmul_rn(DB, D);
+    const double Xn = __fma_rn(XA, X, pX);
+    const double Dn = __fma_rn(DA, X, pD);
+    const int    fa = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
+    const int    fb = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
+                                        static_cast<uint32_t>(__double2hiint(XA))) >> 31);
+    // orientation: the sign of the discrete Wronskian of (A, v).  In the X form's coordinates D is
+    // MINUS the backward difference (D = S - X), in the D form's it is PLUS (D = Y_k - f Y_{k-1}),
+    // so the two forms need opposite signs; D_start = -1 / +1 carries exactly that.
+    const int    sg0 = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
+    const int    sg  = D_start < 0.0 ? sg0 : -sg0;
+    st.nodes += so.nA[o] + static_cast<uint32_t>(sg * (fb - fa));
+    const double magX = fabs(__dmul_rn(XA, X)) + fabs(pX), magD = fabs(__dmul_rn(DA, X)) + fabs(pD);
+    const double cX = magX > 0.0 ? fabs(Xn) / magX : 1.0, cD = magD > 0.0 ? fabs(Dn) / magD : 1.0;
+    const double c  = last_seg ? cX : fmax(cX, cD);
+    st.rho          = (st.rho + kEta) / c;  // c == 0 -> inf -> flagged
+    st.X            = Xn;
+    st.D            = Dn;
+    st.ex += so.eA[o];
+    uint32_t e11 = (static_cast<uint32_t>(__double2hiint(st.X)) >> 20) & 0x7ffu;
+    if (e11 == 0) e11 = (static_cast<uint32_t>(__double2hiint(st.D)) >> 20) & 0x7ffu;
+    if (e11 != 0 && !last_seg) {
+        const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
+        st.X = __dmul_rn(st.X, sc);
+        st.D = __dmul_rn(st.D, sc);
+        st.ex += static_cast<int>(e11) - 1023;
+    }
+}
+
+// Result of one energy: node count, tail in the sweep's (mantissa in [1,2), exponent) form, flag.
+__device__ __forceinline__ void combine_emit(CombState st, const uint64_t o, uint32_t* __restrict__ nodes_out,
+                                             double* __restrict__ mant_out, int32_t* __restrict__ exp_out,
+                                             uint32_t* __restrict__ n_flagged, uint2* __restrict__ flagged,
+                                             const uint32_t flagged_cap, const uint32_t row, const uint32_t j) {
+    const uint32_t e11 = (static_cast<uint32_t>(__double2hiint(st.X)) >> 20) & 0x7ffu;
+    if (e11 != 0) {
+        st.X = __dmul_rn(st.X, __hiloint2double(static_cast<int>((2046u - e11) << 20), 0));
+        st.ex += static_cast<int>(e11) - 1023;
+    }
+    nodes_out[o] = st.nodes;
+    if (mant_out) mant_out[o] = st.X;
+    if (exp_out) exp_out[o] = st.ex;
+    if (!(st.rho < 9.765625e-4)) {
+        const uint32_t pos = atomicAdd(n_flagged, 1u);
+        if (pos < flagged_cap) flagged[pos] = make_uint2(row, j);
+    }
+}
+
 __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ jobs, uint32_t n_jobs,
                                        uint32_t n_seg, uint64_t out_stride,
                                        uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
@@ -506,58 +570,149 @@ __global__ void segment_combine_kernel(const SegOut so, const Job* __restrict__ 
     const uint32_t row = blockIdx.x;  // rows on grid.x (up to 2^31 - 1 of them), energy blocks on grid.y
     const uint32_t j   = blockIdx.y * blockDim.x + threadIdx.x;
     if (row >= n_jobs || j >= jobs[row].nE) return;
-    constexpr double kEta = 5.820766091346741e-11;  // 2^-34
-    double   X = 1.0, D = D_start, rho = 0.0;  // start state in (X, D): X form (1, S - X = -1), D form (1, 1)
-    int      ex = 0;
-    uint32_t nodes = 0;
-    for (uint32_t sgm = 0; sgm < n_seg; sgm++) {
-        const uint64_t o  = (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + j;
-        const double   XA = so.XA[o], DA = so.SA[o];
-        int            sh = so.eB[o] - so.eA[o];
-        sh                = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
-        const double XB = scalbn(so.XB[o], sh), DB = scalbn(so.SB[o], sh);
-        const double pX = __dmul_rn(XB, D), pD = __dmul_rn(DB, D);
-        const double Xn = __fma_rn(XA, X, pX);
-        const double Dn = __fma_rn(DA, X, pD);
-        const int    fa = static_cast<int>(static_cast<uint32_t>(__double2hiint(X)) >> 31);
-        const int    fb = static_cast<int>((static_cast<uint32_t>(__double2hiint(Xn)) ^
-                                            static_cast<uint32_t>(__double2hiint(XA))) >> 31);
-        // orientation: the sign of the discrete Wronskian of (A, v).  In the X form's coordinates D is
-        // MINUS the backward difference (D = S - X), in the D form's it is PLUS (D = Y_k - f Y_{k-1}),
-        // so the two forms need opposite signs; D_start = -1 / +1 carries exactly that.
-        const int    sg0 = D > 0.0 ? 1 : (D < 0.0 ? -1 : 0);
-        const int    sg  = D_start < 0.0 ? sg0 : -sg0;
-        nodes += so.nA[o] + static_cast<uint32_t>(sg * (fb - fa));
-        const double magX = fabs(__dmul_rn(XA, X)) + fabs(pX), magD = fabs(__dmul_rn(DA, X)) + fabs(pD);
-        const double cX = magX > 0.0 ? fabs(Xn) / magX : 1.0, cD = magD > 0.0 ? fabs(Dn) / magD : 1.0;
-        const double c  = (sgm + 1 == n_seg) ? cX : fmax(cX, cD);
-        rho             = (rho + kEta) / c;  // c == 0 -> inf -> flagged
-        X               = Xn;
-        D               = Dn;
-        ex += so.eA[o];
-        uint32_t e11 = (static_cast<uint32_t>(__double2hiint(X)) >> 20) & 0x7ffu;
-        if (e11 == 0) e11 = (static_cast<uint32_t>(__double2hiint(D)) >> 20) & 0x7ffu;
-        if (e11 != 0 && sgm + 1 < n_seg) {
+    CombState st{1.0, D_start, 0.0, 0, 0u};  // start state in (X, D): X form (1, S - X = -1), D form (1, 1)
+    for (uint32_t sgm = 0; sgm < n_seg; sgm++)
+        combine_segment(st, so, (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + j, sgm + 1 == n_seg, D_start);
+    combine_emit(st, static_cast<uint64_t>(row) * out_stride + j, nodes_out, mant_out, exp_out, n_flagged, flagged,
+                 flagged_cap, row, j);
+}
+
+// ---------------------------------------------------------------------------
+// N4 combine as a BLOCK-LEVEL PARALLEL PREFIX over the 2x2 transfer matrices (many segments).
+//   CTA = 32 trial energies (threadIdx.x: coalesced loads) x kLanes segment lanes (threadIdx.y);
+//   lane l owns the m = ceil(n_seg / kLanes) consecutive segments [l m, (l+1) m).
+//   1. every lane multiplies its m matrices (entries with one shared binary exponent);
+//   2. Hillis-Steele inclusive scan of the lane products through shared memory, log2(kLanes)
+//      rounds of one 2x2 product each: Pi_l = M_l ... M_0;
+//   3. lane l enters its segments with v = Pi_{l-1} v_0 and applies them one by one with the very
+//      body of the serial kernel (node corrections, cancellation guard), so the signs that decide
+//      the node count are taken at EVERY segment boundary, not only at lane boundaries;
+//   4. the guard travels across lanes as the affine map rho -> alpha rho + beta of each lane, plus
+//      the MEASURED mismatch between lane l's exit state and the prefix's entry state of lane
+//      l + 1 (relative difference of their D/X ratios): rounding inside the matrix products shows
+//      up there and nowhere else, so no a-priori bound on the tree's error is needed.
+// Node counts are the serial kernel's (integers decided by the same signs; whatever the guard
+// does not vouch for is recomputed by the sequential sweep); tails agree to rounding.
+// ---------------------------------------------------------------------------
+struct Mat2 {
+    double a, b, c, d;  // [[a, b], [c, d]] 2^e acting on (X, D)
+    int    e;
+};
+__device__ __forceinline__ void mat2_renorm(Mat2& m) {
+    const double   mx  = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
+    const uint32_t e11 = (static_cast<uint32_t>(__double2hiint(mx)) >> 20) & 0x7ffu;
+    if (e11 != 0 && e11 != 0x7ffu) {
+        const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
+        m.a *= sc; m.b *= sc; m.c *= sc; m.d *= sc;
+        m.e += static_cast<int>(e11) - 1023;
+    }
+}
+__device__ __forceinline__ Mat2 mat2_mul(const Mat2& L, const Mat2& R) {  // L after R
+    Mat2 m;
+    m.a = fma(L.a, R.a, L.b * R.c);
+    m.b = fma(L.a, R.b, L.b * R.d);
+    m.c = fma(L.c, R.a, L.d * R.c);
+    m.d = fma(L.c, R.b, L.d * R.d);
+    m.e = L.e + R.e;
+    mat2_renorm(m);
+    return m;
+}
+__device__ __forceinline__ Mat2 mat2_load(const SegOut& so, const uint64_t o) {
+    int sh = so.eB[o] - so.eA[o];
+    sh     = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+    Mat2 m{so.XA[o], scalbn(so.XB[o], sh), so.SA[o], scalbn(so.SB[o], sh), so.eA[o]};
+    return m;
+}
+
+template <int kLanes>
+__global__ void __launch_bounds__(32 * kLanes)
+segment_prefix_kernel(const SegOut so, const Job* __restrict__ jobs, uint32_t n_jobs, uint32_t n_seg,
+                      uint64_t out_stride, uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
+                      int32_t* __restrict__ exp_out, uint32_t* __restrict__ n_flagged, uint2* __restrict__ flagged,
+                      uint32_t flagged_cap, const double D_start) {
+    __shared__ double sh_m[4][kLanes][32];
+    __shared__ int    sh_e[kLanes][32];
+    __shared__ double sh_v[2][kLanes][32];       // exit state of every lane (X, D), normalised
+    __shared__ double sh_g[3][kLanes][32];       // alpha, beta, mismatch
+    __shared__ int    sh_x[kLanes][32];          // exit exponent
+    __shared__ uint32_t sh_n[kLanes][32];
+    const uint32_t row = blockIdx.x;
+    const uint32_t tx = threadIdx.x, l = threadIdx.y;
+    const uint32_t j   = blockIdx.y * 32 + tx;
+    const uint32_t nE  = row < n_jobs ? jobs[row].nE : 0u;
+    const bool     live = j < nE;
+    const uint32_t jj  = live ? j : (nE ? nE - 1 : 0);  // clamp: every thread takes part in the barriers
+    const uint32_t m   = (n_seg + kLanes - 1) / kLanes;
+    const uint32_t s0  = min(l * m, n_seg), s1 = min(s0 + m, n_seg);
+    if (nE == 0) return;  // uniform per CTA
+
+    // 1. product of this lane's segments
+    Mat2 M{1.0, 0.0, 0.0, 1.0, 0};
+    for (uint32_t sgm = s0; sgm < s1; sgm++)
+        M = mat2_mul(mat2_load(so, (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + jj), M);
+    // 2. inclusive scan over the lanes
+#pragma unroll
+    for (int off = 1; off < kLanes; off <<= 1) {
+        sh_m[0][l][tx] = M.a; sh_m[1][l][tx] = M.b; sh_m[2][l][tx] = M.c; sh_m[3][l][tx] = M.d; sh_e[l][tx] = M.e;
+        __syncthreads();
+        if (l >= static_cast<uint32_t>(off)) {
+            const Mat2 R{sh_m[0][l - off][tx], sh_m[1][l - off][tx], sh_m[2][l - off][tx], sh_m[3][l - off][tx], sh_e[l - off][tx]};
+            M = mat2_mul(M, R);
+        }
+        __syncthreads();
+    }
+    sh_m[0][l][tx] = M.a; sh_m[1][l][tx] = M.b; sh_m[2][l][tx] = M.c; sh_m[3][l][tx] = M.d; sh_e[l][tx] = M.e;
+    __syncthreads();
+    // 3. entry state of this lane: Pi_{l-1} (1, D_start); then its own segments, serially
+    CombState st{1.0, D_start, 0.0, 0, 0u};
+    if (l > 0) {
+        st.X  = fma(sh_m[0][l - 1][tx], 1.0, sh_m[1][l - 1][tx] * D_start);
+        st.D  = fma(sh_m[2][l - 1][tx], 1.0, sh_m[3][l - 1][tx] * D_start);
+        st.ex = sh_e[l - 1][tx];
+        uint32_t e11 = (static_cast<uint32_t>(__double2hiint(st.X)) >> 20) & 0x7ffu;
+        if (e11 == 0) e11 = (static_cast<uint32_t>(__double2hiint(st.D)) >> 20) & 0x7ffu;
+        if (e11 != 0 && e11 != 0x7ffu) {
             const double sc = __hiloint2double(static_cast<int>((2046u - e11) << 20), 0);
-            X = __dmul_rn(X, sc);
-            D = __dmul_rn(D, sc);
-            ex += static_cast<int>(e11) - 1023;
+            st.X *= sc;
+            st.D *= sc;
+            st.ex += static_cast<int>(e11) - 1023;
         }
     }
-    {   // tail in the sweep's (mantissa in [1,2), exponent) form
-        const uint32_t e11 = (static_cast<uint32_t>(__double2hiint(X)) >> 20) & 0x7ffu;
-        if (e11 != 0) {
-            X = __dmul_rn(X, __hiloint2double(static_cast<int>((2046u - e11) << 20), 0));
-            ex += static_cast<int>(e11) - 1023;
-        }
+    const double Xin = st.X, Din = st.D;
+    // the guard of this lane as an affine map of the incoming rho: rho_out = alpha rho_in + beta, with
+    // beta = the lane's own run from rho_in = 0 and alpha = prod 1/c (1/c read off rho' = (rho + eta) / c)
+    double alpha = 1.0;
+    for (uint32_t sgm = s0; sgm < s1; sgm++) {
+        const double r0 = st.rho;
+        combine_segment(st, so, (static_cast<uint64_t>(row) * n_seg + sgm) * out_stride + jj, sgm + 1 == n_seg, D_start);
+        alpha *= st.rho / (r0 + 5.820766091346741e-11);
     }
-    const uint64_t o = static_cast<uint64_t>(row) * out_stride + j;
-    nodes_out[o]     = nodes;
-    if (mant_out) mant_out[o] = X;
-    if (exp_out) exp_out[o] = ex;
-    if (!(rho < 9.765625e-4)) {
-        const uint32_t pos = atomicAdd(n_flagged, 1u);
-        if (pos < flagged_cap) flagged[pos] = make_uint2(row, j);
+    sh_v[0][l][tx] = st.X; sh_v[1][l][tx] = st.D; sh_x[l][tx] = st.ex; sh_n[l][tx] = st.nodes;
+    sh_g[0][l][tx] = alpha;
+    sh_g[1][l][tx] = st.rho;  // beta
+    // 4. mismatch between the previous lane's exit state and this lane's entry state (set by lane l for l-1)
+    __syncthreads();
+    double mis = 0.0;
+    if (l > 0 && s0 < n_seg) {
+        const double Xp = sh_v[0][l - 1][tx], Dp = sh_v[1][l - 1][tx];
+        const double u = Xp * Din, w = Dp * Xin;
+        const double den = fmax(fabs(u), fabs(w));
+        mis = den > 0.0 ? fabs(u - w) / den : 1.0;
+    }
+    sh_g[2][l][tx] = mis;
+    __syncthreads();
+    if (l == 0 && live) {
+        double   rho = 0.0;
+        uint32_t nodes = 0;
+        uint32_t last = 0;
+        for (uint32_t q = 0; q < static_cast<uint32_t>(kLanes) && q * m < n_seg; q++) {
+            rho   = sh_g[0][q][tx] * (rho + sh_g[2][q][tx]) + sh_g[1][q][tx];
+            nodes += sh_n[q][tx];
+            last = q;
+        }
+        CombState fin{sh_v[0][last][tx], sh_v[1][last][tx], rho, sh_x[last][tx], nodes};
+        combine_emit(fin, static_cast<uint64_t>(row) * out_stride + j, nodes_out, mant_out, exp_out, n_flagged, flagged,
+                     flagged_cap, row, j);
     }
 }
 

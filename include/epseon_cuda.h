@@ -231,6 +231,11 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   regime: 0 = automatic (default), 1 = never, n >= 2 = always cut the grid into n segments.
  *   On the scan path node counts equal the sequential march's (energies whose result is
  *   ill-conditioned are detected and recomputed sequentially); tails agree to rounding.
+ *   Up to 512 segments of whole 2048-step tiles.
+ * EPS_OPT_SCAN_COMBINE: how the segment transfer matrices of an energy are chained.  0 = automatic:
+ *   a serial loop per energy below 8 segments, from 8 on a block-level parallel prefix over the
+ *   2x2 matrices (16 segment lanes x 32 energies per CTA, Hillis-Steele in shared memory); 1 = serial
+ *   loop always, 2 = prefix always.  Same node counts; tails agree to rounding.
  * EPS_OPT_SCAN_EXACT: 1 (default) = eps_solve_levels also recomputes flagged energies
  *   sequentially, so levels carry the sequential march's bits (late refinement rounds, whose
  *   energies all crowd an eigenvalue, then run at sequential speed); 0 = it does not: faster,
@@ -260,7 +265,8 @@ int eps_solve_levels_grid(eps_ctx* ctx, const eps_solve_params* p, const double*
  *   (tests/test_accuracy_floor.py).  Node counts and levels of each form are bit-identical to the
  *   oracle's same form; the two forms agree with each other to the X form's noise floor. */
 enum { EPS_OPT_SCAN_SEGMENTS = 1, EPS_OPT_SCAN_EXACT = 2, EPS_OPT_CBANK = 3, EPS_OPT_CBANK_SHAPE = 4, EPS_OPT_CBANK_PDL = 5,
-       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7, EPS_OPT_PACK128 = 8, EPS_OPT_CBANK_GROUP = 9 };
+       EPS_OPT_PREP_PARTS = 6, EPS_OPT_FORM = 7, EPS_OPT_PACK128 = 8, EPS_OPT_CBANK_GROUP = 9,
+       EPS_OPT_SCAN_COMBINE = 10 };
 enum { EPS_CNT_SCAN_LAUNCHES = 1, EPS_CNT_SCAN_FLAGGED = 2, EPS_CNT_CBANK_LAUNCHES = 3 };
 int eps_set_option(eps_ctx* ctx, int option, int64_t value);
 int eps_get_counter(eps_ctx* ctx, int counter, uint64_t* value);

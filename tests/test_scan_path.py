@@ -32,11 +32,13 @@ def _tail_ratio(m_g, x_g, m_o, x_o):
     return (m_g / m_o) * np.exp2((x_g - x_o).astype(np.float64))
 
 
+@pytest.mark.parametrize("combine", [1, 2], ids=["serial", "prefix"])
 @pytest.mark.parametrize("n_seg", [2, 3, 5])
-def test_forced_scan_c1(oracle, scan_ctx, n_seg):
+def test_forced_scan_c1(oracle, scan_ctx, n_seg, combine):
     w = W.c1()
     scan_ctx.set_potentials(w["V"], w["s"])
     scan_ctx.set_option(scan_ctx.OPT_SCAN_SEGMENTS, n_seg)
+    scan_ctx.set_option(scan_ctx.OPT_SCAN_COMBINE, combine)
     F, *_ = oracle.prep(w["V"], w["s"])
     E = np.linspace(w["E_lo"], w["E_hi"], 1500)
     n_g, m_g, x_g = scan_ctx.sweep(E)
@@ -48,15 +50,17 @@ def test_forced_scan_c1(oracle, scan_ctx, n_seg):
     assert np.median(np.abs(r - 1.0)) < 1e-10 and np.abs(r - 1.0).max() < 1e-5
 
 
+@pytest.mark.parametrize("combine", [1, 2], ids=["serial", "prefix"])
 @pytest.mark.parametrize("N", [2300, 4097, 6200, 16500])
 @pytest.mark.parametrize("n_seg,nE", [(2, 31), (4, 257), (64, 700)])
-def test_forced_scan_ragged(oracle, scan_ctx, N, n_seg, nE):
+def test_forced_scan_ragged(oracle, scan_ctx, N, n_seg, nE, combine):
     """Segment counts above the tile count (clamped), ragged last tiles, ragged energy rows."""
     rng = np.random.default_rng(N + n_seg)
     V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, N)
     s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, N))
     scan_ctx.set_potentials(V, s)
     scan_ctx.set_option(scan_ctx.OPT_SCAN_SEGMENTS, n_seg)
+    scan_ctx.set_option(scan_ctx.OPT_SCAN_COMBINE, combine)
     F, *_ = oracle.prep(V, s)
     E = np.sort(rng.uniform(V.min(), min(V[-1], V.min() + 0.45 / s), nE))
     n_g, _, _ = scan_ctx.sweep(E, tails=False)
@@ -151,3 +155,47 @@ def test_c3_reduced_tabulated_curve(oracle, scan_ctx):
     n_o, _, _ = oracle.sweep_uniform(F, w["s"], w["E_lo"], dE, 0, w["nE"], tails=False)
     assert np.array_equal(n_g[0], n_o)
     assert n_o[-1] > n_o[0]
+
+
+@pytest.mark.parametrize("n_seg", [8, 18, 37, 73])
+def test_prefix_combine_many_segments(oracle, scan_ctx, n_seg):
+    """The block-level parallel prefix over the 2x2 segment matrices (EPS_OPT_SCAN_COMBINE): node counts
+    of the sequential oracle bit for bit, the same counts and (to rounding) tails as the serial combine,
+    for segment counts that give the 16 lanes 1 .. 5 segments each (73 = one 2048-step tile per segment)."""
+    N, nE = 150_000, 777
+    V = W.morse(W.H2["De"], W.H2["re"], W.H2["a"], 0.2, 12.0, N)
+    s = W.scale(W.H2["m0"], W.H2["m1"], W.grid_h(0.2, 12.0, N))
+    scan_ctx.set_potentials(V, s)
+    scan_ctx.set_option(scan_ctx.OPT_SCAN_SEGMENTS, n_seg)
+    F, *_ = oracle.prep(V, s)
+    rng = np.random.default_rng(n_seg)
+    E = np.sort(rng.uniform(0.0, W.H2["De"] - 1.0, nE))
+    n_o, m_o, x_o = oracle.sweep(F, s, E)
+    out = {}
+    for combine in (1, 2):
+        scan_ctx.set_option(scan_ctx.OPT_SCAN_COMBINE, combine)
+        before = scan_ctx.counter(scan_ctx.CNT_SCAN_LAUNCHES)
+        out[combine] = scan_ctx.sweep(E)
+        assert scan_ctx.counter(scan_ctx.CNT_SCAN_LAUNCHES) == before + 1
+        assert np.array_equal(out[combine][0][0], n_o)
+        r = _tail_ratio(out[combine][1][0], out[combine][2][0], m_o, x_o)
+        assert np.median(np.abs(r - 1.0)) < 1e-9 and np.abs(r - 1.0).max() < 1e-4
+    r12 = _tail_ratio(out[1][1][0], out[1][2][0], out[2][1][0], out[2][2][0])
+    assert np.median(np.abs(r12 - 1.0)) < 1e-11
+
+
+def test_few_energies_long_grid_uses_many_segments(oracle, scan_ctx):
+    """256 energies on a 300k grid: the automatic policy cuts the grid into one segment per tile (146,
+    the serial combine stopped at 64) and chains them with the prefix kernel; energies placed ON
+    eigenvalues are flagged and recomputed, so the counts are the oracle's."""
+    N, nE = 300_000, 256
+    V = W.morse(W.H2["De"], W.H2["re"], W.H2["a"], 0.2, 12.0, N)
+    s = W.scale(W.H2["m0"], W.H2["m1"], W.grid_h(0.2, 12.0, N))
+    scan_ctx.set_potentials(V, s)
+    F, *_ = oracle.prep(V, s)
+    lev, wid, *_ = oracle.solve_levels(F, s, 0.0, W.H2["De"] - 1.0, 1024, 0, 16, 96, 1e-15, 14)
+    E = np.sort(np.concatenate([lev, np.linspace(50.0, W.H2["De"] - 2.0, nE - lev.size)]))
+    n_g, _, _ = scan_ctx.sweep(E, tails=False)
+    assert scan_ctx.counter(scan_ctx.CNT_SCAN_LAUNCHES) == 1
+    n_o, _, _ = oracle.sweep(F, s, E, tails=False)
+    assert np.array_equal(n_g[0], n_o)
