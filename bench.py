@@ -63,15 +63,18 @@ FORM_NAME = {0: "X form (4 FP64 operations per step; eigenvalue noise floor 1e-9
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 lanes/SM at the 1965 MHz max clock
 SUB_STEPS = 10  # timed steps of a sub-record (min with --steps)
 
-C2 = dict(N=100_000, n_coarse=65_536, refine_points=4457, rel_tol=1e-10, max_rounds=8, v_max=16)
+# refinement points per level per round: k-section needs M / log2(M + 1) sweeps-worth of energies per bit,
+# and a round of few energies is latency-bound -- C2: 17 levels x 2228 points = one 256-energy CTA (2 chains
+# per thread) per SM, two rounds; C4: 8 levels x 16 points = one 128-energy CTA per curve (profiles/r2_refine_points.log)
+C2 = dict(N=100_000, n_coarse=65_536, refine_points=2228, rel_tol=1e-10, max_rounds=8, v_max=16)
 C3 = dict(N=1_000_000, nE=4096)
-C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=32, rel_tol=1e-10, max_rounds=8, v_max=7)
+C4 = dict(nC=4096, N=10_000, n_coarse=1024, refine_points=16, rel_tol=1e-10, max_rounds=12, v_max=7)
 C5 = dict(N=200_000, nE=1 << 24, check_sample=4096)
 
 KERNELS = {
-    "c2": "eps::numerov_sweep_kernel<EPT=4,WARPS=4,STRIDE=32> (TMA ring, flat refinement rows)",
+    "c2": "eps::numerov_sweep_kernel<EPT=4|2,WARPS=4,STRIDE=32> (TMA ring; coarse sweep 4 chains per thread, flat refinement rows 2)",
     "c3": "eps::numerov_sweep_kernel<...,SCAN=true> + segment_combine_kernel (transfer-matrix scan)",
-    "c4": "eps::numerov_sweep_kernel<EPT=4|2,WARPS=4,STRIDE=8> (TMA ring, packed refinement rows)",
+    "c4": "eps::numerov_sweep_kernel<EPT=4|1,WARPS=4,STRIDE=8> (TMA ring; coarse sweep 512-energy CTAs, packed refinement rows in 128-energy CTAs)",
     "c5": "eps::numerov_cbank_kernel<EPT=4,THREADS=128,STRIDE=32> (constant-bank chunks)",
 }
 

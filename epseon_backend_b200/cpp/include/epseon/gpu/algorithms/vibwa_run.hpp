@@ -216,12 +216,19 @@ namespace epseon::gpu::cpp {
         // points per round needs less total work -- take just enough points for one curve's rows to
         // fill a 256-energy CTA ("small packed CTAs").
         {
-            const uint64_t wave = static_cast<uint64_t>(detail::sm_count_of(guard.device)) * 512u;
+            const uint64_t sms  = static_cast<uint64_t>(detail::sm_count_of(guard.device));
+            const uint64_t wave = sms * 512u;
             if (nC > 1 && static_cast<uint64_t>(nC) * nlev * p.refine_points >= 4u * wave) {
+                // many curves: one curve's rows fill a 128-energy CTA (8 levels -> 16 points; k-section needs
+                // M / log2(M + 1) sweeps-worth of energies per bit: C4 20.1 ms with 16 points, 25.5 with 32)
                 uint32_t rows = 1;
                 while (rows < nlev) rows <<= 1;
-                p.refine_points = std::max<uint32_t>(16u, 256u / std::min<uint32_t>(rows, 256u));
-                p.max_rounds    = 24;
+                p.refine_points = std::max<uint32_t>(4u, 128u / std::min<uint32_t>(rows, 128u));
+                p.max_rounds    = 32;
+            } else if (nC == 1) {
+                // one curve: a round of <= 256 energies per SM (2 chains per thread) is latency-bound and costs
+                // about half a full wave, so it is filled exactly: C2 3.97 ms with 17 x 2228 points, 5.64 with 4457
+                p.refine_points = static_cast<uint32_t>(std::clamp<uint64_t>(sms * 256u / nlev, 256u, 32768u));
             }
         }
         if (configurator.getLevelSearch() != 0) { // Cooley iteration instead of k-section sweeps

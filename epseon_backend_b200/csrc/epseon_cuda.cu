@@ -127,6 +127,7 @@ struct eps_ctx {
 
     // measurement
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_round[2] = {nullptr, nullptr};  // refinement rounds: the active-bracket count of round r has reached the host
     cudaEvent_t ev[kEventPairs][2];
     int         ev_used = 0;
     eps_stats   stats{};
@@ -276,11 +277,14 @@ uint32_t pack_log2_for(uint32_t nE, uint32_t pack_rows, uint32_t per_cta = 512) 
 
 cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                               bool tails, int stride, const SweepOut& out, uint32_t pack_log2 = 0, uint32_t pack_cta = 512) {
-    if (pack_log2 && pack_log2 != kFlatRows && pack_cta == 128)  // small packed CTAs (balance of small per-device batches)
+    // pack_cta (packed or flat rows): energies per CTA = 128 / 256 / 512 as 1 / 2 / 4 chains x 4 warps.  Packed rows:
+    // what one curve's rows fill.  Flat rows: few energies are spread over all SMs with fewer chains per
+    // scheduler instead of filling a few SMs with four (a sweep is latency-bound below ~3 chains).
+    if (pack_log2 && pack_cta == 128)
         return ctx->form_resident == 1 ? launch_sweep_s<1, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2)
                                        : launch_sweep_s<1, 4, 0>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     if (ctx->form_resident == 1) {  // D form: the two product shapes only (the EPS_FORCE_* tuning shapes are X-form)
-        if ((pack_log2 && pack_log2 != kFlatRows && pack_cta == 256) || (!pack_log2 && nE <= 256u))
+        if ((pack_log2 && pack_cta == 256) || (!pack_log2 && nE <= 256u))
             return launch_sweep_s<2, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
         return launch_sweep_s<4, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
     }
@@ -512,14 +516,14 @@ int launch_scan(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, c
 // path, recompute ill-conditioned energies with the sequential kernel (one host sync).
 int launch_sweep(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, uint32_t nE, const double* d_Eexp,
                  bool tails, double t_max, bool fix_flagged = true, uint32_t n_rows_active = 0, uint32_t pack_rows = 1,
-                 uint32_t pack_cta = 512) {
+                 uint32_t pack_cta = 512, bool allow_scan = true) {
     const size_t n_out = static_cast<size_t>(n_jobs) * nE;
     EPS_CUDA(ctx, ctx->d_nodes.reserve(n_out));
     if (tails) {
         EPS_CUDA(ctx, ctx->d_mant.reserve(n_out));
         EPS_CUDA(ctx, ctx->d_exp.reserve(n_out));
     }
-    const uint32_t n_seg = pick_segments(ctx, n_rows_active ? n_rows_active : n_jobs, nE, tails);
+    const uint32_t n_seg = (allow_scan || ctx->opt_scan_segments >= 2) ? pick_segments(ctx, n_rows_active ? n_rows_active : n_jobs, nE, tails) : 1u;
     if (n_seg >= 2) {  // reserve before the timed region
         const size_t n_so = n_out * n_seg;
         EPS_CUDA(ctx, ctx->d_segXA.reserve(n_so));
@@ -727,6 +731,8 @@ int eps_ctx_create(int device, eps_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (auto& evt : ctx->ev_round)
+        if ((e = cudaEventCreateWithFlags(&evt, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& pr : ctx->ev)
         for (auto& evt : pr)
             if ((e = cudaEventCreate(&evt)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -771,6 +777,8 @@ int eps_ctx_destroy(eps_ctx* ctx) {
         if (ctx->h_stop_src) cudaFreeHost(ctx->h_stop_src);
         if (ctx->t0) cudaEventDestroy(ctx->t0);
         if (ctx->t1) cudaEventDestroy(ctx->t1);
+        for (auto evt : ctx->ev_round)
+            if (evt) cudaEventDestroy(evt);
         for (auto& pr : ctx->ev)
             for (auto& evt : pr)
                 if (evt) cudaEventDestroy(evt);
@@ -1093,6 +1101,13 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     const uint32_t n_dense   = nC * nlev_pad;
     EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_dense));
     EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_dense, total)));
+    // Dense rows (several curves): the launch shape of a round does not depend on how many brackets are
+    // still active (idle rows have nE = 0 and their CTAs leave at once), so the host never waits for the
+    // stream: it enqueues round r while round r - 1 still sweeps, and only reads the count of round r - 1
+    // -- copied right after that round's jobs were made, long done -- to decide whether to go on.  The
+    // last sweep enqueued is then an empty one.  One curve (flat rows): the count sizes the grid, so the
+    // host reads it first.
+    uint32_t n_prev_pending = 0;  // dense rows: a count copy of the previous round is in flight
     for (uint32_t round = 0; round < p->max_rounds && !cooley; round++) {
         if (flat) {
             compact_refine_jobs_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
@@ -1104,15 +1119,35 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         }
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches++;
-        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16 + (round & 1), ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->stats.d2h_bytes += sizeof(uint32_t);
-        const uint32_t n_active = ctx->h_pinned[0];
+        uint32_t n_active;
+        if (flat) {
+            EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            n_active = ctx->h_pinned[16 + (round & 1)];
+        } else {
+            EPS_CUDA(ctx, cudaEventRecord(ctx->ev_round[round & 1], ctx->stream));
+            n_active = n_dense;  // not known yet: the sweep below idles where nothing is left
+            if (n_prev_pending) {
+                EPS_CUDA(ctx, cudaEventSynchronize(ctx->ev_round[(round - 1) & 1]));
+                if (ctx->h_pinned[16 + ((round - 1) & 1)] == 0) { n_prev_pending = 0; break; }
+            }
+            n_prev_pending = 1;
+        }
         EPS_CHECK_STOP(ctx);
         if (n_active == 0) break;
         const uint32_t n_rows = flat ? n_active : n_dense;
+        uint32_t       cta    = pack_cta;
+        if (flat) {  // one curve: the round's energies over all SMs, with as few chains per scheduler as that takes
+            const uint64_t e = static_cast<uint64_t>(n_active) * M;
+            cta              = e <= 128ull * ctx->sm_count ? 128u : (e <= 256ull * ctx->sm_count ? 256u : 512u);
+        }
+        // Refinement energies crowd the eigenvalues, where the scan path's tails are cancellations: with the
+        // exact fix-up on, a good part of every round is flagged and marched again sequentially, so the
+        // scan can only add to the round (C2 with a third round: 9.2 instead of 4.9 ms).  It is left to the
+        // coarse sweep, and to refinement in the fast mode (EPS_OPT_SCAN_EXACT = 0).
         if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows,
-                                  pack_cta))
+                                  cta, ctx->opt_scan_exact == 0))
             return rc;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_rows * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;

@@ -385,7 +385,7 @@ def test_batch_task_uses_fewer_points_per_round(gpu_mod, oracle, oracle_d):
     handle.wait()
     assert not handle.has_failed(), handle.get_status_message()
     n_coarse, M, rounds, tol = handle.get_search_parameters()
-    assert (n_coarse, M, tol) == (1024, 32, 1e-12) and rounds >= 16
+    assert (n_coarse, M, tol) == (1024, 16, 1e-12) and rounds >= 16
     levels = np.array(handle.get_levels())
     assert levels.shape == (nC, 8) and np.all(np.isfinite(levels))
     s = oracle.scale(20.0, 20.0, W.grid_h(0.4, 10.0, N))

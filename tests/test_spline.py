@@ -92,5 +92,7 @@ def test_file_loader_resamples_non_uniform_table(tmp_path, oracle, fmt, oracle_d
     V = oracle.spline_resample(rk, Vk, rk[0], rk[-1], N)
     s = oracle.scale(W.H2["m0"], W.H2["m1"], (rk[-1] - rk[0]) / (N - 1))
     F, _, _, vmin = oracle_d.prep(V, s)
-    ref, *_ = oracle_d.solve_levels(F, s, vmin, V[-1] - 1.0, 1024, 0, 9, 256, 1e-12, 16)
+    n_coarse, M, rounds, tol = handle.get_search_parameters()  # one curve: the rounds are sized to the device (vibwa_run.hpp)
+    assert (n_coarse, tol) == (1024, 1e-12) and M >= 256
+    ref, *_ = oracle_d.solve_levels(F, s, vmin, V[-1] - 1.0, n_coarse, 0, 9, M, tol, rounds)
     assert np.array_equal(levels.view(np.uint64), ref.view(np.uint64))
