@@ -452,7 +452,9 @@ class Workload:
             self.dE = float(multi.global_step(w["E_lo"], w["E_hi"], C5["nE"]))
             self.w, self.V, self.s, self.scaling = w, pinned(w["V"]), w["s"], "strong"
             self.resident = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=False, tails=False)
-            self.e2e_tail = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=True, tails=False)  # 4 B/energy D2H
+            self.nodes_host = ctx.pinned_empty((1, self.per), np.uint32)  # the caller's page-locked result buffer
+            self.e2e_tail = lambda: ctx.sweep_grid(w["E_lo"], self.dE, self.j0, self.per, nodes=True, tails=False,
+                                                   out_nodes=self.nodes_host)  # 4 B/energy D2H
             self.gather = lambda res: comm.gather(np.zeros(1))  # completion only: the node counts stay on the devices
         ctx.set_potentials(self.V, self.s)
         self.n_steps = ctx.curve_info(0).n_steps
@@ -609,6 +611,47 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     return rec
 
 
+def api_task_record(steps: int) -> dict:
+    """C2 as ONE TASK through the reference's own Python API (`submit_task` .. `wait`, pybind11 module
+    `_libepseon_gpu`): wall clock per task, host tabulation of V(r), upload, accurate recurrence
+    (D form), all 17 levels to 1e-12, results back in the TaskHandle -- the drop-in path's fixed cost
+    beside the C-ABI numbers above.  Rank 0, device 0."""
+    from epseon_backend.device.gpu._libepseon_gpu import EpseonComputeContext, MorsePotentialConfig
+    from tests import workloads as W
+
+    interface = EpseonComputeContext.create().get_device_interface(0)
+
+    def task():
+        cfg = (interface.get_task_configurator("float64")
+               .set_hardware_config(potential_buffer_size=C2["N"], group_size=C2["n_coarse"], allocation_block_size=1 << 24)
+               .set_morse_potential([MorsePotentialConfig(dissociation_energy=W.H2["De"], equilibrium_bond_distance=W.H2["re"],
+                                                          well_width=W.H2["a"], min_r=0.2, max_r=12.0, point_count=C2["N"])])
+               .set_vibwa_algorithm(mass_atom_0=W.H2["m0"], mass_atom_1=W.H2["m1"], integration_step=0.1,
+                                    min_distance_to_asymptote=1.0, min_level=0, max_level=C2["v_max"]))
+        t = time.perf_counter()
+        h = interface.submit_task(cfg)
+        h.wait()
+        wall = (time.perf_counter() - t) * 1e3
+        if h.has_failed():
+            raise RuntimeError(h.get_status_message())
+        return wall, h.get_device_milliseconds(), h
+    for _ in range(3):
+        task()
+    walls, devs = [], []
+    for _ in range(steps):
+        w_ms, d_ms, h = task()
+        walls.append(w_ms)
+        devs.append(d_ms)
+    lev = np.array(h.get_levels())[0]
+    exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
+    n_coarse, M, rounds, tol = h.get_search_parameters()
+    return {"what": "C2 as one task through submit_task()/wait() of the reference API (accurate recurrence, rel_tol 1e-12)",
+            "tasks": steps, "wall_ms_per_task": float(np.mean(walls)), "wall_ms_min": float(np.min(walls)),
+            "device_solve_ms": float(np.mean(devs)), "levels_found": int(np.sum(np.isfinite(lev))),
+            "max_rel_err_vs_analytic": float(np.nanmax(np.abs(lev[: exact.size] - exact) / exact)),
+            "search": {"n_coarse": int(n_coarse), "refine_points": int(M), "max_rounds": int(rounds), "rel_tol": float(tol)}}
+
+
 def main() -> None:
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,
     # compiler chatter of build()) goes to stderr instead.
@@ -670,6 +713,10 @@ def main() -> None:
                         "max_rel_diff_vs_ksection", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 subs[name]["cooley_mode"] = {k: rec[k] for k in keep if k in rec}
         if line is not None:
+            try:
+                line["api_task"] = api_task_record(min(args.steps, SUB_STEPS))
+            except Exception as e:  # the C-ABI records stand on their own
+                line["api_task"] = {"error": f"{type(e).__name__}: {e}"}
             line["sub_records"] = subs
             line["time_to_all_levels_ms"] = {"c2": subs["c2"]["time_to_all_levels_ms"], "c4": subs["c4"]["time_to_all_levels_ms"]}
     if line is not None:

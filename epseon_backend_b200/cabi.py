@@ -236,10 +236,14 @@ class Context:
                                             _ptr(x, np.int32)))
         return n, m, x
 
-    def sweep_grid(self, E0, dE, j0: int, nE: int, nodes: bool = True, tails: bool = True):
-        """Affine grid E_j = E0 + (j0 + j) dE (a slice of a global uniform grid)."""
+    def sweep_grid(self, E0, dE, j0: int, nE: int, nodes: bool = True, tails: bool = True, out_nodes: np.ndarray | None = None):
+        """Affine grid E_j = E0 + (j0 + j) dE (a slice of a global uniform grid).  out_nodes: the caller's
+        [n_curves, nE] uint32 buffer for the node counts (page-locked, ``pinned_empty``, for a full-rate D2H)."""
         a, b = _vec(E0, self.n_curves), _vec(dE, self.n_curves)
-        n, m, x = self._outs(nE, nodes, tails)
+        n, m, x = self._outs(nE, nodes and out_nodes is None, tails)
+        if nodes and out_nodes is not None:
+            assert out_nodes.dtype == np.uint32 and out_nodes.shape == (self.n_curves, nE) and out_nodes.flags.c_contiguous
+            n = out_nodes
         self._ck(self.lib.eps_sweep_grid(self.h, _ptr(a, np.float64), _ptr(b, np.float64), C.c_uint32(j0),
                                          C.c_uint64(nE), _ptr(n, np.uint32), _ptr(m, np.float64),
                                          _ptr(x, np.int32)))

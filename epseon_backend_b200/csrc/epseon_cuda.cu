@@ -110,7 +110,7 @@ struct eps_ctx {
     DevBuf<int32_t>     d_cbexp;
     DevBuf<uint32_t>    d_cbnodes, d_cbprev;
     int64_t             opt_cbank = 0;  // 0 auto (large single-curve sweeps), 1 always when the launch qualifies, 2 never
-    int                 cb_ept = 4, cb_threads = 128, cb_pdl = 1, cb_group = 4;
+    int                 cb_ept = 4, cb_threads = 128, cb_pdl = 1, cb_group = 2;
     uint64_t            cbank_launches = 0;
 
     // wavefunction scratch
@@ -315,9 +315,11 @@ cudaError_t launch_cbank_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     // 470 MB out and 470 MB in per chunk -- 45 GB of HBM traffic per sweep for 1.6 MB of table.  Running
     // the chunk launches group by group, a group being as many CTAs as keep its state (and the L2's
     // other tenants) resident, leaves the state in L2: HBM then sees the table and the node counts.
-    // cb_group = CTAs per group in resident waves of the device (0: one group, the round-1 order).  Default 4
-    // (4736 CTAs, 68 MB of state on a B200): 754.8 ms against 753.8 ms ungrouped on C5, same node counts
-    // (profiles/r2_cbank_group.log); smaller groups pay more launch boundaries (1 wave: +1.9 %).
+    // cb_group = CTAs per group in resident waves of the device (0: one group, the round-1 order).  Default 2
+    // (2368 CTAs, 34 MB of state on a B200).  Measured on C5 with the L2 as the sweep leaves it (ncu
+    // application replay, profiles/r2_cbank_traffic.log, r2_cbank_group2.log): per chunk launch 0.7 MB of
+    // DRAM traffic with 2 waves, 8 MB with 3, 46 MB with 4 (ungrouped: 0.9 GB, the round-1 capture's 45 GB per
+    // sweep); sweep 758.2 / 758.5 / 755.9 / 753.2 ms -- 715 instead of 52 launch boundaries cost 0.7 %.
     const int  resident_ctas = std::max(1, 2048 / kThreads > 8 ? 8 : 2048 / kThreads);  // 64 regs x 128 threads: 8 per SM
     uint64_t   group         = grid;
     if (ctx->cb_group > 0) group = std::min<uint64_t>(grid, static_cast<uint64_t>(ctx->cb_group) * resident_ctas * ctx->sm_count);

@@ -19,12 +19,22 @@ while read -r w f pat key per skip; do
 done <<SPECS
 c2 0 numerov_sweep c2 1
 c2 1 numerov_sweep c2_dform 1
-c5 0 numerov_cbank c5 357 10
-c5 1 numerov_cbank c5_dform 357 10
+c5 0 numerov_cbank c5 715 10
+c5 1 numerov_cbank c5_dform 715 10
 c3 0 numerov_sweep|segment_combine c3 1
 c3 1 numerov_sweep|segment_combine c3_dform 1
 c4 0 numerov_sweep c4 1
 c4 1 numerov_sweep c4_dform 1
 cooley 1 cooley cooley 1
 SPECS
+# c5 traffic: kernel replay flushes L2 before every pass, so the figures above always show the carried state
+# coming from DRAM; application replay without cache control sees the L2 a real sweep leaves behind
+for f in 0 1; do
+  ncu --replay-mode application --cache-control none --clock-control none \
+      --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:numerov_cbank \
+      --launch-skip 120 -c 120 --csv --log-file /tmp/r2_c5_f${f}_appreplay.csv python scripts/ncu_target.py c5 $f 1 > gpurun_out/r2_ncu_c5_f${f}_app.log 2>&1
+  per=$(grep -o "cbank launches per sweep [0-9]*" gpurun_out/r2_ncu_c5_f${f}_app.log | tail -1 | grep -o "[0-9]*$")
+  key=c5; [ $f = 1 ] && key=c5_dform
+  python scripts/summarize_profiles.py r2_c5_f${f}_appreplay --out $O --traffic-csv /tmp/r2_c5_f${f}_appreplay.csv --traffic $key --per-step ${per:-715}
+done
 ls -la $O

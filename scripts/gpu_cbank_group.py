@@ -18,8 +18,9 @@ for form in (0, 1):
     ctx.set_potentials(w["V"], w["s"])
     n_steps = ctx.curve_info(0).n_steps
     ref = None
-    for group in (0, 1, 2, 3, 4, 8):
+    for group, pdl in ((0, 1), (2, 1), (2, 3), (2, 4), (2, 6), (3, 1), (3, 4), (4, 1), (4, 4)):
         ctx.set_option(ctx.OPT_CBANK_GROUP, group)
+        ctx.set_option(ctx.OPT_CBANK_PDL, pdl)
         ctx.sweep_uniform(w["E_lo"], w["E_hi"], nE, nodes=False, tails=False)
         ctx.sync()
         ctx.stats_reset()
@@ -32,6 +33,6 @@ for form in (0, 1):
         n = ctx.sweep_uniform(w["E_lo"], w["E_hi"], nE, nodes=True, tails=False)[0]
         if ref is None:
             ref = n
-        print(f"form {form} group {group}: {st.sweep_ms / reps:9.3f} ms  steps/s {rate:.4g}  launches/sweep {st.kernel_launches // reps}"
+        print(f"form {form} group {group} pdl {pdl}: {st.sweep_ms / reps:9.3f} ms  steps/s {rate:.4g}  launches/sweep {st.kernel_launches // reps}"
               f"  nodes {'== ungrouped' if np.array_equal(n, ref) else 'MISMATCH'}", flush=True)
 ctx.close()

@@ -1,6 +1,6 @@
 """Short workload for ncu captures: one BASELINE workload's resident step, a few times.
 
-    python scripts/ncu_target.py c2|c3|c4|c5|cooley [form] [reps]
+    python scripts/ncu_target.py c2|c3|c4|c4s|c5|cooley [form] [reps]
 
 c2: 65 536-energy coarse sweep + refinement of 17 levels (TMA ring kernel, flat rows);
 c3: 4096 energies x 1M grid (scan path); c4: 4096 curves x (1024 coarse + packed refinement rows);
@@ -26,18 +26,24 @@ if which == "c2":
     w = W.c2()
     ctx.set_potentials(w["V"], w["s"])
     for _ in range(reps):
-        ctx.solve_levels(w["E_lo"], w["E_hi"], 65536, 0, 16, 4457, 1e-10, 8)
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 65536, 0, 16, 2228, 1e-10, 8)
 elif which == "c3":
     w = W.c3()
     ctx.set_potentials(w["V"], w["s"])
     for _ in range(reps):
         ctx.sweep_uniform(w["E_lo"], w["E_hi"], 4096, nodes=False, tails=False)
-elif which == "c4":
-    w = W.c4()
+elif which in ("c4", "c4s"):  # c4s: one GPU's share of C4 on an 8-GPU box (512 curves)
+    w = W.c4() if which == "c4" else W.c4(512, 10_000, 1024)
     ctx.set_potentials(w["V"], w["s"])
+    import time
     for _ in range(reps):
-        ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, 7, 32, 1e-10, 8)
+        t0 = time.perf_counter()
+        ctx.solve_levels(w["E_lo"], w["E_hi"], 1024, 0, 7, 16, 1e-10, 12)
+        print("solve wall ms", (time.perf_counter() - t0) * 1e3)
 elif which == "c5":
+    import os
+    if "EPS_CB_GROUP" in os.environ:  # tuning: energy-group size of the constant-bank sweep (resident waves; 0 = one group)
+        ctx.set_option(ctx.OPT_CBANK_GROUP, int(os.environ["EPS_CB_GROUP"]))
     w = W.c5()  # the full 2^24 energies: the carried state's path through L2 / HBM depends on the size
     ctx.set_potentials(w["V"], w["s"])
     for _ in range(reps):

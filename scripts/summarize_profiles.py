@@ -156,6 +156,33 @@ def traffic_json(tag: str, rep: Path, name: str, kernel: str, per_step: int) -> 
     path.write_text(json.dumps(cur, indent=1, sort_keys=True) + "\n")
 
 
+def traffic_csv(tag: str, path_csv: Path, name: str, per_step: int) -> None:
+    """profiles/traffic.json[name] from an APPLICATION-replay ncu CSV (`--replay-mode application
+    --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum`): the kernels see the L2
+    state the previous launches left, which is what decides whether the constant-bank sweep's carried
+    state crosses HBM (kernel replay flushes L2 before every pass and always reads it from DRAM)."""
+    rows = list(csv.reader(line for line in open(path_csv) if line.startswith('"')))
+    h = rows[0]
+    mi, vi, ui, ki = h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit"), h.index("Kernel Name")
+    tot, ids, names = 0.0, set(), set()
+    for r in rows[1:]:
+        if r[mi] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            continue
+        tot += float(r[vi].replace(",", "")) * UNIT[r[ui]]
+        ids.add(r[h.index("ID")])
+        names.add(r[ki].split("(")[0])
+    n = len(ids)
+    if n == 0:
+        raise SystemExit("no launches in " + str(path_csv))
+    path = PROF / "traffic.json"
+    cur = json.loads(path.read_text()) if path.exists() else {}
+    cur[name] = {"dram_bytes_per_launch": int(round(tot / n * per_step)), "launches_captured": n, "kernel_launches_per_bench_launch": per_step,
+                 "kernel": sorted(names)[0], "csrc_digest": csrc_digest(),
+                 "source": f"profiles/{tag}.csv (ncu --replay-mode application --cache-control none: L2 as the sweep leaves it)"}
+    path.write_text(json.dumps(cur, indent=1, sort_keys=True) + "\n")
+    shutil.copy(path_csv, PROF / f"{tag}.csv")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
@@ -165,7 +192,8 @@ def main() -> None:
     ap.add_argument("--out", type=Path, help="write into this directory instead of profiles/ (on the GPU box: gpurun_out/profiles)")
     ap.add_argument("--traffic", help="workload key of profiles/traffic.json to (re)write from --rep, e.g. c2 or c5_dform")
     ap.add_argument("--kernel", default="numerov_sweep_kernel", help="kernel-name substring for --traffic")
-    ap.add_argument("--per-step", type=int, default=1, help="kernel launches per bench launch (51 for the c5 chunks)")
+    ap.add_argument("--per-step", type=int, default=1, help="kernel launches per bench launch (the chunk launches of a c5 sweep)")
+    ap.add_argument("--traffic-csv", type=Path, help="application-replay ncu CSV with the dram__bytes metrics -> traffic.json[--traffic]")
     a = ap.parse_args()
     global PROF
     if a.out:
@@ -177,6 +205,8 @@ def main() -> None:
         ncu_md(a.tag, a.rep)
         if a.traffic:
             traffic_json(a.tag, a.rep, a.traffic, a.kernel, a.per_step)
+    if a.traffic_csv:
+        traffic_csv(a.tag, a.traffic_csv, a.traffic, a.per_step)
     for f in a.copy:
         shutil.copy(f, PROF / f.name)
 
