@@ -280,9 +280,20 @@ cudaError_t launch_sequential(eps_ctx* ctx, const Job* d_jobs, uint32_t n_jobs, 
     // pack_cta (packed or flat rows): energies per CTA = 128 / 256 / 512 as 1 / 2 / 4 chains x 4 warps.  Packed rows:
     // what one curve's rows fill.  Flat rows: few energies are spread over all SMs with fewer chains per
     // scheduler instead of filling a few SMs with four (a sweep is latency-bound below ~3 chains).
-    if (pack_log2 && pack_cta == 128)
+    // 128 energies as 2 chains x 2 warps or as 1 chain x 4 warps.  With one chain per thread ptxas feeds none
+    // of the three-register DFMAs from the reuse cache (9.06 modelled pipe cycles per step against 8.33,
+    // scripts/sass_pipe_model.py), and a launch of at most one resident wave is faster with two (512 curves:
+    // 3.09 against 3.27 ms per solve); over many waves the four-warp CTA wins (4096 curves: 20.1 against
+    // 20.7 ms): profiles/r2_refine_points2.log, r2_refine_points3.log.
+    if (pack_log2 && pack_cta == 128) {
+        const uint64_t ctas = pack_log2 == kFlatRows ? (static_cast<uint64_t>(n_jobs) * nE + 127) / 128
+                                                     : ((static_cast<uint64_t>(n_jobs) + (1u << pack_log2) - 1) >> pack_log2);
+        if (ctas <= 4ull * ctx->sm_count)
+            return ctx->form_resident == 1 ? launch_sweep_s<2, 2, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2)
+                                           : launch_sweep_s<2, 2, 0>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
         return ctx->form_resident == 1 ? launch_sweep_s<1, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2)
                                        : launch_sweep_s<1, 4, 0>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
+    }
     if (ctx->form_resident == 1) {  // D form: the two product shapes only (the EPS_FORCE_* tuning shapes are X-form)
         if ((pack_log2 && pack_cta == 256) || (!pack_log2 && nE <= 256u))
             return launch_sweep_s<2, 4, 1>(ctx, stride, d_jobs, n_jobs, nE, d_Eexp, tails, out, pack_log2);
@@ -1082,7 +1093,7 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     uint32_t       pack_cta  = (!flat && M <= 128 && nlev <= rows512 / 2) ? 256u : 512u;
     // Balance of small per-device batches.  Equal CTAs over 148 SMs leave a tail: 512 curves in
     // 256-energy CTAs (2 resident per SM) are 3.46 per SM -> two rounds of 2, i.e. 4 units of SM time
-    // for 3.46 of work.  128-energy CTAs (1 chain x 4 warps, 4 resident per SM: the same four chains
+    // for 3.46 of work.  128-energy CTAs (1 chain x 4 warps or 2 x 2, 4 resident per SM: the same four chains
     // per scheduler) halve the unit: 6.92 per SM -> a round of 4 and one of 3.  Cost model in units of
     // (one chain per scheduler x the grid): full rounds cost `resident x chains`, the last one what is
     // left; the smaller shape is taken when it saves more than 5 %.

@@ -24,7 +24,7 @@ namespace eps {
 
 constexpr int      kTile          = 2048;  // grid steps per shared-memory stage (16 KiB of F_k)
 constexpr int      kStages        = 4;     // TMA ring depth of the big CTA shapes
-// Ring depth by CTA shape: the 128-energy CTA (1 chain x 4 warps) runs four to a SM, so two
+// Ring depth by CTA shape: the 128-energy CTAs (1 chain x 4 warps, 2 chains x 2 warps) run four to a SM, so two
 // stages (32 KiB) per CTA keep as much table in flight per SM as one 4-stage CTA does.
 template <int kEpt, int kWarps>
 __host__ __device__ constexpr int sweep_stages() {
