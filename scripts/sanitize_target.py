@@ -2,7 +2,8 @@
 TMA sweep (tails, packed + flat refinement rows), scan path + fix-up, constant-bank chunks,
 device prep, centrifugal expansion, spline evaluation, wavefunctions; round 2: the D form on every
 route, the Cooley search kernel (box and open tail), a two-context group with its peer copies, the
-stop flag.  Sizes are tiny: the sanitizer slows kernels 10-100x."""
+stop flag; the block-level prefix combine, the constant-bank energy groups and both 128-energy CTA
+shapes.  Sizes are tiny: the sanitizer slows kernels 10-100x."""
 import sys
 from pathlib import Path
 
@@ -56,6 +57,28 @@ with cabi.Context(0) as ctx:
     except cabi.EpsError as e:
         assert e.code == cabi.EPS_ERR_CANCELLED
     ctx.reset_stop()
+    ctx.sync()
+# ---- round 2, later: block-level prefix combine, constant-bank energy groups (cta_base != 0), 128-energy CTA shapes
+with cabi.Context(0) as ctx:
+    for form in (0, 1):
+        ctx.set_option(ctx.OPT_FORM, form)
+        ctx.set_potentials(V[0], s)
+        ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 3)
+        ctx.set_option(ctx.OPT_SCAN_COMBINE, 2)                        # prefix kernel (16 lanes, 3 active)
+        ctx.sweep_uniform(lo[0], hi[0], 300)
+        ctx.set_option(ctx.OPT_SCAN_SEGMENTS, 0)
+        ctx.set_option(ctx.OPT_SCAN_COMBINE, 0)
+        ctx.set_option(ctx.OPT_CBANK, 1)
+        ctx.set_option(ctx.OPT_CBANK_GROUP, 1)                         # 1184 CTAs per group: the second group starts at cta_base 1184
+        ctx.sweep_uniform(lo[0], hi[0], 1184 * 512 + 700, tails=False)
+        ctx.set_option(ctx.OPT_CBANK, 0)
+        ctx.set_option(ctx.OPT_CBANK_GROUP, 2)
+        ctx.solve_levels(lo[0], hi[0], 1024, 0, 5, 40, 1e-10, 8)       # flat rows in 128-energy CTAs (2 chains x 2 warps)
+        ctx.set_potentials(V, s)
+        ctx.solve_levels(lo, hi, 256, 0, 7, 16, 1e-10, 8)              # packed rows, 128-energy CTAs, one wave (2 x 2)
+        Vm = np.ascontiguousarray(np.tile(V, (320, 1))[:, :1500])      # 640 short curves: more than one resident wave (1 x 4)
+        ctx.set_potentials(Vm, s)
+        ctx.solve_levels(Vm.min(axis=1), Vm[:, -1] - 1.0, 64, 0, 7, 16, 1e-9, 4)
     ctx.sync()
 with cabi.Group([0, 0]) as g:                                          # two contexts, host threads, peer copies
     g.set_potentials(V, s, cabi.SHARD_CURVES)
