@@ -134,7 +134,7 @@ def rank_curve(rank: int):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 20 ms from a
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 100 ms from a
     thread (nvidia_ml_py), falling back to `nvidia-smi -lms` when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -156,7 +156,7 @@ class ClockSampler:
                 self.rows.append((time.time(), float(clk), pw, [k for k, b in bits.items() if mask & b]))
             except Exception:  # noqa: BLE001 - sampling must never break the benchmark
                 pass
-            time.sleep(0.02)
+            time.sleep(0.1)
 
     def start(self):
         try:
@@ -194,7 +194,7 @@ class ClockSampler:
             reasons = sorted({x for r in sel for x in r[3]})
             return {"sm_mhz": float(np.median([r[1] for r in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
                     "samples": len(sel), "power_w_max": max((r[2] for r in sel), default=None), "reasons": reasons,
-                    "source": "nvml, 20 ms period, inside the timed region"}
+                    "source": "nvml, 100 ms period, inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
         time.sleep(0.15)
@@ -700,16 +700,16 @@ def main() -> None:
         # the accurate recurrence on the same workloads (EPS_OPT_FORM = 1): what the drop-in
         # VibwaAlgorithm<FP>::run uses; 5 instead of 4 FP64 operations per step
         for name in ("c5", "c2", "c4", "c3"):
-            rec = measure(name, ctx, comm, sampler, min(args.steps, 5), 3, fp64_peak, 0.001 if cpu_s else 0.0, form=1)
+            rec = measure(name, ctx, comm, sampler, min(args.steps, 5 if name == "c5" else SUB_STEPS), 3, fp64_peak, 0.001 if cpu_s else 0.0, form=1)
             if rec is not None:
-                keep = ("value", "ms_per_step", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
+                keep = ("value", "ms_per_step", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
                         "nodes_bit_identical_to_oracle_full_size_sample", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 (line if name == "c5" else subs[name])["accurate_mode"] = {k: rec[k] for k in keep if k in rec}
         # ... and the Cooley level search on the accurate tables: time to all levels without refinement sweeps
         for name in ("c2", "c4"):
             rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, 0.0, form=1, cooley=True)
             if rec is not None:
-                keep = ("value", "ms_per_step", "time_to_all_levels_ms", "e2e", "gpu_launches", "level_search",
+                keep = ("value", "ms_per_step", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "gpu_launches", "level_search",
                         "max_rel_diff_vs_ksection", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 subs[name]["cooley_mode"] = {k: rec[k] for k in keep if k in rec}
         if line is not None:

@@ -1954,8 +1954,10 @@ int mailbox_wait_ack(eps_mailbox* mb, uint32_t seq) {
         EPS_CUDA(ctx, cudaMemcpyAsync(mb->h_seq + 63, ack, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (static_cast<int32_t>(mb->h_seq[63] - (seq - 1)) >= 0) return EPS_OK;
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
-            return fail(ctx, EPS_ERR_STATE, "eps_mailbox_post: rank 0 never collected the previous payload");
+        const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (waited > 120.0) return fail(ctx, EPS_ERR_STATE, "eps_mailbox_post: rank 0 never collected the previous payload");
+        // rank 0 is busy elsewhere: do not hammer its memory with peer reads (each poll is a copy + a sync)
+        if (waited > 200e-6) std::this_thread::sleep_for(std::chrono::microseconds(waited > 5e-3 ? 200 : 20));
     }
 }
 
@@ -2015,8 +2017,9 @@ int eps_mailbox_collect(eps_mailbox* mb, uint32_t seq, void* out, size_t bytes_p
         bool all = true;
         for (uint32_t r = 0; r < mb->world; r++) all = all && mb->h_flags[r] == seq;
         if (all) break;
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
-            return fail(ctx, EPS_ERR_STATE, "eps_mailbox_collect: timed out waiting for a rank");
+        const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (waited > timeout_s) return fail(ctx, EPS_ERR_STATE, "eps_mailbox_collect: timed out waiting for a rank");
+        if (waited > 5e-3) std::this_thread::sleep_for(std::chrono::microseconds(100));  // a rank is far behind: poll gently
     }
     // the first bytes_per_rank bytes of every slot, packed [world][bytes_per_rank], in one strided copy
     EPS_CUDA(ctx, cudaMemcpy2DAsync(out, bytes_per_rank, mb->d_base, mb->slot_bytes, bytes_per_rank, mb->world,
