@@ -101,6 +101,7 @@ struct eps_ctx {
     uint32_t         n_tiles_max  = 0;   // over the resident curves
     int64_t          opt_scan_segments = 0;  // 0 auto, 1 never, >= 2 forced segment count
     int64_t          opt_scan_exact    = 1;  // 1: eps_solve_levels also recomputes flagged energies sequentially
+    const uint32_t*  flat_rows_dev     = nullptr;  // flat refinement rows: the row count lives on the device (blind rounds)
     int              opt_scan_combine  = 0;  // 0 auto (prefix from kScanPrefixMin segments), 1 serial loop, 2 prefix always
     uint64_t         scan_launches = 0, scan_flagged = 0;
 
@@ -226,7 +227,8 @@ cudaError_t launch_sweep_variant(eps_ctx* ctx, const Job* d_jobs, uint32_t n_job
     ctx->stats.kernel_launches++;
     kern<<<static_cast<unsigned>(grid), (kWarps + 1) * 32, smem, ctx->stream>>>(
         kForm == 0 ? ctx->d_F.p : ctx->d_A.p, ctx->d_curves.p, d_jobs, static_cast<uint32_t>(chunks), d_Eexp, nE, out.nodes,
-        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2, ctx->d_stop);
+        kTails ? out.mant : nullptr, kTails ? out.expo : nullptr, ctx->d_steps, n_seg, tiles_per_seg, so, pack_log2, ctx->d_stop,
+        pack_log2 == kFlatRows ? ctx->flat_rows_dev : nullptr);
     return cudaGetLastError();
 }
 
@@ -1114,14 +1116,30 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
     const uint32_t n_dense   = nC * nlev_pad;
     EPS_CUDA(ctx, ctx->d_jobs_ref.reserve(n_dense));
     EPS_CUDA(ctx, ctx->d_jstar.reserve(std::max(n_dense, total)));
-    // Dense rows (several curves): the launch shape of a round does not depend on how many brackets are
-    // still active (idle rows have nE = 0 and their CTAs leave at once), so the host never waits for the
-    // stream: it enqueues round r while round r - 1 still sweeps, and only reads the count of round r - 1
-    // -- copied right after that round's jobs were made, long done -- to decide whether to go on.  The
-    // last sweep enqueued is then an empty one.  One curve (flat rows): the count sizes the grid, so the
-    // host reads it first.
+    // Rounds without the host.  A round's launches do not need the number of open brackets on the host:
+    // dense rows (several curves) idle where nothing is left (nE = 0, their CTAs leave at once), and flat
+    // rows (one curve) read the row count from the device (flat_rows_dev; the grid is sized for all rows).
+    // The first `blind` rounds are therefore enqueued back to back, before the coarse sweep has even
+    // finished -- `blind` = the rounds the WIDEST tolerance of the job certainly needs, from the coarse
+    // spacing, rel_tol and M -- so a host thread that is descheduled for a few milliseconds (shared
+    // hosts: observed as rare 15 ms .. 1 s spikes in 4 ms solves that synced every round) no longer
+    // idles the device.  After them the count is read: dense rows one round late (the host stays a
+    // round ahead), flat rows before every further round (rare: brackets that needed one more).
+    uint32_t blind = 0;
+    if (!cooley && ctx->opt_scan_exact != 0 && ctx->opt_scan_segments < 2) {  // (the scan path's fix-up reads back per launch anyway)
+        double need = 1e300;  // min over the curves of log(spacing / (rel_tol |E|max)) / log(M + 1)
+        for (uint32_t c = 0; c < nC; c++) {
+            double a, b;
+            grid_ends(g, c, nE, a, b);
+            const double spacing = (b - a) / static_cast<double>(nE - 1), mag = std::max(std::fabs(a), std::fabs(b));
+            const double tol = p->rel_tol * mag;
+            need = std::min(need, (tol > 0.0 && spacing > tol) ? std::log(spacing / tol) / std::log(static_cast<double>(M) + 1.0) : 0.0);
+        }
+        blind = static_cast<uint32_t>(std::min<double>(p->max_rounds, std::ceil(std::max(need, 0.0))));
+    }
     uint32_t n_prev_pending = 0;  // dense rows: a count copy of the previous round is in flight
     for (uint32_t round = 0; round < p->max_rounds && !cooley; round++) {
+        const bool is_blind = round < blind;
         if (flat) {
             compact_refine_jobs_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_lo.p, ctx->d_hi.p, ctx->d_state.p, total, nlev, p->v_min, p->rel_tol, M,
                                                                   ctx->d_jobs_ref.p, ctx->d_nactive.p);
@@ -1132,23 +1150,25 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         }
         EPS_CUDA(ctx, cudaGetLastError());
         ctx->stats.other_launches++;
-        EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16 + (round & 1), ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->stats.d2h_bytes += sizeof(uint32_t);
-        uint32_t n_active;
-        if (flat) {
-            EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            n_active = ctx->h_pinned[16 + (round & 1)];
-        } else {
-            EPS_CUDA(ctx, cudaEventRecord(ctx->ev_round[round & 1], ctx->stream));
-            n_active = n_dense;  // not known yet: the sweep below idles where nothing is left
-            if (n_prev_pending) {
-                EPS_CUDA(ctx, cudaEventSynchronize(ctx->ev_round[(round - 1) & 1]));
-                if (ctx->h_pinned[16 + ((round - 1) & 1)] == 0) { n_prev_pending = 0; break; }
+        uint32_t n_active = flat ? total : n_dense;  // upper bound while the count is not read
+        if (!is_blind) {
+            EPS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 16 + (round & 1), ctx->d_nactive.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += sizeof(uint32_t);
+            if (flat || (blind > 0 && round == blind)) {  // (after the blind rounds: normally the end -- look before another sweep)
+                EPS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                n_active = ctx->h_pinned[16 + (round & 1)];
+                if (!flat && n_active != 0) n_active = n_dense;
+            } else {
+                EPS_CUDA(ctx, cudaEventRecord(ctx->ev_round[round & 1], ctx->stream));
+                if (n_prev_pending) {
+                    EPS_CUDA(ctx, cudaEventSynchronize(ctx->ev_round[(round - 1) & 1]));
+                    if (ctx->h_pinned[16 + ((round - 1) & 1)] == 0) { n_prev_pending = 0; break; }
+                }
+                n_prev_pending = 1;
             }
-            n_prev_pending = 1;
+            EPS_CHECK_STOP(ctx);
+            if (n_active == 0) break;
         }
-        EPS_CHECK_STOP(ctx);
-        if (n_active == 0) break;
         const uint32_t n_rows = flat ? n_active : n_dense;
         uint32_t       cta    = pack_cta;
         if (flat) {  // one curve: the round's energies over all SMs, with as few chains per scheduler as that takes
@@ -1159,9 +1179,11 @@ int solve_rows(eps_ctx* ctx, const eps_solve_params* p, const GridSpec& g, doubl
         // exact fix-up on, a good part of every round is flagged and marched again sequentially, so the
         // scan can only add to the round (C2 with a third round: 9.2 instead of 4.9 ms).  It is left to the
         // coarse sweep, and to refinement in the fast mode (EPS_OPT_SCAN_EXACT = 0).
-        if (int rc = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows,
-                                  cta, ctx->opt_scan_exact == 0))
-            return rc;
+        ctx->flat_rows_dev = (flat && is_blind) ? ctx->d_nactive.p : nullptr;
+        const int rc_sweep = launch_sweep(ctx, ctx->d_jobs_ref.p, n_rows, M, nullptr, false, t_max, ctx->opt_scan_exact != 0, n_active, pack_rows,
+                                          cta, ctx->opt_scan_exact == 0);
+        ctx->flat_rows_dev = nullptr;
+        if (rc_sweep) return rc_sweep;
         EPS_CUDA(ctx, cudaMemsetAsync(ctx->d_jstar.p, 0xff, n_rows * sizeof(uint32_t), ctx->stream));
         const uint32_t bpr = (M + 255) / 256;
         crossing_kernel<<<bpr * n_rows, 256, 0, ctx->stream>>>(ctx->d_nodes.p, M, M, bpr, ctx->d_jobs_ref.p, 0, 0, 1, ctx->d_jstar.p);

@@ -256,7 +256,8 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
                      uint32_t* __restrict__ nodes_out, double* __restrict__ mant_out,
                      int32_t* __restrict__ exp_out, unsigned long long* __restrict__ steps_done,
                      const uint32_t n_seg, const uint32_t tiles_per_seg, const SegOut seg_out,
-                     const uint32_t pack_log2, const int* __restrict__ stop_flag) {
+                     const uint32_t pack_log2, const int* __restrict__ stop_flag,
+                     const uint32_t* __restrict__ flat_rows_dev) {
     static_assert(kStride == 1 || kStride == 8 || kStride == 32, "sign sampling stride");
     static_assert(!kScan || (kEpt == 2 && !kTails), "scan mode: two basis chains per energy");
     constexpr uint32_t kPerCta = kScan ? kWarps * 32 : kWarps * 32 * kEpt;
@@ -277,7 +278,9 @@ numerov_sweep_kernel(const double* __restrict__ F, const CurveDev* __restrict__ 
     const CurveDev cv      = curves[job.curve];
     const uint32_t slot_sz = flat ? job.nE : kPerCta >> pack_log2;  // energies per row (flat) / packed row slot
     const uint64_t flat0   = static_cast<uint64_t>(cta) * kPerCta;  // flat mode: first (row * nE + j) of this CTA
-    const uint64_t flat_n  = static_cast<uint64_t>(chunks_per_job) * job.nE;  // flat mode: chunks_per_job carries n_rows
+    // flat mode: chunks_per_job carries the number of rows -- or an upper bound of it, with the true count on
+    // the device (flat_rows_dev): refinement rounds enqueued before the host knows how many brackets are open
+    const uint64_t flat_n  = static_cast<uint64_t>((flat && flat_rows_dev != nullptr) ? *flat_rows_dev : chunks_per_job) * job.nE;
     const uint32_t n_steps = cv.n_steps;
     const uint32_t n_tiles_all = (n_steps + kTile - 1) / kTile;
     const uint32_t t_begin = kScan ? min(seg * tiles_per_seg, n_tiles_all) : 0u;
@@ -893,6 +896,8 @@ __global__ void compact_refine_jobs_kernel(const double* __restrict__ lo, const 
         }
         __syncthreads();
     }
+    __syncthreads();
+    for (uint32_t pos = running + threadIdx.x; pos < total; pos += blockDim.x) jobs_out[pos].nE = 0;  // idle tail rows
     if (threadIdx.x == 0) *n_active = running;
 }
 

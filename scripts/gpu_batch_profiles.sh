@@ -1,14 +1,13 @@
 #!/bin/bash
-# One GPU call: the default bench line, the reference arm, the ncu launch list of the default
-# command and one `ncu --set full` capture per workload and recurrence form.  The .ncu-rep files are
+# One GPU call: the ncu launch list of the default command, one `ncu --set full` capture per workload and
+# recurrence form, the application-replay traffic of the constant-bank sweep, then the default bench line and
+# the reference arm.  The .ncu-rep files are
 # summarised ON THE BOX (gpurun brings back at most 64 MiB): only the markdown summaries and
 # traffic.json return, under gpurun_out/profiles/; copy them into profiles/ afterwards.
 set -x
 O=gpurun_out/profiles
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()"
-python bench.py > $O/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
-python bench.py --impl reference > $O/r2_bench_ref.json 2>> gpurun_out/r2_bench_n1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file /tmp/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_bench_all.log 2>&1
 python scripts/summarize_profiles.py r2_default --out $O --launches /tmp/r2_launches.csv
 cp profiles/traffic.json $O/traffic.json 2>/dev/null
@@ -37,4 +36,8 @@ for f in 0 1; do
   key=c5; [ $f = 1 ] && key=c5_dform
   python scripts/summarize_profiles.py r2_c5_f${f}_appreplay --out $O --traffic-csv /tmp/r2_c5_f${f}_appreplay.csv --traffic $key --per-step ${per:-715}
 done
+# the default bench line and the reference arm LAST, with the traffic figures captured above (same kernel sources)
+cp $O/traffic.json profiles/traffic.json
+python bench.py > $O/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
+python bench.py --impl reference > $O/r2_bench_ref.json 2>> gpurun_out/r2_bench_n1.err
 ls -la $O
