@@ -71,3 +71,37 @@ def test_cbank_not_used_for_batches(cb_ctx):
     cb_ctx.set_potentials(w["V"], w["s"])
     cb_ctx.sweep_uniform(w["E_lo"], w["E_hi"], 64, tails=False)
     assert cb_ctx.counter(cb_ctx.CNT_CBANK_LAUNCHES) == 0
+
+
+@pytest.mark.parametrize("form", [0, 1])
+def test_cbank_energy_groups_same_bits(oracle, oracle_d, cb_ctx, form):
+    """EPS_OPT_CBANK_GROUP: the chunk launches of a sweep run group by group of resident waves (the carried
+    state stays in L2).  Same node counts and tails whatever the group size -- groups of one wave put the
+    second group at CTA 1184 -- and the oracle's bits on a sample."""
+    N, nE = 4200, 1184 * 512 + 901  # two chunks; more than one wave of 512-energy CTAs, ragged last CTA
+    V = W.morse(5500.0, 2.2, 1.6, 1.0, 8.0, N)
+    s = W.scale(20.0, 20.0, W.grid_h(1.0, 8.0, N))
+    orc = oracle_d if form else oracle
+    cb_ctx.set_option(cb_ctx.OPT_FORM, form)
+    try:
+        cb_ctx.set_potentials(V, s)
+        lo, hi = float(V.min()), float(min(V[-1], V.min() + 0.4 / s))
+        out = {}
+        for group in (0, 1, 2):
+            cb_ctx.set_option(cb_ctx.OPT_CBANK_GROUP, group)
+            before = cb_ctx.counter(cb_ctx.CNT_CBANK_LAUNCHES)
+            out[group] = cb_ctx.sweep_uniform(lo, hi, nE)
+            chunks = -(-cb_ctx.curve_info(0).n_steps // 3968)
+            assert cb_ctx.counter(cb_ctx.CNT_CBANK_LAUNCHES) - before == chunks * (2 if group == 1 else 1)
+        for group in (1, 2):
+            assert np.array_equal(out[group][0], out[0][0]) and np.array_equal(out[group][2], out[0][2])
+            assert np.array_equal(_bits(out[group][1]), _bits(out[0][1]))
+        T, *_ = orc.prep(V, s)
+        idx = np.unique(np.concatenate([[0, nE - 1, 1184 * 512 - 1, 1184 * 512], np.random.default_rng(3).integers(0, nE, 2000)]))
+        dE = (hi - lo) / (nE - 1)
+        E = lo + idx.astype(np.float64) * dE
+        n_o, m_o, x_o = orc.sweep(T, s, E)
+        assert np.array_equal(out[1][0][0][idx], n_o) and np.array_equal(_bits(out[1][1][0][idx]), _bits(m_o))
+    finally:
+        cb_ctx.set_option(cb_ctx.OPT_CBANK_GROUP, 2)
+        cb_ctx.set_option(cb_ctx.OPT_FORM, 0)

@@ -80,7 +80,8 @@ def test_forced_scan_multi_curve_uniform(oracle, scan_ctx):
         assert np.array_equal(n_g[c], n_o)
 
 
-def test_flagged_energies_fall_back_to_sequential(oracle, scan_ctx):
+@pytest.mark.parametrize("combine", [1, 2], ids=["serial", "prefix"])
+def test_flagged_energies_fall_back_to_sequential(oracle, scan_ctx, combine):
     """Energies sitting on eigenvalues to 1e-14.  For the upper levels a segment boundary (every
     2048 steps = 2 Angstrom here) lies inside the classically allowed region, so the decaying tail is
     a pure cancellation of the segment's two columns: the device flags those energies and the
@@ -90,6 +91,7 @@ def test_flagged_energies_fall_back_to_sequential(oracle, scan_ctx):
     w = W.c1()
     scan_ctx.set_potentials(w["V"], w["s"])
     scan_ctx.set_option(scan_ctx.OPT_SCAN_SEGMENTS, 5)
+    scan_ctx.set_option(scan_ctx.OPT_SCAN_COMBINE, combine)
     F, *_ = oracle.prep(w["V"], w["s"])
     lev, wid, *_ = oracle.solve_levels(F, w["s"], w["E_lo"], w["E_hi"], 1024, 0, 16, 96, 1e-15, 14)
     E = np.sort(np.concatenate([lev, lev - wid, lev + wid, np.linspace(100.0, 38000.0, 50)]))
