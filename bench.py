@@ -507,7 +507,12 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     st = ctx.stats()
     clocks = sampler.window(t_wall0, t_wall1)
     ms_steps = comm.reduce_vec(ms_rank, "max")  # per step: max over ranks
-    ms_res = float(np.sum(ms_steps))            # ... summed over the K steps
+    # Headline (c5, 0.1 .. 0.8 s steps): the K steps summed, as the contract says.  Sub-records (2 .. 30 ms
+    # steps): K x the MEDIAN step -- the GPU boxes show a 2 .. 8 ms interruption every few seconds on any
+    # workload (three of twenty c5 steps carry +1.8 ms), which is 0.2 % of a c5 step and 200 % of a c2 one;
+    # the mean and the per-step list are reported alongside.
+    robust = name != "c5"
+    ms_res = float(np.median(ms_steps)) * len(ms_steps) if robust else float(np.sum(ms_steps))
     steps_rank = float(st.grid_steps)
     steps_all = float(comm.reduce_vec([steps_rank], "sum")[0])
     value = steps_all / (ms_res * 1e-3)
@@ -515,13 +520,14 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
     launches = int(st.kernel_launches)
 
     # ---- timed: end-to-end through the host-buffer C ABI ----
-    for _ in range(2):
-        wl.e2e()
+    for _ in range(2 if name == "c5" else max(2, warmup)):
+        wl.gather(wl.e2e())
     comm.barrier(ctx)
     ctx.stats_reset()
     ms_rank2, res2, _ = timed_run(wl, comm, wl.e2e, steps)
     st2 = ctx.stats()
-    ms_e2e = float(np.sum(comm.reduce_vec(ms_rank2, "max")))
+    ms_steps2 = comm.reduce_vec(ms_rank2, "max")
+    ms_e2e = float(np.median(ms_steps2)) * len(ms_steps2) if robust else float(np.sum(ms_steps2))
     steps2 = float(comm.reduce_vec([float(st2.grid_steps)], "sum")[0])
 
     # ---- c5: seeded-sample oracle check at FULL size (every rank checks its own slice) ----
@@ -548,9 +554,11 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.cfg,
         "time_to_all_levels_ms": ms_res / steps if name in ("c2", "c4") else None,
         "e2e": {"value": steps2 / (ms_e2e * 1e-3), "unit": "steps/s", "ms_per_step": ms_e2e / steps,
-                "h2d_bytes_per_step": int(st2.h2d_bytes // steps), "d2h_bytes_per_step": int(st2.d2h_bytes // steps)},
+                "h2d_bytes_per_step": int(st2.h2d_bytes // steps), "d2h_bytes_per_step": int(st2.d2h_bytes // steps),
+                "ms_steps_max_over_ranks": [round(float(x), 4) for x in ms_steps2], "ms_per_step_mean": float(np.mean(ms_steps2))},
         "gpu_launches": launches,
         "ms_steps_max_over_ranks": [round(float(x), 4) for x in ms_steps],
+        "ms_per_step_mean": float(np.mean(ms_steps)), "step_statistic": "median of the K steps" if robust else "mean of the K steps",
         "roofline": {
             "bound": "fp64", "kernel": KERNELS[name] + (", D form" if form else ""),
             "achieved": flop * sweep_rate / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac,
@@ -652,7 +660,13 @@ def api_task_record(steps: int) -> dict:
             "search": {"n_coarse": int(n_coarse), "refine_points": int(M), "max_rounds": int(rounds), "rel_tol": float(tol)}}
 
 
+SUB_WARMUP = {"c2": 10, "c3": 20, "c4": 5}  # untimed steps of a sub-record: >= ~40 ms of device work after the CPU legs
+
+
 def main() -> None:
+    # the oracle's OpenMP workers must sleep, not spin, once a CPU leg is over: the timed device steps that
+    # follow share the host cores with them (and with the other ranks' launch threads)
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner,
     # compiler chatter of build()) goes to stderr instead.
     global _REAL_STDOUT
@@ -694,22 +708,23 @@ def main() -> None:
     if args.workload == "all":
         subs = {}
         for name in ("c2", "c4", "c3"):
-            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, cpu_s / 2)
+            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), SUB_WARMUP[name], fp64_peak, cpu_s / 2)
             if rec is not None:
                 subs[name] = rec
         # the accurate recurrence on the same workloads (EPS_OPT_FORM = 1): what the drop-in
         # VibwaAlgorithm<FP>::run uses; 5 instead of 4 FP64 operations per step
         for name in ("c5", "c2", "c4", "c3"):
-            rec = measure(name, ctx, comm, sampler, min(args.steps, 5 if name == "c5" else SUB_STEPS), 3, fp64_peak, 0.001 if cpu_s else 0.0, form=1)
+            rec = measure(name, ctx, comm, sampler, min(args.steps, 5 if name == "c5" else SUB_STEPS), SUB_WARMUP.get(name, 3), fp64_peak,
+                          0.001 if cpu_s else 0.0, form=1)
             if rec is not None:
-                keep = ("value", "ms_per_step", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
+                keep = ("value", "ms_per_step", "ms_per_step_mean", "step_statistic", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "roofline", "gpu_launches", "cpu_baseline",
                         "nodes_bit_identical_to_oracle_full_size_sample", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 (line if name == "c5" else subs[name])["accurate_mode"] = {k: rec[k] for k in keep if k in rec}
         # ... and the Cooley level search on the accurate tables: time to all levels without refinement sweeps
         for name in ("c2", "c4"):
-            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), 3, fp64_peak, 0.0, form=1, cooley=True)
+            rec = measure(name, ctx, comm, sampler, min(args.steps, SUB_STEPS), SUB_WARMUP[name], fp64_peak, 0.0, form=1, cooley=True)
             if rec is not None:
-                keep = ("value", "ms_per_step", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "gpu_launches", "level_search",
+                keep = ("value", "ms_per_step", "ms_per_step_mean", "step_statistic", "ms_steps_max_over_ranks", "time_to_all_levels_ms", "e2e", "gpu_launches", "level_search",
                         "max_rel_diff_vs_ksection", "levels_found", "max_rel_err_vs_analytic_rank0", "steps")
                 subs[name]["cooley_mode"] = {k: rec[k] for k in keep if k in rec}
         if line is not None:
