@@ -543,6 +543,14 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         n_cpu, _, _ = orc1.sweep(F, wl.s, E, tails=False)
         same = bool(np.array_equal(n_cpu, res2[0][0][idx]))
         c5_same = bool(comm.reduce_vec([0.0 if same else 1.0], "sum")[0] == 0.0)
+        # cross-run determinism: the sum of ALL 2^24 node counts (the ranks' slices are disjoint, so the
+        # figure must be the same at 1, 2, 4 and 8 GPUs); exact in float64 (< 2^53)
+        try:
+            local_sum = float(np.sum(res2[0][0], dtype=np.uint64))
+        except Exception:  # noqa: BLE001 - a checksum must never break the run (the reduction below is collective)
+            local_sum = float("nan")
+        c5_sum = comm.reduce_vec([local_sum], "sum")[0]
+        c5_sum = int(c5_sum) if c5_sum == c5_sum else None
     if comm.rank != 0:
         return None
 
@@ -574,6 +582,14 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         },
         "clocks": clocks, "recurrence": FORM_NAME[form],
     }
+    if name in ("c2", "c4") and digest is not None:  # xor of the bits of every gathered level (NaN = absent level included)
+        try:
+            x = np.uint64(0)
+            for part in digest:
+                x ^= np.bitwise_xor.reduce(np.ascontiguousarray(part, dtype=np.float64).view(np.uint64).ravel())
+            rec["checksum"] = {"xor_of_level_bits": f"{int(x):016x}", "levels": int(sum(np.asarray(p).size for p in digest))}
+        except Exception as e:  # noqa: BLE001
+            rec["checksum"] = {"error": f"{type(e).__name__}: {e}"}
     if name == "c2":
         exact = W.morse_levels(W.H2["De"], W.H2["a"], W.H2["m0"], W.H2["m1"])
         rec["levels_found"] = int(np.sum(np.isfinite(digest[0][0])))
@@ -582,6 +598,7 @@ def _measure(name, ctx, comm, sampler, steps, warmup, fp64_peak, cpu_seconds, fo
         rec["scan"] = {"launches": ctx.counter(ctx.CNT_SCAN_LAUNCHES), "flagged": ctx.counter(ctx.CNT_SCAN_FLAGGED)}
     if name == "c5":
         rec["nodes_bit_identical_to_oracle_full_size_sample"] = c5_same
+        rec["checksum"] = {"sum_of_node_counts_all_energies": c5_sum}
         rec["full_size_sample"] = f"{C5['check_sample']} seeded energies of every rank's slice of the 2^24 (incl. both slice ends)"
     if cooley:
         rec["level_search"] = ("Cooley outward/inward matching iteration after the coarse sweep (EPS_SOLVE_COOLEY), one CTA per "
