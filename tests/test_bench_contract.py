@@ -89,3 +89,29 @@ def test_reference_arm_line_live():
     committed = ROOT / "profiles" / "r2_bench_n1.json"
     if committed.exists():
         assert json.loads(committed.read_text())["config"] == d["config"]
+
+
+def test_traffic_figures_belong_to_the_committed_kernel_sources():
+    """profiles/traffic.json (ncu DRAM bytes per workload) carries the digest of the csrc it was captured
+    on; bench.py reports a figure from other sources as stale (traffic: null).  The committed file must
+    match the committed sources, and the committed headline line must carry its c5 figure."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    t = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    assert {"c2", "c3", "c4", "c5", "c2_dform", "c3_dform", "c4_dform", "c5_dform"} <= t.keys()
+    assert {v["csrc_digest"] for v in t.values()} == {bench.csrc_digest()}
+    line = json.loads((ROOT / "profiles" / "r2_bench_n1.json").read_text())
+    assert line["roofline"]["traffic"] == t["c5"]["dram_bytes_per_launch"]
+    # the constant-bank sweep's carried state stays in L2: HBM traffic within 10x of the algorithmic bytes
+    assert line["roofline"]["traffic"] < 10 * line["roofline"]["algorithmic_bytes_per_launch"]
+
+
+def test_cross_run_checksums_agree_across_gpu_counts():
+    """Sum of all 2^24 node counts of c5 and xor of the level bits of c4: the same at 1, 2, 4 and 8 GPUs."""
+    sums, xors = set(), set()
+    for p in LINES:
+        d = json.loads(p.read_text())
+        sums.add(d["checksum"]["sum_of_node_counts_all_energies"])
+        xors.add(d["sub_records"]["c4"]["checksum"]["xor_of_level_bits"])
+    assert len(LINES) >= 4 and len(sums) == 1 and len(xors) == 1
